@@ -1,0 +1,441 @@
+#!/usr/bin/env python
+"""Benchmark of the IDG gridder / degridder hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (BASELINE.json configs[1]/[2]): the reference's default performance shape
+(app/CUDA/util.cpp:177-183): 50 stations x 20 timeslots -> 24,500 subgrids of 32x32
+pixels x 4 polarisations, 128 timesteps x 16 channels each = 50.176 MVis per step,
+synthetic inputs from the reference's generators (app/common/init.cpp) evaluated on
+the device.  A step is one gridder pass over all subgrids; the degridder is timed the
+same way right after and reported under "degridder".  With N GPUs every rank runs the
+full per-GPU workload on its own shard (weak scaling, no collective on the data path).
+
+One JSON line on stdout (rank 0).  `value` = whole-job gridder MVis/s with inputs
+resident in HBM; `e2e` = the same metric through the host-pointer C ABI
+(idgb200_c_run_gridder_ex) with pinned host buffers, copies inside the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+DEFAULT_SHAPE = dict(nr_stations=50, nr_timeslots=20, nr_timesteps=128, nr_channels=16,
+                     subgrid_size=32, grid_size=1024, image_size=0.01)
+SM_FP32_LANES = 128   # FP32 FMA lanes per SM (B200)
+SM_XU_LANES = 16      # MUFU lanes per SM
+
+
+# ----------------------------------------------------------------- shared helpers
+def shape_counts(shape: dict) -> dict:
+    nbl = shape["nr_stations"] * (shape["nr_stations"] - 1) // 2
+    S = nbl * shape["nr_timeslots"]
+    tt = S * shape["nr_timesteps"]
+    return dict(nr_subgrids=S, total_timesteps=tt, mvis=1e-6 * tt * shape["nr_channels"])
+
+
+def rank_shape(overrides: dict, rank: int, world: int) -> dict:
+    """Per-rank workload under weak scaling: the full shape on every rank, with a
+    rank-specific seed so the shards differ like different baselines would."""
+    shape = dict(DEFAULT_SHAPE)
+    shape.update(overrides)
+    shape.update(shape_counts(shape))
+    shape["seed"] = rank
+    shape["rank"], shape["world"] = rank, world
+    return shape
+
+
+def reduce_max_time(seconds: float, device) -> float:
+    """Max over ranks of a locally measured duration."""
+    import torch
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return seconds
+    t = torch.tensor([seconds], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def measured_peaks() -> dict:
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return {}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (profiling recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.proc = None
+        self.lines: list[str] = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}",
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        hi = [x for x in sm if x >= 0.5 * max(sm)]  # under-load samples
+        return {"sm_mhz": statistics.median(hi), "sm_max_mhz": max(mx), "power_w_max": max(pw),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# -------------------------------------------------------------------- CPU arm
+def load_cpu_checker():
+    """(lib, kind): the reference's own CPU code when oracle/_ref was built, else the
+    oracle restatement ("port").  Only used as the reported CPU baseline / checker."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib
+
+    ref = oracle_lib.reference()
+    if ref is not None:
+        return ref, "reference", oracle_lib
+    return oracle_lib.oracle(), "port", oracle_lib
+
+
+def cpu_problem(oracle_lib, shape: dict, nr_subgrids: int):
+    """The first nr_subgrids subgrids of the workload, made by the checker's own
+    restatement of app/common/init.cpp (host rand()), for the CPU arm."""
+    lib, _, _ = load_cpu_checker()
+    nbl_needed = max(1, -(-nr_subgrids // shape["nr_timeslots"]))
+    # smallest station count whose baseline list covers the sample
+    st = 2
+    while st * (st - 1) // 2 < nbl_needed:
+        st += 1
+    p = lib.make_problem(nr_stations=st, nr_timeslots=shape["nr_timeslots"],
+                         nr_timesteps=shape["nr_timesteps"], nr_channels=shape["nr_channels"],
+                         subgrid_size=shape["subgrid_size"], grid_size=shape["grid_size"])
+    S = min(nr_subgrids, p.nr_subgrids)
+    T = shape["nr_timesteps"]
+    return oracle_lib.Problem(
+        grid_size=p.grid_size, subgrid_size=p.subgrid_size, image_size=p.image_size,
+        w_step=p.w_step, nr_channels=p.nr_channels, nr_stations=p.nr_stations,
+        uvw=np.ascontiguousarray(p.uvw[:S * T]), wavenumbers=p.wavenumbers,
+        visibilities=np.ascontiguousarray(p.visibilities[:S * T]), spheroidal=p.spheroidal,
+        aterms=p.aterms, metadata=np.ascontiguousarray(p.metadata[:S]),
+        subgrids=np.ascontiguousarray(p.subgrids[:S]))
+
+
+def time_cpu(lib, prob, which: str) -> float:
+    t0 = time.perf_counter()
+    (lib.gridder if which == "gridder" else lib.degridder)(prob)
+    return time.perf_counter() - t0
+
+
+def run_reference_arm(args) -> None:
+    """--impl reference: the reference's CPU gridder (oracle/_ref when it compiled,
+    else the port) on all host threads, each step a bounded sample of the workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    lib, kind, oracle_lib = load_cpu_checker()
+    cores = lib.max_threads()
+    lib.set_threads(cores)
+    shape = rank_shape({}, 0, 1)
+    # calibrate, then size one step to ~3 s
+    probe = cpu_problem(oracle_lib, shape, max(cores, 4))
+    dt = time_cpu(lib, probe, "gridder")
+    per_subgrid = dt / probe.nr_subgrids
+    n = int(min(shape["nr_subgrids"], max(cores, 3.0 / per_subgrid)))
+    prob = cpu_problem(oracle_lib, shape, n)
+    n = prob.nr_subgrids
+    mvis_step = 1e-6 * n * shape["nr_timesteps"] * shape["nr_channels"]
+    for _ in range(args.warmup):
+        time_cpu(lib, prob, "gridder")
+    t = [time_cpu(lib, prob, "gridder") for _ in range(args.steps)]
+    td = [time_cpu(lib, prob, "degridder") for _ in range(max(1, min(args.steps, 3)))]
+    sec = sum(t) / len(t)
+    value = mvis_step / sec
+    sample = (f"first {n} of {shape['nr_subgrids']} subgrids per step, same shape "
+              f"(N=32, 128 timesteps x 16 channels), all {cores} host threads (OpenMP)")
+    out = {
+        "impl": "reference", "metric": "gridder_mvis_per_s", "value": value, "unit": "MVis/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(shape, args.gpus),
+        "cpu_baseline": {"value": value, "unit": "MVis/s", "cores": cores, "kind": kind,
+                         "sample": sample},
+        "degridder": {"value": mvis_step / (sum(td) / len(td)), "unit": "MVis/s"},
+        "e2e": {"value": value, "unit": "MVis/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out), flush=True)
+
+
+def workload_config(shape: dict, n_gpus: int) -> dict:
+    return {
+        "workload": "ska-sdp-idg-bench default perf shape (app/CUDA/util.cpp:177-183): "
+                    "50 stations x 20 timeslots = 24500 subgrids/GPU, subgrid 32, 4 pols, "
+                    "128 timesteps x 16 channels, grid 1024, image_size 0.01, w_step 0",
+        "subgrids_per_gpu": shape["nr_subgrids"], "mvis_per_step_per_gpu": shape["mvis"],
+        "sharding": f"subgrid list, {n_gpus} independent shard(s), no collective",
+        "l2": "inputs per step (1.6 GB visibilities + 0.8 GB subgrids) exceed the 126 MB L2; no flush",
+    }
+
+
+# --------------------------------------------------------------------- GPU arm
+def run_ours(args) -> None:
+    import torch
+    import torch.distributed as dist
+
+    import ska_sdp_idg_bench_b200 as idg
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device - the product has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    shape = rank_shape({}, rank, world)
+    sincos = {"fast": idg.SINCOS_FAST, "reduced": idg.SINCOS_REDUCED,
+              "accurate": idg.SINCOS_ACCURATE}[args.sincos]
+    prob = idg.init_problem_device(
+        nr_stations=shape["nr_stations"], nr_timeslots=shape["nr_timeslots"],
+        nr_timesteps=shape["nr_timesteps"], nr_channels=shape["nr_channels"],
+        subgrid_size=shape["subgrid_size"], grid_size=shape["grid_size"],
+        image_size=shape["image_size"], seed=shape["seed"], device=dev)
+    S, tt, C_, N = prob["nr_subgrids"], prob["total_timesteps"], prob["nr_channels"], prob["subgrid_size"]
+    scal = (S, prob["grid_size"], N, prob["image_size"], 0.0, C_, prob["nr_stations"], tt)
+    tens = (prob["uvw"], prob["wavenumbers"], prob["visibilities"], prob["spheroidal"],
+            prob["aterms"], prob["metadata"], prob["subgrids"])
+    sub_in = prob["subgrids"].clone()  # degridder input (the gridder overwrites subgrids)
+    vis_out = torch.empty_like(prob["visibilities"])
+
+    def step_gridder():
+        idg.gridder(*scal, *tens, sincos=sincos, variant=args.variant)
+
+    def step_degridder():
+        idg.degridder(*scal, prob["uvw"], prob["wavenumbers"], vis_out, prob["spheroidal"],
+                      prob["aterms"], prob["metadata"], sub_in, sincos=sincos,
+                      variant=args.degridder_variant)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(step, steps, warmup):
+        """K steps between CUDA events on the launching (torch current) stream,
+        barrier + synchronize on both sides; returns (max-over-ranks seconds, launches)."""
+        for _ in range(warmup):
+            step()
+        barrier()
+        l0 = idg.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            step()
+        e1.record()
+        barrier()
+        sec = e0.elapsed_time(e1) * 1e-3
+        return reduce_max_time(sec, dev), idg.launch_count() - l0
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    sec_g, launches_g = timed(step_gridder, args.steps, args.warmup)
+    sec_d, launches_d = timed(step_degridder, args.steps, args.warmup)
+    clocks = sampler.stop() if rank == 0 else {}
+
+    # ---- e2e through the host-pointer C ABI, pinned host buffers
+    e2e = None
+    if not args.no_e2e:
+        host = {}
+        for k in ("uvw", "wavenumbers", "visibilities", "spheroidal", "aterms", "metadata", "subgrids"):
+            t = prob[k]
+            h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+            h.copy_(t)
+            host[k] = h
+        torch.cuda.synchronize()
+        npy = {k: v.numpy() for k, v in host.items()}
+        meta_np = np.ascontiguousarray(npy["metadata"]).view(idg.METADATA_DTYPE).reshape(-1)
+        a = (S, prob["grid_size"], N, prob["image_size"], 0.0, C_, prob["nr_stations"],
+             npy["uvw"], npy["wavenumbers"], npy["visibilities"], npy["spheroidal"],
+             npy["aterms"], meta_np, npy["subgrids"])
+
+        def e2e_step():
+            idg.c_run_gridder(*a, sincos=sincos, variant=args.variant)
+
+        e_steps = max(1, min(args.steps, 5))
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e_steps):
+            e2e_step()          # returns after the D2H of the result completed
+        torch.cuda.synchronize()
+        sec_e = reduce_max_time(time.perf_counter() - t0, dev)
+        h2d = sum(npy[k].nbytes for k in ("uvw", "wavenumbers", "visibilities", "spheroidal",
+                                          "aterms", "metadata"))
+        e2e = {"value": world * shape["mvis"] * e_steps / sec_e, "unit": "MVis/s",
+               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(npy["subgrids"].nbytes),
+               "ms_per_step": sec_e / e_steps * 1e3, "steps": e_steps,
+               "api": "idgb200_c_run_gridder_ex (host pointers, pinned; chunked H2D/kernel/D2H on 3 streams)"}
+
+    # ---- CPU baseline + parity sample, rank 0 at N=1 only
+    cpu_baseline, parity = None, None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        lib, kind, oracle_lib = load_cpu_checker()
+        cores = lib.max_threads()
+        lib.set_threads(cores)
+        n = max(64, 4 * cores)
+        # the same workload: copy the first n subgrids of the device-generated inputs
+        T = shape["nr_timesteps"]
+        cp = oracle_lib.Problem(
+            grid_size=prob["grid_size"], subgrid_size=N, image_size=prob["image_size"], w_step=0.0,
+            nr_channels=C_, nr_stations=prob["nr_stations"],
+            uvw=prob["uvw"][:n * T].cpu().numpy(), wavenumbers=prob["wavenumbers"].cpu().numpy(),
+            visibilities=prob["visibilities"][:n * T].cpu().numpy(),
+            spheroidal=prob["spheroidal"].cpu().numpy(), aterms=prob["aterms"].cpu().numpy(),
+            metadata=np.ascontiguousarray(prob["metadata"][:n].cpu().numpy()).view(
+                oracle_lib.METADATA_DTYPE).reshape(-1),
+            subgrids=sub_in[:n].cpu().numpy())
+        dt = time_cpu(lib, cp, "gridder")          # also a warm-up
+        reps = int(max(1, min(20, 12.0 / max(dt, 1e-3))))
+        tg = [time_cpu(lib, cp, "gridder") for _ in range(reps)]
+        td = [time_cpu(lib, cp, "degridder") for _ in range(max(1, reps // 2))]
+        mv = 1e-6 * n * T * C_
+        cpu_baseline = {
+            "value": mv / (sum(tg) / len(tg)), "unit": "MVis/s", "cores": cores, "kind": kind,
+            "sample": f"first {n} subgrids of the same device-generated workload, {reps} repeats, "
+                      f"OpenMP over subgrids on all {cores} host threads",
+            "degridder_value": mv / (sum(td) / len(td)),
+        }
+        # parity of the bench-size run on that sample (per-pol max|d|/max|ref|)
+        ref_g = lib.gridder(cp)
+        got_g = prob["subgrids"][:n].cpu().numpy()
+        ref_d = lib.degridder(cp)
+        got_d = vis_out[:n * T].cpu().numpy()
+        parity = {
+            "sample_subgrids": n, "sincos": args.sincos,
+            "gridder_max_rel_per_pol": [float(np.abs(got_g[:, p] - ref_g[:, p]).max() /
+                                              np.abs(ref_g[:, p]).max()) for p in range(4)],
+            "degridder_max_rel_per_pol": [float(np.abs(got_d[..., p] - ref_d[..., p]).max() /
+                                                np.abs(ref_d[..., p]).max()) for p in range(4)],
+        }
+
+    if rank == 0:
+        peaks = measured_peaks()
+        sms = idg.sm_count()
+        f_max = float(peaks.get("sm_max_mhz") or clocks.get("sm_max_mhz") or 1965.0)
+        p_fp32 = sms * SM_FP32_LANES * 2 * f_max * 1e6 * 1e-12       # TFLOP/s
+        p_xu = sms * SM_XU_LANES * f_max * 1e6                       # MUFU/s
+        flops = idg.flops_gridder(C_, tt, S, N)
+        nbytes = idg.bytes_gridder(C_, tt, S, N)
+        hbm_peak = float(peaks.get("hbm_gbs") or 6650.0)
+
+        def roof(sec, steps):
+            t = sec / steps
+            tf = flops / t * 1e-12
+            r = {"bound": "fp32", "achieved": tf, "peak": p_fp32, "unit": "TFLOP/s",
+                 "frac": tf / p_fp32, "traffic": None,
+                 "peak_source": f"{sms} SMs x 128 FP32 lanes x 2 x {f_max:.0f} MHz (sm_max_mhz of "
+                                "MEASURED_PEAKS.json; the file holds no FP32 figure)",
+                 "kernel_ms": t * 1e3,
+                 "sfu_frac": 2.0 * N * N * (tt * C_) / t / p_xu,
+                 "hbm": {"achieved": nbytes / t * 1e-9, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": nbytes / t * 1e-9 / hbm_peak,
+                         "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks.get("hbm_gbs")
+                         else "fallback 6650"}}
+            if clocks.get("sm_mhz"):
+                r["frac_at_measured_clock"] = tf / (p_fp32 * clocks["sm_mhz"] / f_max)
+            return r
+
+        total_mvis = world * shape["mvis"]
+        out = {
+            "metric": "gridder_mvis_per_s", "value": total_mvis * args.steps / sec_g,
+            "unit": "MVis/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": sec_g / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": dict(workload_config(shape, world), sincos=args.sincos,
+                           gridder_variant=args.variant, degridder_variant=args.degridder_variant),
+            "tflops": world * flops * args.steps / sec_g * 1e-12,
+            "roofline": roof(sec_g, args.steps),
+            "degridder": {"value": total_mvis * args.steps / sec_d, "unit": "MVis/s",
+                          "ms_per_step": sec_d / args.steps * 1e3,
+                          "tflops": world * flops * args.steps / sec_d * 1e-12,
+                          "roofline": roof(sec_d, args.steps)},
+            "cpu_baseline": cpu_baseline, "parity": parity, "e2e": e2e,
+            "gpu_launches": int(launches_g), "degridder_gpu_launches": int(launches_d),
+            "clocks": clocks, "device": idg.device_name(),
+        }
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--sincos", default="fast", choices=["fast", "reduced", "accurate"])
+    ap.add_argument("--variant", type=int, default=0)
+    ap.add_argument("--degridder-variant", type=int, default=0)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

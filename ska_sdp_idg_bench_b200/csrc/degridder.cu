@@ -1,0 +1,222 @@
+// IDG degridder for B200 (sm_100a): the transpose of the gridder.
+//
+//   P'[y][x]       = A1 * (sph[y][x] * subgrid[s][.][y][x]) * A2^H
+//   vis[t][c][pol] = sum_{y,x} P'[y][x][pol] * e^{i phase},
+//   phase          = phase_index(t,x,y) * wavenumber[c] - phase_offset(x,y)
+//
+// Behaviour follows cpu::kernel_degridder_reference
+// (app/CPU/kernels/degridder_reference.cpp:6-129); the design is new:
+//
+//  * one thread block per subgrid.  A prologue applies taper and A-terms once
+//    per pixel and leaves P' (in the duplicated (re,re)(im,im) layout FFMA2
+//    wants) plus (l, m, n, phase_offset) in shared memory;
+//  * the unit of work is a task = (timestep, block of V channels).  The lanes of
+//    a warp are split into 32/PS task slots x PS pixel groups: a lane sums its
+//    task over every PS-th pixel with the same packed inner product as the
+//    gridder (8 FFMA2 + 1 FFMA + 1 FMUL + 2 MUFU per pixel x channel), all lanes of
+//    a slot read the same shared-memory words (one wavefront per load), and the
+//    PS partial sums are combined with __shfl_xor_sync butterflies.  PS is chosen
+//    per subgrid (>= 4, up to 32 = one warp per task) so that short subgrids
+//    still fill the block.  No reference kernel reduces this way: they all loop
+//    one thread over all pixels of a visibility (degridder_v6.cu:88-116);
+//  * every visibility of the subgrid's time range is written exactly once, by the
+//    lanes that own it after the butterfly (no read-modify-write of global
+//    memory as in degridder_v4.cu:155-161).
+#include "common.cuh"
+#include "kernels.h"
+
+namespace idgb200 {
+
+namespace {
+
+constexpr int TILE = 1024;  // pixels resident in shared memory at a time (80 KB)
+
+// SCHEME 0: FFMA2 rotated accumulators (A += (Pr,Pr)*ph, B += (Pi,Pi)*ph)
+// SCHEME 1: scalar FFMA baseline
+template <int NT, int V, int SCHEME, int MODE>
+__global__ void __launch_bounds__(NT, 2)
+degridder_kernel(const KernelArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float4 *s_pix = reinterpret_cast<float4 *>(smem_raw);   // [4][TILE] (Pr,Pr,Pi,Pi)
+  float4 *s_lmno = s_pix + NR_POL * TILE;                  // [TILE]    (l,m,n,phase_offset)
+
+  const int N = a.subgrid_size;
+  const int C = a.nr_channels;
+  const int npix = N * N;
+  const int s = a.subgrid_offset + blockIdx.x;
+  const int tid = threadIdx.x;
+  const SubgridCtx ctx = load_ctx(a, s);
+  const int nt = ctx.nr_timesteps;
+
+  const int ncb = (C + V - 1) / V;   // channel blocks per timestep
+  const int ntasks = nt * ncb;
+  if (ntasks == 0) return;
+
+  // pixel split: smallest power of two >= NT/ntasks, at least 4, at most 32
+  int ps_log2 = 2;
+  while ((ntasks << ps_log2) < NT && ps_log2 < 5) ps_log2++;
+  const int PS = 1 << ps_log2;
+  const int slots = NT >> ps_log2;
+  const int slot = tid >> ps_log2;
+  const int pg = tid & (PS - 1);
+  const int nrounds = (ntasks + slots - 1) / slots;
+  const int ntiles = (npix + TILE - 1) / TILE;
+
+  const size_t plane = (size_t)npix;
+  const size_t at1 = ((size_t)ctx.aterm_index * a.nr_stations + ctx.station1) * plane;
+  const size_t at2 = ((size_t)ctx.aterm_index * a.nr_stations + ctx.station2) * plane;
+  const float2 *sub = a.subgrids + (size_t)s * NR_POL * plane;
+  const float *g_uvw = reinterpret_cast<const float *>(a.uvw) + (size_t)ctx.time_offset * 3;
+  float4 *g_vis = reinterpret_cast<float4 *>(const_cast<float2 *>(a.visibilities)) +
+                  (size_t)ctx.time_offset * C * 2;
+
+  // degridder_reference.cpp:38-74 for the pixels [tile0, tile0 + tile_n)
+  auto prologue = [&](int tile0, int tile_n) {
+    for (int i = tid; i < tile_n; i += NT) {
+      const int q = tile0 + i;
+      const int y = q / N, x = q - y * N;
+      const float sph = __ldg(&a.spheroidal[q]);
+      float2 px[NR_POL];
+#pragma unroll
+      for (int p = 0; p < NR_POL; p++) {
+        const float2 v = __ldg(&sub[p * plane + q]);
+        px[p] = make_float2(__fmul_rn(sph, v.x), __fmul_rn(sph, v.y));
+      }
+      float2 a1[4], a2[4];
+      load_jones(a.aterms, (at1 + q) * NR_POL, a1);
+      load_jones(a.aterms, (at2 + q) * NR_POL, a2);
+      apply_aterm_degridder(px, a1, a2);
+#pragma unroll
+      for (int p = 0; p < NR_POL; p++)
+        s_pix[p * TILE + i] = make_float4(px[p].x, px[p].x, px[p].y, px[p].y);
+      const float l = compute_l(x, N, a.image_size);
+      const float m = compute_l(y, N, a.image_size);
+      const float n = compute_n(l, m);
+      // the CPU binary leaves the w term unfused here (oracle/idg_oracle.c)
+      const float off = __fadd_rn(__fmaf_rn(ctx.u_offset, l, __fmul_rn(ctx.v_offset, m)),
+                                  __fmul_rn(ctx.w_offset, n));
+      s_lmno[i] = make_float4(l, m, n, off);
+    }
+  };
+
+  for (int round = 0; round < nrounds; round++) {
+    const int task = round * slots + slot;
+    const bool live = task < ntasks;
+    const int tq = live ? task : 0;
+    const int t = tq / ncb;
+    const int c0 = (tq - t * ncb) * V;
+    const float u = g_uvw[t * 3 + 0], v = g_uvw[t * 3 + 1], w = g_uvw[t * 3 + 2];
+    float wn[V];
+#pragma unroll
+    for (int c = 0; c < V; c++) wn[c] = (c0 + c < C) ? __ldg(&a.wavenumbers[c0 + c]) : 0.f;
+
+    float2 accA[V][NR_POL], accB[V][NR_POL];
+#pragma unroll
+    for (int c = 0; c < V; c++)
+#pragma unroll
+      for (int p = 0; p < NR_POL; p++) {
+        accA[c][p] = make_float2(0.f, 0.f);
+        accB[c][p] = make_float2(0.f, 0.f);
+      }
+
+    for (int tile = 0; tile < ntiles; tile++) {
+      const int tile0 = tile * TILE;
+      const int tile_n = min(TILE, npix - tile0);
+      if (ntiles > 1 || round == 0) {
+        __syncthreads();  // previous tile fully consumed
+        prologue(tile0, tile_n);
+        __syncthreads();
+      }
+
+      for (int i = pg; i < tile_n; i += PS) {
+        const float4 g = s_lmno[i];
+        const float4 p0 = s_pix[0 * TILE + i], p1 = s_pix[1 * TILE + i];
+        const float4 p2 = s_pix[2 * TILE + i], p3 = s_pix[3 * TILE + i];
+        // degridder_reference.cpp:106 as the CPU binary evaluates it
+        const float idx = __fadd_rn(__fmaf_rn(u, g.x, __fmul_rn(v, g.y)), __fmul_rn(w, g.z));
+#pragma unroll
+        for (int c = 0; c < V; c++) {
+          const float2 ph = phasor<MODE>(__fmaf_rn(idx, wn[c], -g.w));  // :112
+          if (SCHEME == 0) {
+            accA[c][0] = ffma2(make_float2(p0.x, p0.y), ph, accA[c][0]);
+            accB[c][0] = ffma2(make_float2(p0.z, p0.w), ph, accB[c][0]);
+            accA[c][1] = ffma2(make_float2(p1.x, p1.y), ph, accA[c][1]);
+            accB[c][1] = ffma2(make_float2(p1.z, p1.w), ph, accB[c][1]);
+            accA[c][2] = ffma2(make_float2(p2.x, p2.y), ph, accA[c][2]);
+            accB[c][2] = ffma2(make_float2(p2.z, p2.w), ph, accB[c][2]);
+            accA[c][3] = ffma2(make_float2(p3.x, p3.y), ph, accA[c][3]);
+            accB[c][3] = ffma2(make_float2(p3.z, p3.w), ph, accB[c][3]);
+          } else {
+            const float pr[4] = {p0.x, p1.x, p2.x, p3.x};
+            const float pi[4] = {p0.z, p1.z, p2.z, p3.z};
+#pragma unroll
+            for (int p = 0; p < NR_POL; p++) {
+              accA[c][p].x = fmaf(pr[p], ph.x, accA[c][p].x);
+              accA[c][p].x = fmaf(-pi[p], ph.y, accA[c][p].x);
+              accA[c][p].y = fmaf(pr[p], ph.y, accA[c][p].y);
+              accA[c][p].y = fmaf(pi[p], ph.x, accA[c][p].y);
+            }
+          }
+        }
+      }
+    }
+
+    // recombine, butterfly over the PS pixel groups, store
+#pragma unroll
+    for (int c = 0; c < V; c++) {
+      float2 sum[NR_POL];
+#pragma unroll
+      for (int p = 0; p < NR_POL; p++) {
+        if (SCHEME == 0)
+          sum[p] = make_float2(accA[c][p].x - accB[c][p].y, accA[c][p].y + accB[c][p].x);
+        else
+          sum[p] = accA[c][p];
+        for (int o = PS >> 1; o > 0; o >>= 1) {
+          sum[p].x += __shfl_xor_sync(0xffffffffu, sum[p].x, o);
+          sum[p].y += __shfl_xor_sync(0xffffffffu, sum[p].y, o);
+        }
+      }
+      // after the butterfly every lane of the slot holds the totals; lane pg
+      // stores the channels with c == pg (mod PS), so the stores are spread
+      // over the slot's lanes
+      if (live && pg == (c & (PS - 1)) && c0 + c < C) {
+        float4 *dst = g_vis + ((size_t)t * C + (c0 + c)) * 2;
+        dst[0] = make_float4(sum[0].x, sum[0].y, sum[1].x, sum[1].y);
+        dst[1] = make_float4(sum[2].x, sum[2].y, sum[3].x, sum[3].y);
+      }
+    }
+  }
+}
+
+template <int NT, int V, int SCHEME>
+cudaError_t launch_t(const KernelArgs &a, int mode, cudaStream_t stream) {
+  const size_t smem = (size_t)(NR_POL + 1) * TILE * sizeof(float4);
+  void (*k)(const KernelArgs) = nullptr;
+  switch (mode) {
+    case IDGB200_SINCOS_FAST: k = degridder_kernel<NT, V, SCHEME, IDGB200_SINCOS_FAST>; break;
+    case IDGB200_SINCOS_REDUCED: k = degridder_kernel<NT, V, SCHEME, IDGB200_SINCOS_REDUCED>; break;
+    case IDGB200_SINCOS_ACCURATE: k = degridder_kernel<NT, V, SCHEME, IDGB200_SINCOS_ACCURATE>; break;
+    default: return cudaErrorInvalidValue;
+  }
+  cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  k<<<dim3((unsigned)a.nr_subgrids), dim3(NT), smem, stream>>>(a);
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+// variant: 0 default (FFMA2, 256 threads, 4 channels per task)
+//          1 scalar-FFMA baseline (256 threads, 4 channels per task)
+//          2 FFMA2, 8 channels per task
+cudaError_t launch_degridder(const KernelArgs &a, int sincos_mode, int variant, cudaStream_t stream) {
+  if (a.nr_subgrids == 0) return cudaSuccess;
+  switch (variant) {
+    case 0: return launch_t<256, 4, 0>(a, sincos_mode, stream);
+    case 1: return launch_t<256, 4, 1>(a, sincos_mode, stream);
+    case 2: return launch_t<256, 8, 0>(a, sincos_mode, stream);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+}  // namespace idgb200

@@ -1,0 +1,13 @@
+// Internal launcher interface between the kernels (*.cu) and the C ABI (capi.cu).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "common.cuh"
+
+namespace idgb200 {
+
+// sincos_mode: IDGB200_SINCOS_*; variant: see the launcher definitions.
+cudaError_t launch_gridder(const KernelArgs &a, int sincos_mode, int variant, cudaStream_t stream);
+cudaError_t launch_degridder(const KernelArgs &a, int sincos_mode, int variant, cudaStream_t stream);
+
+}  // namespace idgb200
