@@ -230,6 +230,13 @@ int host_run(bool gridding, const idgb200_params *p, int64_t total_timesteps, in
                           (size_t)(r1 - r0) * C * NR_POL * sizeof(float2), cudaMemcpyHostToDevice, s_in);
     return e;
   };
+  int64_t down_hi = 0;
+  bool unordered = false;
+  auto download = [&](int64_t r0, int64_t r1) -> cudaError_t {
+    if (r1 <= r0) return cudaSuccess;
+    return cudaMemcpyAsync(vis + (size_t)r0 * C * NR_POL, d_vis + (size_t)r0 * C * NR_POL,
+                           (size_t)(r1 - r0) * C * NR_POL * sizeof(float2), cudaMemcpyDeviceToHost, s_out);
+  };
   for (int i = 0; i < nchunks && !status; i++) {
     const int s0 = i * chunk, s1 = (s0 + chunk < S) ? s0 + chunk : S;
     int64_t t0, t1;
@@ -268,10 +275,21 @@ int host_run(bool gridding, const idgb200_params *p, int64_t total_timesteps, in
       e = cudaMemcpyAsync(sg + (size_t)s0 * NR_POL * npix, d_sg + (size_t)s0 * NR_POL * npix,
                           (size_t)(s1 - s0) * NR_POL * npix * sizeof(float2), cudaMemcpyDeviceToHost, s_out);
     } else if (t1 > t0) {
-      e = cudaMemcpyAsync(vis + (size_t)t0 * C * NR_POL, d_vis + (size_t)t0 * C * NR_POL,
-                          (size_t)(t1 - t0) * C * NR_POL * sizeof(float2), cudaMemcpyDeviceToHost, s_out);
+      // time-ordered metadata: rows [down_hi, t1) are final once this chunk is done
+      // (including never-covered rows, which the memset left at zero); otherwise
+      // everything is fetched in one go after the last kernel
+      if (!unordered && t0 >= down_hi) {
+        e = download(down_hi, t1);
+        down_hi = t1;
+      } else {
+        unordered = true;
+      }
     }
     if (e != cudaSuccess) { status = (int)e; break; }
+  }
+  if (!gridding && !status) {  // the whole visibility array is (re)written exactly once
+    cudaError_t e = unordered ? download(0, total_timesteps) : download(down_hi, total_timesteps);
+    if (e != cudaSuccess) status = (int)e;
   }
   cudaError_t e1 = cudaStreamSynchronize(s_in);
   cudaError_t e2 = cudaStreamSynchronize(s_k);

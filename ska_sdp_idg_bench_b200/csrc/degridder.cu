@@ -31,8 +31,10 @@ namespace {
 
 constexpr int TILE = 1024;  // pixels resident in shared memory at a time (80 KB)
 
-// SCHEME 0: FFMA2 rotated accumulators (A += (Pr,Pr)*ph, B += (Pi,Pi)*ph)
+// SCHEME 0: FFMA2 rotated accumulators (A += (Pr,Pr)*ph, B += (Pi,Pi)*ph), software
+//           pipelined (default)
 // SCHEME 1: scalar FFMA baseline
+// SCHEME 2: FFMA2 without the software pipeline (A/B)
 template <int NT, int V, int SCHEME, int MODE>
 __global__ void __launch_bounds__(NT, 2)
 degridder_kernel(const KernelArgs a) {
@@ -128,33 +130,67 @@ degridder_kernel(const KernelArgs a) {
         __syncthreads();
       }
 
-      for (int i = pg; i < tile_n; i += PS) {
-        const float4 g = s_lmno[i];
-        const float4 p0 = s_pix[0 * TILE + i], p1 = s_pix[1 * TILE + i];
-        const float4 p2 = s_pix[2 * TILE + i], p3 = s_pix[3 * TILE + i];
-        // degridder_reference.cpp:106 as the CPU binary evaluates it
-        const float idx = __fadd_rn(__fmaf_rn(u, g.x, __fmul_rn(v, g.y)), __fmul_rn(w, g.z));
+      // degridder_reference.cpp:106 as the CPU binary evaluates it (w term unfused)
+      auto phase_index = [&](const float4 &g) {
+        return __fadd_rn(__fmaf_rn(u, g.x, __fmul_rn(v, g.y)), __fmul_rn(w, g.z));
+      };
+      if (SCHEME == 0) {
+        // software pipelined like the gridder: ph[] holds the phasors of the pixel
+        // about to be accumulated, those of the lane's next pixel are made meanwhile
+        float2 ph[V];
+        if (pg < tile_n) {
+          const float4 g = s_lmno[pg];
+          const float idx = phase_index(g);
 #pragma unroll
-        for (int c = 0; c < V; c++) {
-          const float2 ph = phasor<MODE>(__fmaf_rn(idx, wn[c], -g.w));  // :112
-          if (SCHEME == 0) {
-            accA[c][0] = ffma2(make_float2(p0.x, p0.y), ph, accA[c][0]);
-            accB[c][0] = ffma2(make_float2(p0.z, p0.w), ph, accB[c][0]);
-            accA[c][1] = ffma2(make_float2(p1.x, p1.y), ph, accA[c][1]);
-            accB[c][1] = ffma2(make_float2(p1.z, p1.w), ph, accB[c][1]);
-            accA[c][2] = ffma2(make_float2(p2.x, p2.y), ph, accA[c][2]);
-            accB[c][2] = ffma2(make_float2(p2.z, p2.w), ph, accB[c][2]);
-            accA[c][3] = ffma2(make_float2(p3.x, p3.y), ph, accA[c][3]);
-            accB[c][3] = ffma2(make_float2(p3.z, p3.w), ph, accB[c][3]);
-          } else {
-            const float pr[4] = {p0.x, p1.x, p2.x, p3.x};
-            const float pi[4] = {p0.z, p1.z, p2.z, p3.z};
+          for (int c = 0; c < V; c++) ph[c] = phasor<MODE>(__fmaf_rn(idx, wn[c], -g.w));  // :112
+        }
+        for (int i = pg; i < tile_n; i += PS) {
+          const float4 gn = s_lmno[min(i + PS, tile_n - 1)];  // last one: result unused
+          const float4 p0 = s_pix[0 * TILE + i], p1 = s_pix[1 * TILE + i];
+          const float4 p2 = s_pix[2 * TILE + i], p3 = s_pix[3 * TILE + i];
+          const float idxn = phase_index(gn);
 #pragma unroll
-            for (int p = 0; p < NR_POL; p++) {
-              accA[c][p].x = fmaf(pr[p], ph.x, accA[c][p].x);
-              accA[c][p].x = fmaf(-pi[p], ph.y, accA[c][p].x);
-              accA[c][p].y = fmaf(pr[p], ph.y, accA[c][p].y);
-              accA[c][p].y = fmaf(pi[p], ph.x, accA[c][p].y);
+          for (int c = 0; c < V; c++) {
+            const float2 nx = phasor<MODE>(__fmaf_rn(idxn, wn[c], -gn.w));
+            accA[c][0] = ffma2(make_float2(p0.x, p0.y), ph[c], accA[c][0]);
+            accB[c][0] = ffma2(make_float2(p0.z, p0.w), ph[c], accB[c][0]);
+            accA[c][1] = ffma2(make_float2(p1.x, p1.y), ph[c], accA[c][1]);
+            accB[c][1] = ffma2(make_float2(p1.z, p1.w), ph[c], accB[c][1]);
+            accA[c][2] = ffma2(make_float2(p2.x, p2.y), ph[c], accA[c][2]);
+            accB[c][2] = ffma2(make_float2(p2.z, p2.w), ph[c], accB[c][2]);
+            accA[c][3] = ffma2(make_float2(p3.x, p3.y), ph[c], accA[c][3]);
+            accB[c][3] = ffma2(make_float2(p3.z, p3.w), ph[c], accB[c][3]);
+            ph[c] = nx;
+          }
+        }
+      } else {
+        for (int i = pg; i < tile_n; i += PS) {
+          const float4 g = s_lmno[i];
+          const float4 p0 = s_pix[0 * TILE + i], p1 = s_pix[1 * TILE + i];
+          const float4 p2 = s_pix[2 * TILE + i], p3 = s_pix[3 * TILE + i];
+          const float idx = phase_index(g);
+#pragma unroll
+          for (int c = 0; c < V; c++) {
+            const float2 ph = phasor<MODE>(__fmaf_rn(idx, wn[c], -g.w));  // :112
+            if (SCHEME == 2) {
+              accA[c][0] = ffma2(make_float2(p0.x, p0.y), ph, accA[c][0]);
+              accB[c][0] = ffma2(make_float2(p0.z, p0.w), ph, accB[c][0]);
+              accA[c][1] = ffma2(make_float2(p1.x, p1.y), ph, accA[c][1]);
+              accB[c][1] = ffma2(make_float2(p1.z, p1.w), ph, accB[c][1]);
+              accA[c][2] = ffma2(make_float2(p2.x, p2.y), ph, accA[c][2]);
+              accB[c][2] = ffma2(make_float2(p2.z, p2.w), ph, accB[c][2]);
+              accA[c][3] = ffma2(make_float2(p3.x, p3.y), ph, accA[c][3]);
+              accB[c][3] = ffma2(make_float2(p3.z, p3.w), ph, accB[c][3]);
+            } else {
+              const float pr[4] = {p0.x, p1.x, p2.x, p3.x};
+              const float pi[4] = {p0.z, p1.z, p2.z, p3.z};
+#pragma unroll
+              for (int p = 0; p < NR_POL; p++) {
+                accA[c][p].x = fmaf(pr[p], ph.x, accA[c][p].x);
+                accA[c][p].x = fmaf(-pi[p], ph.y, accA[c][p].x);
+                accA[c][p].y = fmaf(pr[p], ph.y, accA[c][p].y);
+                accA[c][p].y = fmaf(pi[p], ph.x, accA[c][p].y);
+              }
             }
           }
         }
@@ -167,7 +203,7 @@ degridder_kernel(const KernelArgs a) {
       float2 sum[NR_POL];
 #pragma unroll
       for (int p = 0; p < NR_POL; p++) {
-        if (SCHEME == 0)
+        if (SCHEME != 1)
           sum[p] = make_float2(accA[c][p].x - accB[c][p].y, accA[c][p].y + accB[c][p].x);
         else
           sum[p] = accA[c][p];
@@ -206,15 +242,17 @@ cudaError_t launch_t(const KernelArgs &a, int mode, cudaStream_t stream) {
 
 }  // namespace
 
-// variant: 0 default (FFMA2, 256 threads, 4 channels per task)
+// variant: 0 default (FFMA2 pipelined, 256 threads, 4 channels per task)
 //          1 scalar-FFMA baseline (256 threads, 4 channels per task)
-//          2 FFMA2, 8 channels per task
+//          2 FFMA2 without the software pipeline (4 channels per task)
+//          3 FFMA2 pipelined, 2 channels per task
 cudaError_t launch_degridder(const KernelArgs &a, int sincos_mode, int variant, cudaStream_t stream) {
   if (a.nr_subgrids == 0) return cudaSuccess;
   switch (variant) {
     case 0: return launch_t<256, 4, 0>(a, sincos_mode, stream);
     case 1: return launch_t<256, 4, 1>(a, sincos_mode, stream);
-    case 2: return launch_t<256, 8, 0>(a, sincos_mode, stream);
+    case 2: return launch_t<256, 4, 2>(a, sincos_mode, stream);
+    case 3: return launch_t<256, 2, 0>(a, sincos_mode, stream);
     default: return cudaErrorInvalidValue;
   }
 }

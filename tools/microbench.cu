@@ -109,6 +109,52 @@ __global__ void __launch_bounds__(256, 2) k_mix(float *out, int iters, float k0,
   out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// ---- same item mix, software pipelined: the phasors of iteration i+1 are produced while
+// iteration i is accumulated, so MUFU and FFMA2 interleave inside one warp
+template <int P, int MINB>
+__global__ void __launch_bounds__(256, MINB) k_mix_sp(float *out, int iters, float k0, const float4 *vis_g) {
+  __shared__ float4 s_vis[64 * 4];
+  for (int i = threadIdx.x; i < 64 * 4; i += blockDim.x) s_vis[i] = vis_g[i];
+  __syncthreads();
+  float2 accA[P][4], accB[P][4];
+  float idx[P], off[P];
+  for (int j = 0; j < P; j++) {
+    idx[j] = 1.0f + threadIdx.x * 1e-3f + j;
+    off[j] = 0.5f * j;
+    for (int p = 0; p < 4; p++) accA[j][p] = accB[j][p] = make_float2(0, 0);
+  }
+  float2 ph[P];
+  for (int j = 0; j < P; j++) { float sn, cs; __sincosf(fmaf(-idx[j], k0, off[j]), &sn, &cs); ph[j] = make_float2(cs, sn); }
+#pragma unroll 2
+  for (int it = 0; it < iters; it++) {
+    const float wn = k0 + (it + 1) * 1e-6f;
+    const float4 *vt = s_vis + (it & 63) * 4;
+    const float4 v0 = vt[0], v1 = vt[1], v2 = vt[2], v3 = vt[3];
+    float2 nxt[P];
+#pragma unroll
+    for (int j = 0; j < P; j++) {
+      float sn, cs;
+      __sincosf(fmaf(-idx[j], wn, off[j]), &sn, &cs);
+      nxt[j] = make_float2(cs, sn);
+      const float2 p_ = ph[j];
+      accA[j][0] = ffma2(make_float2(v0.x, v0.y), p_, accA[j][0]);
+      accB[j][0] = ffma2(make_float2(v0.z, v0.w), p_, accB[j][0]);
+      accA[j][1] = ffma2(make_float2(v1.x, v1.y), p_, accA[j][1]);
+      accB[j][1] = ffma2(make_float2(v1.z, v1.w), p_, accB[j][1]);
+      accA[j][2] = ffma2(make_float2(v2.x, v2.y), p_, accA[j][2]);
+      accB[j][2] = ffma2(make_float2(v2.z, v2.w), p_, accB[j][2]);
+      accA[j][3] = ffma2(make_float2(v3.x, v3.y), p_, accA[j][3]);
+      accB[j][3] = ffma2(make_float2(v3.z, v3.w), p_, accB[j][3]);
+    }
+#pragma unroll
+    for (int j = 0; j < P; j++) ph[j] = nxt[j];
+  }
+  float s = 0;
+  for (int j = 0; j < P; j++)
+    for (int p = 0; p < 4; p++) s += accA[j][p].x + accA[j][p].y + accB[j][p].x + accB[j][p].y;
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 template <typename F>
 double time_ms(F launch, int reps = 5) {
   cudaEvent_t e0, e1;
@@ -140,6 +186,21 @@ int main() {
     if (items_per_smsp > 0) printf("  %7.2f cyc/item/SMSP (FP32 floor 18, XU floor 16)", cyc / items_per_smsp);
     printf("\n");
   };
+  for (int bps = 1; bps <= 4; bps++) {
+    const int grid = sms * bps, warps_per_smsp = 2 * bps;
+    printf("--- software pipelined, %d block(s)/SM x 256 threads (%d warps/SMSP)\n", bps, warps_per_smsp);
+    double ms;
+    if (bps <= 2) {
+      ms = time_ms([&] { k_mix_sp<4, 2><<<grid, 256>>>(out, iters, 3.1f, vis); });
+      report("SP item mix FFMA2 P=4 + LDS", ms, (double)iters * 4 * 12 * warps_per_smsp, (double)iters * 4 * warps_per_smsp);
+    }
+    ms = time_ms([&] { k_mix_sp<2, 4><<<grid, 256>>>(out, iters, 3.1f, vis); });
+    report("SP item mix FFMA2 P=2 + LDS", ms, (double)iters * 2 * 12 * warps_per_smsp, (double)iters * 2 * warps_per_smsp);
+    if (bps <= 3) {
+      ms = time_ms([&] { k_mix_sp<3, 3><<<grid, 256>>>(out, iters, 3.1f, vis); });
+      report("SP item mix FFMA2 P=3 + LDS", ms, (double)iters * 3 * 12 * warps_per_smsp, (double)iters * 3 * warps_per_smsp);
+    }
+  }
   for (int bps = 1; bps <= 2; bps++) {   // blocks per SM (256 threads each = 2 warps per SMSP per block)
     const int grid = sms * bps, warps_per_smsp = 2 * bps;
     printf("--- %d block(s)/SM x 256 threads (%d warps/SMSP)\n", bps, warps_per_smsp);
