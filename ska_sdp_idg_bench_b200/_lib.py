@@ -55,12 +55,12 @@ SYMBOLS = {
 }
 
 
-def load() -> C.CDLL:
-    if not os.path.exists(LIB_PATH):
+def load(path: str = LIB_PATH) -> C.CDLL:
+    if not os.path.exists(path):
         raise ImportError(
-            f"{LIB_PATH} is missing: build it with `make -C ska_sdp_idg_bench_b200/csrc` "
+            f"{path} is missing: build it with `make -C ska_sdp_idg_bench_b200/csrc` "
             "(or __graft_entry__.build()).  There is no fallback implementation.")
-    lib = C.CDLL(LIB_PATH)
+    lib = C.CDLL(path)
     for name, (res, args) in SYMBOLS.items():
         f = getattr(lib, name)  # AttributeError if the library does not export it
         f.restype = res

@@ -1,0 +1,200 @@
+#!/usr/bin/env python
+"""Post-ptxas tuning of the FFMA2 operand-reuse flags in a sm_100a cubin.
+
+Why.  On B200 an FFMA2 holds the sub-partition's dispatch port for 2 cycles, or 3 when it
+has to read three registers from one register-file bank; the register *reuse cache*
+(one latch per operand slot, filled by an operand flagged `.reuse`, consumed by the next
+instruction of the warp that reads the same register in the same slot) is what keeps a
+packed multiply-add at 2 reads per bank.  ptxas 12.9 leaves the flag off (a) the first
+FFMA2 after a scoreboard wait and (b) every instruction it marks "yield", which in the
+gridder / degridder inner loops costs 2 of every 8 FFMA2 a third cycle
+(tools/sass_model.py, DESIGN.md "what bounds the kernels").
+
+What.  For every pair of address-adjacent FFMA2 instructions in the selected kernels that
+read the same register through the same operand slot (A or B), set the slot's reuse bit
+on the first one and replace its "yield" hint by "hold" so that the pair issues back to
+back.  Nothing else is touched: opcodes, operands, stall counts, scoreboard fields and
+instruction order stay exactly as ptxas emitted them, so the arithmetic is unchanged
+(tests/test_gpu_parity.py::test_sass_tuned_equals_untuned_bitwise checks bit equality
+against the untuned build).
+
+The bit positions (128-bit instruction word, little endian; verified against cuobjdump
+output of ptxas' own flagged instructions before anything is written):
+    hi[41:45) stall   hi[45] hold(1)/yield(0)   hi[58] reuse A   hi[59] reuse B   hi[60] reuse C
+    lo[0:16) = 0x7249 for FFMA2 reg,reg,reg;  lo[24:32) Ra  lo[32:40) Rb  hi[0:8) Rc
+
+Usage: sass_tune.py <cubin> [--kernels REGEX] [--dry-run] [--report]
+"""
+from __future__ import annotations
+
+import re
+import struct
+import subprocess
+import sys
+
+FFMA2_OPCODE = 0x7249
+BIT_HOLD = 1 << 45
+BIT_REUSE = {0: 1 << 58, 1: 1 << 59}
+
+INSTR = re.compile(r"^\s+/\*([0-9a-f]{4,6})\*/\s+(.*?);\s+/\* (0x[0-9a-f]{16}) \*/")
+HIWORD = re.compile(r"^\s+/\* (0x[0-9a-f]{16}) \*/")
+
+
+def disassemble(path: str) -> dict[str, list[dict]]:
+    out = subprocess.run(["cuobjdump", "-sass", path], capture_output=True, text=True, check=True).stdout
+    funcs: dict[str, list[dict]] = {}
+    cur = None
+    pending = None
+    for line in out.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            cur = funcs.setdefault(m.group(1), [])
+            pending = None
+            continue
+        m = INSTR.match(line)
+        if m and cur is not None:
+            pending = dict(addr=int(m.group(1), 16), text=m.group(2).strip(), lo=int(m.group(3), 16), hi=None)
+            cur.append(pending)
+            continue
+        m = HIWORD.match(line)
+        if m and pending is not None and pending["hi"] is None:
+            pending["hi"] = int(m.group(1), 16)
+    return funcs
+
+
+def elf_sections(blob: bytes) -> dict[str, tuple[int, int]]:
+    """name -> (file offset, size) of an ELF64 little-endian file."""
+    assert blob[:4] == b"\x7fELF" and blob[4] == 2 and blob[5] == 1, "not an ELF64-LE cubin"
+    shoff, = struct.unpack_from("<Q", blob, 0x28)
+    shentsize, shnum, shstrndx = struct.unpack_from("<HHH", blob, 0x3A)
+    secs = []
+    for i in range(shnum):
+        name, _type, _flags, _addr, off, size = struct.unpack_from("<IIQQQQ", blob, shoff + i * shentsize)
+        secs.append((name, off, size))
+    stroff = secs[shstrndx][1]
+    res = {}
+    for name, off, size in secs:
+        end = blob.index(b"\0", stroff + name)
+        res[blob[stroff + name:end].decode()] = (off, size)
+    return res
+
+
+def operands(text: str) -> list[str]:
+    body = text.split(None, 1)[1] if " " in text else ""
+    if text.startswith("@"):
+        body = text.split(None, 2)[2] if len(text.split(None, 2)) > 2 else ""
+    return [a.strip() for a in body.split(",")]
+
+
+def src_key(arg: str):
+    """(register number, operand form) of a source operand, None for non-register operands."""
+    m = re.match(r"^(-?)(\|?)R(\d+)((?:\.[A-Za-z0-9_]+)*)$", arg)
+    if not m:
+        return None
+    form = ".".join(f for f in m.group(4).split(".") if f and f != "reuse")
+    return int(m.group(3)), form, m.group(1)
+
+
+def tune_function(ins: list[dict]) -> tuple[list[tuple[int, int]], dict]:
+    """Returns ([(index, new_hi)], stats) for one kernel."""
+    patches = []
+    stats = dict(ffma2=0, pairs=0, already=0, set_reuse=0, set_hold=0)
+    for i in range(len(ins) - 1):
+        a, b = ins[i], ins[i + 1]
+        if (a["lo"] & 0xFFFF) != FFMA2_OPCODE:
+            continue
+        stats["ffma2"] += 1
+        if (b["lo"] & 0xFFFF) != FFMA2_OPCODE or b["addr"] != a["addr"] + 16:
+            continue
+        if a["text"].startswith("@") or b["text"].startswith("@"):
+            continue
+        oa, ob = operands(a["text"]), operands(b["text"])
+        if len(oa) != 4 or len(ob) != 4:
+            continue
+        dst_a = src_key(oa[0])
+        hi = a["hi"]
+        for slot in (0, 1):  # operand slots A and B (sources 1 and 2)
+            ka, kb = src_key(oa[1 + slot]), src_key(ob[1 + slot])
+            if ka is None or kb is None or ka[0] != kb[0]:
+                continue
+            # the first instruction must not overwrite the register (pair) it would cache
+            src_regs = {ka[0], ka[0] + 1} if "F32x2" in ka[1] else {ka[0]}
+            if dst_a is None or src_regs & {dst_a[0], dst_a[0] + 1}:
+                continue
+            stats["pairs"] += 1
+            if hi & BIT_REUSE[slot]:
+                stats["already"] += 1
+                continue
+            # cross-check the bit position with the disassembler: ".reuse" must be absent
+            assert ".reuse" not in oa[1 + slot], (a["text"], hex(a["hi"]))
+            hi |= BIT_REUSE[slot]
+            stats["set_reuse"] += 1
+        if hi != a["hi"]:
+            if not hi & BIT_HOLD:
+                hi |= BIT_HOLD
+                stats["set_hold"] += 1
+            patches.append((i, hi))
+    return patches, stats
+
+
+def verify_bit_positions(funcs) -> None:
+    """ptxas' own output must agree with the bit positions this script writes."""
+    checked = 0
+    for ins in funcs.values():
+        for x in ins:
+            if (x["lo"] & 0xFFFF) != FFMA2_OPCODE or x["hi"] is None:
+                continue
+            ops = operands(x["text"])
+            if len(ops) != 4:
+                continue
+            for slot in (0, 1):
+                flagged = ".reuse" in ops[1 + slot]
+                assert bool(x["hi"] & BIT_REUSE[slot]) == flagged, ("reuse bit", slot, x["text"], hex(x["hi"]))
+            ka, kb = src_key(ops[1]), src_key(ops[2])
+            if ka:
+                assert (x["lo"] >> 24) & 0xFF == ka[0], ("Ra field", x["text"], hex(x["lo"]))
+            if kb:
+                assert (x["lo"] >> 32) & 0xFF == kb[0], ("Rb field", x["text"], hex(x["lo"]))
+            checked += 1
+    assert checked > 0, "no FFMA2 found: nothing to verify"
+
+
+def main(argv) -> int:
+    path = argv[1]
+    kre = re.compile(argv[argv.index("--kernels") + 1]) if "--kernels" in argv else re.compile(".")
+    dry = "--dry-run" in argv
+    funcs = disassemble(path)
+    verify_bit_positions(funcs)
+    blob = bytearray(open(path, "rb").read())
+    secs = elf_sections(bytes(blob))
+    total = dict(ffma2=0, pairs=0, already=0, set_reuse=0, set_hold=0)
+    for name, ins in funcs.items():
+        if not kre.search(name):
+            continue
+        sec = secs.get(".text." + name)
+        if sec is None:
+            continue
+        patches, stats = tune_function(ins)
+        for k in total:
+            total[k] += stats[k]
+        for idx, new_hi in patches:
+            x = ins[idx]
+            off = sec[0] + x["addr"]
+            lo, hi = struct.unpack_from("<QQ", blob, off)
+            assert (lo, hi) == (x["lo"], x["hi"]), f"cubin bytes at {off:#x} differ from the disassembly"
+            struct.pack_into("<Q", blob, off + 8, new_hi)
+        if "--report" in argv and patches:
+            print(f"  {name[:90]}: {stats}")
+    if not dry:
+        open(path, "wb").write(bytes(blob))
+        # the patched file must still disassemble, with the new flags visible
+        after = disassemble(path)
+        verify_bit_positions(after)
+    print(f"sass_tune: {path}: FFMA2 {total['ffma2']}, reusable adjacent pairs {total['pairs']} "
+          f"({total['already']} already flagged by ptxas), reuse bits set {total['set_reuse']}, "
+          f"yield->hold {total['set_hold']}{' (dry run)' if dry else ''}")
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main(sys.argv))

@@ -336,3 +336,38 @@ def test_sharded_equals_unsharded_bitwise():
         assert run_gridder(q).tobytes() == full_g[s0:s1].tobytes()
         rows = covered_rows(q)
         assert run_degridder(q)[rows].tobytes() == full_d[t0:t1][rows].tobytes()
+
+
+def test_sass_tuned_equals_untuned_bitwise(config1):
+    """libidgb200.so has its FFMA2 reuse flags tuned after ptxas (csrc/sass_tune.py);
+    libidgb200_untuned.so is the same source straight out of nvcc.  Only control bits
+    differ, so every output bit must be identical."""
+    import ctypes as C
+
+    from ska_sdp_idg_bench_b200 import _lib
+
+    path = os.path.join(os.path.dirname(_lib.LIB_PATH), "libidgb200_untuned.so")
+    if not os.path.exists(path):
+        pytest.skip("untuned twin not built")
+    unt = _lib.load(path)
+    problems = [config1[0], random_problem(31, nr_subgrids=4, subgrid_size=32, nr_channels=7, max_timesteps=33),
+                random_problem(32, nr_subgrids=3, subgrid_size=24, nr_channels=16, max_timesteps=20)]
+    for p in problems:
+        for sincos in (idg.SINCOS_FAST, idg.SINCOS_ACCURATE):
+            par = _lib.Params()
+            par.nr_subgrids, par.grid_size, par.subgrid_size = p.nr_subgrids, p.grid_size, p.subgrid_size
+            par.image_size, par.w_step_in_lambda = p.image_size, p.w_step
+            par.nr_channels, par.nr_stations, par.sincos_mode, par.variant = p.nr_channels, p.nr_stations, sincos, 0
+            ptr = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+            g = np.full_like(p.subgrids, np.nan)
+            rc = unt.idgb200_c_run_gridder_ex(C.byref(par), p.total_timesteps, p.aterms.shape[0], ptr(p.uvw),
+                                              ptr(p.wavenumbers), ptr(p.visibilities), ptr(p.spheroidal),
+                                              ptr(p.aterms), ptr(p.metadata), ptr(g))
+            assert rc == 0
+            assert g.tobytes() == run_gridder(p, sincos).tobytes()
+            d = np.zeros_like(p.visibilities)
+            rc = unt.idgb200_c_run_degridder_ex(C.byref(par), p.total_timesteps, p.aterms.shape[0], ptr(p.uvw),
+                                                ptr(p.wavenumbers), ptr(d), ptr(p.spheroidal), ptr(p.aterms),
+                                                ptr(p.metadata), ptr(p.subgrids))
+            assert rc == 0
+            assert d.tobytes() == run_degridder(p, sincos).tobytes()
