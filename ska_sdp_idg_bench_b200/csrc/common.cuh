@@ -165,6 +165,15 @@ __device__ __forceinline__ void load_jones(const float2 *aterms, size_t index, f
   a[3] = make_float2(hi.z, hi.w);
 }
 
+// 16-byte shared-memory load the compiler may not hoist out of a loop (used for values
+// that are wanted once per outer iteration and must not occupy registers in between)
+__device__ __forceinline__ float4 lds128_pinned(const float4 *p) {
+  float4 r;
+  const unsigned s = (unsigned)__cvta_generic_to_shared(p);
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(s));
+  return r;
+}
+
 // ----------------------------------------------------------------- async copy
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
   const unsigned s = (unsigned)__cvta_generic_to_shared(smem);

@@ -7,21 +7,27 @@
 // Behaviour follows cpu::kernel_degridder_reference
 // (app/CPU/kernels/degridder_reference.cpp:6-129); the design is new:
 //
-//  * one thread block per subgrid.  A prologue applies taper and A-terms once
-//    per pixel and leaves P' (in the duplicated (re,re)(im,im) layout FFMA2
-//    wants) plus (l, m, n, phase_offset) in shared memory;
-//  * the unit of work is a task = (timestep, block of V channels).  The lanes of
-//    a warp are split into 32/PS task slots x PS pixel groups: a lane sums its
-//    task over every PS-th pixel with the same packed inner product as the
-//    gridder (8 FFMA2 + 1 FFMA + 1 FMUL + 2 MUFU per pixel x channel), all lanes of
-//    a slot read the same shared-memory words (one wavefront per load), and the
-//    PS partial sums are combined with __shfl_xor_sync butterflies.  PS is chosen
-//    per subgrid (>= 4, up to 32 = one warp per task) so that short subgrids
-//    still fill the block.  No reference kernel reduces this way: they all loop
-//    one thread over all pixels of a visibility (degridder_v6.cu:88-116);
-//  * every visibility of the subgrid's time range is written exactly once, by the
-//    lanes that own it after the butterfly (no read-modify-write of global
-//    memory as in degridder_v4.cu:155-161).
+//  * one thread block per subgrid.  A prologue applies taper and A-terms once per pixel
+//    and leaves P' in shared memory in the 48-byte record layout of the gridder,
+//        (Pr0 Pr1 Pr2 Pr3) (-Pi0 Pi0 -Pi1 Pi1) (-Pi2 Pi2 -Pi3 Pi3)
+//    plus (l, m, n, phase_offset), so that the complex multiply-add is two FFMA2 with free
+//    operand modes and no sign / shuffle instruction (see gridder.cu):
+//        acc[pol] += Pr.F32 * (cos,sin)          acc[pol] += (-Pi,Pi) * (sin,cos)
+//  * the unit of work is a task = (timestep, block of V = 8 channels): 64 accumulator
+//    registers, the pixel record (4 LDS.128) and the phase index (4 FP32 ops) are shared
+//    by 8 (pixel, channel) items.  The lanes of a warp are split into 32/PS task slots x
+//    PS pixel groups: a lane sums its task over every PS-th pixel, all lanes of a slot
+//    read the same shared-memory words (one wavefront per load), and the PS partial sums
+//    are combined with __shfl_xor_sync butterflies.  PS is chosen per subgrid (>= 4, up to
+//    32 = one warp per task) so that short subgrids still fill the block.  No reference
+//    kernel reduces this way: they all loop one thread over all pixels of a visibility
+//    (degridder_v6.cu:88-116);
+//  * every visibility of the subgrid's time range is written exactly once, by the lanes
+//    that own it after the butterfly (no read-modify-write of global memory as in
+//    degridder_v4.cu:155-161);
+//  * phase_index / phase_offset / phase are evaluated in the CPU binary's operation order
+//    (the degridder leaves the w terms unfused, oracle/idg_oracle.c), so the angle fed to
+//    sincos is bit-identical to the reference's.
 #include "common.cuh"
 #include "kernels.h"
 
@@ -29,18 +35,16 @@ namespace idgb200 {
 
 namespace {
 
-constexpr int TILE = 1024;  // pixels resident in shared memory at a time (80 KB)
+constexpr int TILE = 1024;  // pixels resident in shared memory at a time (64 KB)
 
-// SCHEME 0: FFMA2 rotated accumulators (A += (Pr,Pr)*ph, B += (Pi,Pi)*ph), software
-//           pipelined (default)
-// SCHEME 1: scalar FFMA baseline
-// SCHEME 2: FFMA2 without the software pipeline (A/B)
-template <int NT, int V, int SCHEME, int MODE>
-__global__ void __launch_bounds__(NT, 2)
+// SCHEME 3 (default): swizzled FFMA2 on 48-byte pixel records
+// SCHEME 1: scalar FFMA baseline (same records)
+template <int NT, int V, int SCHEME, int MODE, int MINB>
+__global__ void __launch_bounds__(NT, MINB)
 degridder_kernel(const KernelArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  float4 *s_pix = reinterpret_cast<float4 *>(smem_raw);   // [4][TILE] (Pr,Pr,Pi,Pi)
-  float4 *s_lmno = s_pix + NR_POL * TILE;                  // [TILE]    (l,m,n,phase_offset)
+  float4 *s_pix = reinterpret_cast<float4 *>(smem_raw);   // [3][TILE] records, component-major
+  float4 *s_lmno = s_pix + 3 * TILE;                       // [TILE]    (l, m, n, phase_offset)
 
   const int N = a.subgrid_size;
   const int C = a.nr_channels;
@@ -88,9 +92,9 @@ degridder_kernel(const KernelArgs a) {
       load_jones(a.aterms, (at1 + q) * NR_POL, a1);
       load_jones(a.aterms, (at2 + q) * NR_POL, a2);
       apply_aterm_degridder(px, a1, a2);
-#pragma unroll
-      for (int p = 0; p < NR_POL; p++)
-        s_pix[p * TILE + i] = make_float4(px[p].x, px[p].x, px[p].y, px[p].y);
+      s_pix[0 * TILE + i] = make_float4(px[0].x, px[1].x, px[2].x, px[3].x);
+      s_pix[1 * TILE + i] = make_float4(-px[0].y, px[0].y, -px[1].y, px[1].y);
+      s_pix[2 * TILE + i] = make_float4(-px[2].y, px[2].y, -px[3].y, px[3].y);
       const float l = compute_l(x, N, a.image_size);
       const float m = compute_l(y, N, a.image_size);
       const float n = compute_n(l, m);
@@ -112,14 +116,11 @@ degridder_kernel(const KernelArgs a) {
 #pragma unroll
     for (int c = 0; c < V; c++) wn[c] = (c0 + c < C) ? __ldg(&a.wavenumbers[c0 + c]) : 0.f;
 
-    float2 accA[V][NR_POL], accB[V][NR_POL];
+    float2 acc[V][NR_POL];
 #pragma unroll
     for (int c = 0; c < V; c++)
 #pragma unroll
-      for (int p = 0; p < NR_POL; p++) {
-        accA[c][p] = make_float2(0.f, 0.f);
-        accB[c][p] = make_float2(0.f, 0.f);
-      }
+      for (int p = 0; p < NR_POL; p++) acc[c][p] = make_float2(0.f, 0.f);
 
     for (int tile = 0; tile < ntiles; tile++) {
       const int tile0 = tile * TILE;
@@ -130,83 +131,47 @@ degridder_kernel(const KernelArgs a) {
         __syncthreads();
       }
 
-      // degridder_reference.cpp:106 as the CPU binary evaluates it (w term unfused)
-      auto phase_index = [&](const float4 &g) {
-        return __fadd_rn(__fmaf_rn(u, g.x, __fmul_rn(v, g.y)), __fmul_rn(w, g.z));
-      };
-      if (SCHEME == 0) {
-        // software pipelined like the gridder: ph[] holds the phasors of the pixel
-        // about to be accumulated, those of the lane's next pixel are made meanwhile
-        float2 ph[V];
-        if (pg < tile_n) {
-          const float4 g = s_lmno[pg];
-          const float idx = phase_index(g);
+#pragma unroll 1
+      for (int i = pg; i < tile_n; i += PS) {
+        const float4 g = s_lmno[i];
+        const float4 q0 = s_pix[0 * TILE + i], q1 = s_pix[1 * TILE + i], q2 = s_pix[2 * TILE + i];
+        // degridder_reference.cpp:106 as the CPU binary evaluates it (w term unfused)
+        const float idx = __fadd_rn(__fmaf_rn(u, g.x, __fmul_rn(v, g.y)), __fmul_rn(w, g.z));
 #pragma unroll
-          for (int c = 0; c < V; c++) ph[c] = phasor<MODE>(__fmaf_rn(idx, wn[c], -g.w));  // :112
-        }
-        for (int i = pg; i < tile_n; i += PS) {
-          const float4 gn = s_lmno[min(i + PS, tile_n - 1)];  // last one: result unused
-          const float4 p0 = s_pix[0 * TILE + i], p1 = s_pix[1 * TILE + i];
-          const float4 p2 = s_pix[2 * TILE + i], p3 = s_pix[3 * TILE + i];
-          const float idxn = phase_index(gn);
+        for (int c = 0; c < V; c++) {
+          const float2 ph = phasor<MODE>(__fmaf_rn(idx, wn[c], -g.w));  // :112, (cos, sin)
+          if (SCHEME == 3) {
+            const float2 hp = make_float2(ph.y, ph.x);                   // LO_HI swizzle
+            acc[c][0] = ffma2(make_float2(q0.x, q0.x), ph, acc[c][0]);
+            acc[c][1] = ffma2(make_float2(q0.y, q0.y), ph, acc[c][1]);
+            acc[c][2] = ffma2(make_float2(q0.z, q0.z), ph, acc[c][2]);
+            acc[c][3] = ffma2(make_float2(q0.w, q0.w), ph, acc[c][3]);
+            acc[c][0] = ffma2(make_float2(q1.x, q1.y), hp, acc[c][0]);
+            acc[c][1] = ffma2(make_float2(q1.z, q1.w), hp, acc[c][1]);
+            acc[c][2] = ffma2(make_float2(q2.x, q2.y), hp, acc[c][2]);
+            acc[c][3] = ffma2(make_float2(q2.z, q2.w), hp, acc[c][3]);
+          } else {
+            const float pr[4] = {q0.x, q0.y, q0.z, q0.w};
+            const float pi[4] = {q1.y, q1.w, q2.y, q2.w};
 #pragma unroll
-          for (int c = 0; c < V; c++) {
-            const float2 nx = phasor<MODE>(__fmaf_rn(idxn, wn[c], -gn.w));
-            accA[c][0] = ffma2(make_float2(p0.x, p0.y), ph[c], accA[c][0]);
-            accB[c][0] = ffma2(make_float2(p0.z, p0.w), ph[c], accB[c][0]);
-            accA[c][1] = ffma2(make_float2(p1.x, p1.y), ph[c], accA[c][1]);
-            accB[c][1] = ffma2(make_float2(p1.z, p1.w), ph[c], accB[c][1]);
-            accA[c][2] = ffma2(make_float2(p2.x, p2.y), ph[c], accA[c][2]);
-            accB[c][2] = ffma2(make_float2(p2.z, p2.w), ph[c], accB[c][2]);
-            accA[c][3] = ffma2(make_float2(p3.x, p3.y), ph[c], accA[c][3]);
-            accB[c][3] = ffma2(make_float2(p3.z, p3.w), ph[c], accB[c][3]);
-            ph[c] = nx;
-          }
-        }
-      } else {
-        for (int i = pg; i < tile_n; i += PS) {
-          const float4 g = s_lmno[i];
-          const float4 p0 = s_pix[0 * TILE + i], p1 = s_pix[1 * TILE + i];
-          const float4 p2 = s_pix[2 * TILE + i], p3 = s_pix[3 * TILE + i];
-          const float idx = phase_index(g);
-#pragma unroll
-          for (int c = 0; c < V; c++) {
-            const float2 ph = phasor<MODE>(__fmaf_rn(idx, wn[c], -g.w));  // :112
-            if (SCHEME == 2) {
-              accA[c][0] = ffma2(make_float2(p0.x, p0.y), ph, accA[c][0]);
-              accB[c][0] = ffma2(make_float2(p0.z, p0.w), ph, accB[c][0]);
-              accA[c][1] = ffma2(make_float2(p1.x, p1.y), ph, accA[c][1]);
-              accB[c][1] = ffma2(make_float2(p1.z, p1.w), ph, accB[c][1]);
-              accA[c][2] = ffma2(make_float2(p2.x, p2.y), ph, accA[c][2]);
-              accB[c][2] = ffma2(make_float2(p2.z, p2.w), ph, accB[c][2]);
-              accA[c][3] = ffma2(make_float2(p3.x, p3.y), ph, accA[c][3]);
-              accB[c][3] = ffma2(make_float2(p3.z, p3.w), ph, accB[c][3]);
-            } else {
-              const float pr[4] = {p0.x, p1.x, p2.x, p3.x};
-              const float pi[4] = {p0.z, p1.z, p2.z, p3.z};
-#pragma unroll
-              for (int p = 0; p < NR_POL; p++) {
-                accA[c][p].x = fmaf(pr[p], ph.x, accA[c][p].x);
-                accA[c][p].x = fmaf(-pi[p], ph.y, accA[c][p].x);
-                accA[c][p].y = fmaf(pr[p], ph.y, accA[c][p].y);
-                accA[c][p].y = fmaf(pi[p], ph.x, accA[c][p].y);
-              }
+            for (int p = 0; p < NR_POL; p++) {
+              acc[c][p].x = fmaf(pr[p], ph.x, acc[c][p].x);
+              acc[c][p].x = fmaf(-pi[p], ph.y, acc[c][p].x);
+              acc[c][p].y = fmaf(pr[p], ph.y, acc[c][p].y);
+              acc[c][p].y = fmaf(pi[p], ph.x, acc[c][p].y);
             }
           }
         }
       }
     }
 
-    // recombine, butterfly over the PS pixel groups, store
+    // butterfly over the PS pixel groups, store
 #pragma unroll
     for (int c = 0; c < V; c++) {
       float2 sum[NR_POL];
 #pragma unroll
       for (int p = 0; p < NR_POL; p++) {
-        if (SCHEME != 1)
-          sum[p] = make_float2(accA[c][p].x - accB[c][p].y, accA[c][p].y + accB[c][p].x);
-        else
-          sum[p] = accA[c][p];
+        sum[p] = acc[c][p];
         for (int o = PS >> 1; o > 0; o >>= 1) {
           sum[p].x += __shfl_xor_sync(0xffffffffu, sum[p].x, o);
           sum[p].y += __shfl_xor_sync(0xffffffffu, sum[p].y, o);
@@ -224,14 +189,14 @@ degridder_kernel(const KernelArgs a) {
   }
 }
 
-template <int NT, int V, int SCHEME>
+template <int NT, int V, int SCHEME, int MINB>
 cudaError_t launch_t(const KernelArgs &a, int mode, cudaStream_t stream) {
-  const size_t smem = (size_t)(NR_POL + 1) * TILE * sizeof(float4);
+  const size_t smem = (size_t)4 * TILE * sizeof(float4);
   void (*k)(const KernelArgs) = nullptr;
   switch (mode) {
-    case IDGB200_SINCOS_FAST: k = degridder_kernel<NT, V, SCHEME, IDGB200_SINCOS_FAST>; break;
-    case IDGB200_SINCOS_REDUCED: k = degridder_kernel<NT, V, SCHEME, IDGB200_SINCOS_REDUCED>; break;
-    case IDGB200_SINCOS_ACCURATE: k = degridder_kernel<NT, V, SCHEME, IDGB200_SINCOS_ACCURATE>; break;
+    case IDGB200_SINCOS_FAST: k = degridder_kernel<NT, V, SCHEME, IDGB200_SINCOS_FAST, MINB>; break;
+    case IDGB200_SINCOS_REDUCED: k = degridder_kernel<NT, V, SCHEME, IDGB200_SINCOS_REDUCED, MINB>; break;
+    case IDGB200_SINCOS_ACCURATE: k = degridder_kernel<NT, V, SCHEME, IDGB200_SINCOS_ACCURATE, MINB>; break;
     default: return cudaErrorInvalidValue;
   }
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -242,17 +207,17 @@ cudaError_t launch_t(const KernelArgs &a, int mode, cudaStream_t stream) {
 
 }  // namespace
 
-// variant: 0 default (FFMA2 pipelined, 256 threads, 4 channels per task)
+// variant: 0 default: swizzled FFMA2, 256 threads, 8 channels per task, 2 blocks/SM
 //          1 scalar-FFMA baseline (256 threads, 4 channels per task)
-//          2 FFMA2 without the software pipeline (4 channels per task)
-//          3 FFMA2 pipelined, 2 channels per task
+//          2 swizzled FFMA2, 4 channels per task (3 blocks/SM)
+//          3 swizzled FFMA2, 128 threads, 8 channels per task, 3 blocks/SM
 cudaError_t launch_degridder(const KernelArgs &a, int sincos_mode, int variant, cudaStream_t stream) {
   if (a.nr_subgrids == 0) return cudaSuccess;
   switch (variant) {
-    case 0: return launch_t<256, 4, 0>(a, sincos_mode, stream);
-    case 1: return launch_t<256, 4, 1>(a, sincos_mode, stream);
-    case 2: return launch_t<256, 4, 2>(a, sincos_mode, stream);
-    case 3: return launch_t<256, 2, 0>(a, sincos_mode, stream);
+    case 0: return launch_t<256, 8, 3, 2>(a, sincos_mode, stream);
+    case 1: return launch_t<256, 4, 1, 2>(a, sincos_mode, stream);
+    case 2: return launch_t<256, 4, 3, 3>(a, sincos_mode, stream);
+    case 3: return launch_t<128, 8, 3, 3>(a, sincos_mode, stream);
     default: return cudaErrorInvalidValue;
   }
 }

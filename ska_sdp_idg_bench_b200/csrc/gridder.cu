@@ -160,9 +160,9 @@ gridder_kernel(const KernelArgs a, const int slabs, const int vis_per_chunk) {
     if (LMN_IN_SMEM) {
 #pragma unroll
       for (int g = 0; g < P / 4; g++) {
-        const float4 l4 = s_lmn[(0 * (P / 4) + g) * NT + tid];
-        const float4 m4 = s_lmn[(1 * (P / 4) + g) * NT + tid];
-        const float4 n4 = s_lmn[(2 * (P / 4) + g) * NT + tid];
+        const float4 l4 = lds128_pinned(&s_lmn[(0 * (P / 4) + g) * NT + tid]);
+        const float4 m4 = lds128_pinned(&s_lmn[(1 * (P / 4) + g) * NT + tid]);
+        const float4 n4 = lds128_pinned(&s_lmn[(2 * (P / 4) + g) * NT + tid]);
         idx[4 * g + 0] = __fmaf_rn(w, n4.x, __fmaf_rn(u, l4.x, __fmul_rn(v, m4.x)));
         idx[4 * g + 1] = __fmaf_rn(w, n4.y, __fmaf_rn(u, l4.y, __fmul_rn(v, m4.y)));
         idx[4 * g + 2] = __fmaf_rn(w, n4.z, __fmaf_rn(u, l4.z, __fmul_rn(v, m4.z)));
@@ -191,10 +191,11 @@ gridder_kernel(const KernelArgs a, const int slabs, const int vis_per_chunk) {
         float idx[P];
         phase_index(uvw_k + 3 * t, idx);
         const float4 *vt = s_vis + (size_t)t * C * 3;
+        const float4 *vp = vt;
 #pragma unroll 1
-        for (int c = 0; c < C; c++) {
+        for (int c = 0; c < C; c++, vp += 3) {
           const float wn = s_wn[c];
-          const float4 q0 = vt[c * 3 + 0], q1 = vt[c * 3 + 1], q2 = vt[c * 3 + 2];
+          const float4 q0 = vp[0], q1 = vp[1], q2 = vp[2];
           // the phasor of pixel j+1 is started before the FFMA2 group of pixel j so that
           // the group does not open with a scoreboard wait on the MUFU results
           float2 ph = phasor<MODE>(__fmaf_rn(-idx[0], wn, off[0]));  // :69, (cos, sin)
@@ -367,6 +368,10 @@ cudaError_t launch_gridder(const KernelArgs &a, int sincos_mode, int variant, cu
     case 3: return launch_t<256, 8, 3, 1>(a, sincos_mode, stream);
     case 4: return launch_t<256, 4, 0, 2>(a, sincos_mode, stream);
     case 5: return launch_t<128, 8, 3, 3>(a, sincos_mode, stream);
+    case 6: return launch_t<128, 8, 3, 5>(a, sincos_mode, stream);   // experiments: occupancy vs registers
+    case 7: return launch_t<64, 8, 3, 8>(a, sincos_mode, stream);
+    case 8: return launch_t<256, 4, 3, 3>(a, sincos_mode, stream);
+    case 9: return launch_t<128, 4, 3, 6>(a, sincos_mode, stream);
     default: return cudaErrorInvalidValue;
   }
 }

@@ -124,7 +124,7 @@ def test_error_vs_float64_truth(config1):
 
 
 # ---------------------------------------------------------------- kernel variants
-@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5])
 def test_gridder_variants(config1, variant):
     p, ref_g, _ = config1
     assert_close(run_gridder(p, idg.SINCOS_ACCURATE, variant), ref_g, 1, idg.SINCOS_ACCURATE,
@@ -167,7 +167,7 @@ def test_shapes_vs_oracle(shape):
         assert_close(run_gridder(p, idg.SINCOS_ACCURATE, variant), ref_g, 1, idg.SINCOS_ACCURATE,
                      f"gridder {shape} v{variant}")
     rows = covered_rows(p)
-    for variant in (0, 3):
+    for variant in (0, 2):
         got = run_degridder(p, idg.SINCOS_ACCURATE, variant)
         assert_close(got[rows], ref_d[rows], 2, idg.SINCOS_ACCURATE, f"degridder {shape} v{variant}")
 
