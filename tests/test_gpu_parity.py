@@ -371,3 +371,36 @@ def test_sass_tuned_equals_untuned_bitwise(config1):
                                                 ptr(p.metadata), ptr(p.subgrids))
             assert rc == 0
             assert d.tobytes() == run_degridder(p, sincos).tobytes()
+
+
+# --------------------------------------------------- the reference's own test mains
+REF_BIN = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref")
+
+
+@pytest.mark.parametrize("kind", ["gridder", "degridder"])
+def test_reference_harness_dropin(kind):
+    """oracle/_ref/cuda-<kind>_b200 is the reference's UNMODIFIED tests/<kind>_common.cpp and
+    CPU library linked against csrc/shim/idg_cuda_shim.cpp + libidgb200.so (oracle/Makefile,
+    target dropin).  `-c` is the reference's correctness run: its CPU result vs ours, judged
+    by its own check_error (tests/test_util.hpp:28-92, gate 1e-5)."""
+    import re
+    import subprocess
+
+    exe = os.path.join(REF_BIN, f"cuda-{kind}_b200")
+    if not os.path.exists(exe):
+        pytest.skip("drop-in harness not built (needs /root/reference at build time)")
+    env = dict(os.environ, IDGB200_SINCOS="2")
+    out = subprocess.run([exe, "-c"], capture_output=True, text=True, env=env, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    err = float(re.search(r">>> Error: ([0-9.eE+-]+)", out.stdout).group(1))
+    print(f"reference harness, accurate sincos: {kind} error {err:g}")
+    assert ">>> Result PASSED" in out.stdout and err <= 1e-5
+    # default (fast) sincos: same run, the reference's number is reported, bounded by our tolerance
+    out = subprocess.run([exe, "-c"], capture_output=True, text=True, env=dict(os.environ), timeout=300)
+    err = float(re.search(r">>> Error: ([0-9.eE+-]+)", out.stdout).group(1))
+    print(f"reference harness, fast sincos: {kind} error {err:g}")
+    assert err <= 1e-3
+    # performance mode (no argument) on a small shape
+    env = dict(os.environ, NR_STATIONS="8", NR_TIMESLOTS="2", NR_ITERATIONS="2")
+    out = subprocess.run([exe], capture_output=True, text=True, env=env, timeout=300)
+    assert out.returncode == 0 and "MVis/s" in out.stdout, out.stdout + out.stderr
