@@ -377,11 +377,17 @@ def run_ours(args) -> None:
         nbytes = idg.bytes_gridder(C_, tt, S, N)
         hbm_peak = float(peaks.get("hbm_gbs") or 6650.0)
 
-        def roof(sec, steps):
+        def roof(sec, steps, traffic_per_subgrid):
             t = sec / steps
             tf = flops / t * 1e-12
+            # dram bytes of one launch from the round-1 `ncu --set full` capture
+            # (profiles/r01_*_ncu_full.txt: 1740-subgrid launch, read+write 145.2 MB gridder /
+            # 128.3 MB degridder), scaled to this launch's subgrid count
             r = {"bound": "fp32", "achieved": tf, "peak": p_fp32, "unit": "TFLOP/s",
-                 "frac": tf / p_fp32, "traffic": None,
+                 "frac": tf / p_fp32, "traffic": traffic_per_subgrid * S,
+                 "traffic_note": "DRAM bytes/launch from ncu on a 1740-subgrid launch, scaled by subgrid count; "
+                                 "algorithmic bytes (bytes_gridder) = %.3f GB/launch" % (nbytes * 1e-9),
+                 "bound_note": "CUDA-core FP32 bound (359 flop/B): neither HBM nor tensor is the roof",
                  "peak_source": f"{sms} SMs x 128 FP32 lanes x 2 x {f_max:.0f} MHz (sm_max_mhz of "
                                 "MEASURED_PEAKS.json; the file holds no FP32 figure)",
                  "kernel_ms": t * 1e3,
@@ -403,11 +409,11 @@ def run_ours(args) -> None:
             "config": dict(workload_config(shape, world), sincos=args.sincos,
                            gridder_variant=args.variant, degridder_variant=args.degridder_variant),
             "tflops": world * flops * args.steps / sec_g * 1e-12,
-            "roofline": roof(sec_g, args.steps),
+            "roofline": roof(sec_g, args.steps, 145.165e6 / 1740),
             "degridder": {"value": total_mvis * args.steps / sec_d, "unit": "MVis/s",
                           "ms_per_step": sec_d / args.steps * 1e3,
                           "tflops": world * flops * args.steps / sec_d * 1e-12,
-                          "roofline": roof(sec_d, args.steps)},
+                          "roofline": roof(sec_d, args.steps, 128.329e6 / 1740)},
             "cpu_baseline": cpu_baseline, "parity": parity, "e2e": e2e,
             "gpu_launches": int(launches_g), "degridder_gpu_launches": int(launches_d),
             "clocks": clocks, "device": idg.device_name(),
