@@ -163,6 +163,37 @@ def cpu_problem(oracle_lib, shape: dict, nr_subgrids: int):
         subgrids=np.ascontiguousarray(p.subgrids[:S]))
 
 
+def host_threads() -> int:
+    """Cores this process may use.  torchrun exports OMP_NUM_THREADS=1, which is not what
+    "all the host threads it can use" means, so the CPU arm sets the count explicitly."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
+_REAL_STDOUT = None
+
+
+def quiet_stdout() -> None:
+    """Anything a library prints to stdout (NCCL's version banner ...) goes to stderr, so
+    that the JSON line is the only thing on stdout."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(obj: dict) -> None:
+    line = (json.dumps(obj) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(line.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, line)
+
+
 def time_cpu(lib, prob, which: str) -> float:
     t0 = time.perf_counter()
     (lib.gridder if which == "gridder" else lib.degridder)(prob)
@@ -176,7 +207,7 @@ def run_reference_arm(args) -> None:
     if rank != 0:
         return
     lib, kind, oracle_lib = load_cpu_checker()
-    cores = lib.max_threads()
+    cores = host_threads()
     lib.set_threads(cores)
     shape = rank_shape({}, 0, 1)
     # calibrate, then size one step to ~3 s
@@ -207,7 +238,7 @@ def run_reference_arm(args) -> None:
         "e2e": {"value": value, "unit": "MVis/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(out), flush=True)
+    emit(out)
 
 
 def workload_config(shape: dict, n_gpus: int) -> dict:
@@ -228,6 +259,7 @@ def run_ours(args) -> None:
 
     import ska_sdp_idg_bench_b200 as idg
 
+    quiet_stdout()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -329,7 +361,7 @@ def run_ours(args) -> None:
     cpu_baseline, parity = None, None
     if rank == 0 and world == 1 and not args.no_cpu:
         lib, kind, oracle_lib = load_cpu_checker()
-        cores = lib.max_threads()
+        cores = host_threads()
         lib.set_threads(cores)
         n = max(64, 4 * cores)
         # the same workload: copy the first n subgrids of the device-generated inputs
@@ -418,7 +450,7 @@ def run_ours(args) -> None:
             "gpu_launches": int(launches_g), "degridder_gpu_launches": int(launches_d),
             "clocks": clocks, "device": idg.device_name(),
         }
-        print(json.dumps(out), flush=True)
+        emit(out)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
