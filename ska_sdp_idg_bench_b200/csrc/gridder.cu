@@ -349,8 +349,11 @@ cudaError_t launch_t(const KernelArgs &a, int mode, cudaStream_t stream) {
 
 }  // namespace
 
-// variant: 0 default: swizzled FFMA2; 128 threads x 8 pixels (x 4 blocks/SM) when the
+// variant: 0 default: FAST sincos and a channel count that fills >= 3/4 of its 16-channel
+//            blocks -> tensor-core kernel (gridder_tc.cu); otherwise the FP32 kernel (= variant 10)
+//         10 FP32 kernel: swizzled FFMA2; 128 threads x 8 pixels (x 4 blocks/SM) when the
 //            subgrid has >= 1024 pixels, 128 x 4 below that
+//         11 tensor-core kernel (FAST sincos only)
 //          1 scalar-FFMA baseline (256 x 4)
 //          2 swizzled FFMA2, 256 threads x 4 pixels
 //          3 swizzled FFMA2, 256 threads x 8 pixels
@@ -359,10 +362,17 @@ cudaError_t launch_t(const KernelArgs &a, int mode, cudaStream_t stream) {
 cudaError_t launch_gridder(const KernelArgs &a, int sincos_mode, int variant, cudaStream_t stream) {
   if (a.nr_subgrids == 0) return cudaSuccess;
   const int npix = a.subgrid_size * a.subgrid_size;
+  if (variant == 0) {
+    const int ncb = (a.nr_channels + 15) / 16;
+    const bool tc = sincos_mode == IDGB200_SINCOS_FAST && 4 * a.nr_channels >= 3 * ncb * 16;
+    variant = tc ? 11 : 10;
+  }
   switch (variant) {
-    case 0:
+    case 10:
       return npix >= 1024 ? launch_t<128, 8, 3, 4>(a, sincos_mode, stream)
                           : launch_t<128, 4, 3, 4>(a, sincos_mode, stream);
+    case 11:
+      return sincos_mode == IDGB200_SINCOS_FAST ? launch_gridder_tc(a, stream) : cudaErrorInvalidValue;
     case 1: return launch_t<256, 4, 1, 2>(a, sincos_mode, stream);
     case 2: return launch_t<256, 4, 3, 2>(a, sincos_mode, stream);
     case 3: return launch_t<256, 8, 3, 1>(a, sincos_mode, stream);

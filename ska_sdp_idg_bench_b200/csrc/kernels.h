@@ -10,4 +10,7 @@ namespace idgb200 {
 cudaError_t launch_gridder(const KernelArgs &a, int sincos_mode, int variant, cudaStream_t stream);
 cudaError_t launch_degridder(const KernelArgs &a, int sincos_mode, int variant, cudaStream_t stream);
 
+// tcgen05 / TMEM gridder (gridder_tc.cu); FAST sincos only
+cudaError_t launch_gridder_tc(const KernelArgs &a, cudaStream_t stream);
+
 }  // namespace idgb200

@@ -124,11 +124,23 @@ def test_error_vs_float64_truth(config1):
 
 
 # ---------------------------------------------------------------- kernel variants
-@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5, 10])
 def test_gridder_variants(config1, variant):
     p, ref_g, _ = config1
     assert_close(run_gridder(p, idg.SINCOS_ACCURATE, variant), ref_g, 1, idg.SINCOS_ACCURATE,
                  f"gridder v{variant}")
+
+
+def test_gridder_tensor_core_variant(config1):
+    """variant 11 = tcgen05 kernel (what variant 0 picks for FAST sincos), variant 10 = FP32
+    kernel: both inside the FAST tolerance; the tensor kernel refuses the other sincos modes."""
+    p, ref_g, _ = config1
+    mx, rms = assert_close(run_gridder(p, idg.SINCOS_FAST, 11), ref_g, 1, idg.SINCOS_FAST, "gridder tcgen05")
+    print(f"tcgen05 gridder: per-pol max rel {mx}, rel rms {rms}")
+    mx, rms = assert_close(run_gridder(p, idg.SINCOS_FAST, 10), ref_g, 1, idg.SINCOS_FAST, "gridder fp32")
+    print(f"fp32 gridder   : per-pol max rel {mx}, rel rms {rms}")
+    with pytest.raises(idg.IdgError):
+        run_gridder(p, idg.SINCOS_ACCURATE, 11)
 
 
 @pytest.mark.parametrize("variant", [0, 1, 2, 3])
@@ -166,6 +178,7 @@ def test_shapes_vs_oracle(shape):
     for variant in (0, 2):
         assert_close(run_gridder(p, idg.SINCOS_ACCURATE, variant), ref_g, 1, idg.SINCOS_ACCURATE,
                      f"gridder {shape} v{variant}")
+    assert_close(run_gridder(p, idg.SINCOS_FAST, 11), ref_g, 1, idg.SINCOS_FAST, f"gridder tcgen05 {shape}")
     rows = covered_rows(p)
     for variant in (0, 2):
         got = run_degridder(p, idg.SINCOS_ACCURATE, variant)
