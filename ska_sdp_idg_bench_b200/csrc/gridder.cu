@@ -371,8 +371,12 @@ cudaError_t launch_gridder(const KernelArgs &a, int sincos_mode, int variant, cu
     case 10:
       return npix >= 1024 ? launch_t<128, 8, 3, 4>(a, sincos_mode, stream)
                           : launch_t<128, 4, 3, 4>(a, sincos_mode, stream);
-    case 11:
-      return sincos_mode == IDGB200_SINCOS_FAST ? launch_gridder_tc(a, stream) : cudaErrorInvalidValue;
+    case 11: case 12: case 13: case 14: case 15:   // 12..15: part of the phasors by FP32 polynomial
+      return sincos_mode == IDGB200_SINCOS_FAST ? launch_gridder_tc(a, variant - 11, stream)
+                                                : cudaErrorInvalidValue;
+    case 16: case 17: case 18: case 19: case 20: case 21:   // self-issuing producer warps
+      return sincos_mode == IDGB200_SINCOS_FAST ? launch_gridder_tc2(a, variant - 16, stream)
+                                                : cudaErrorInvalidValue;
     case 1: return launch_t<256, 4, 1, 2>(a, sincos_mode, stream);
     case 2: return launch_t<256, 4, 3, 2>(a, sincos_mode, stream);
     case 3: return launch_t<256, 8, 3, 1>(a, sincos_mode, stream);

@@ -11,6 +11,7 @@ cudaError_t launch_gridder(const KernelArgs &a, int sincos_mode, int variant, cu
 cudaError_t launch_degridder(const KernelArgs &a, int sincos_mode, int variant, cudaStream_t stream);
 
 // tcgen05 / TMEM gridder (gridder_tc.cu); FAST sincos only
-cudaError_t launch_gridder_tc(const KernelArgs &a, cudaStream_t stream);
+cudaError_t launch_gridder_tc(const KernelArgs &a, int poly, cudaStream_t stream);
+cudaError_t launch_gridder_tc2(const KernelArgs &a, int poly, cudaStream_t stream);
 
 }  // namespace idgb200
