@@ -349,11 +349,13 @@ cudaError_t launch_t(const KernelArgs &a, int mode, cudaStream_t stream) {
 
 }  // namespace
 
-// variant: 0 default: FAST sincos and a channel count that fills >= 3/4 of its 16-channel
-//            blocks -> tensor-core kernel (gridder_tc.cu); otherwise the FP32 kernel (= variant 10)
+// variant: 0 default: FAST sincos and a shape that fills >= 3/4 of its 8-channel blocks and
+//            128-pixel tiles -> tensor-core kernel (= variant 12, gridder_tc.cu); otherwise the
+//            FP32 kernel (= variant 10)
 //         10 FP32 kernel: swizzled FFMA2; 128 threads x 8 pixels (x 4 blocks/SM) when the
 //            subgrid has >= 1024 pixels, 128 x 4 below that
-//         11 tensor-core kernel (FAST sincos only)
+//         11 tensor-core kernel (FAST sincos only), every phasor by MUFU
+//         12 tensor-core kernel, 4 of every 16 channels' phasors by FP32 polynomial (13: 5, 14: 6, 15: 8)
 //          1 scalar-FFMA baseline (256 x 4)
 //          2 swizzled FFMA2, 256 threads x 4 pixels
 //          3 swizzled FFMA2, 256 threads x 8 pixels
@@ -363,19 +365,18 @@ cudaError_t launch_gridder(const KernelArgs &a, int sincos_mode, int variant, cu
   if (a.nr_subgrids == 0) return cudaSuccess;
   const int npix = a.subgrid_size * a.subgrid_size;
   if (variant == 0) {
-    const int ncb = (a.nr_channels + 15) / 16;
-    const bool tc = sincos_mode == IDGB200_SINCOS_FAST && 4 * a.nr_channels >= 3 * ncb * 16;
-    variant = tc ? 11 : 10;
+    // the tensor kernel pads the channels to blocks of 8 (K = 16) and the pixels to tiles of 128
+    const int ncb = (a.nr_channels + 7) / 8, tiles = (npix + 127) / 128;
+    const bool tc = sincos_mode == IDGB200_SINCOS_FAST && 4 * a.nr_channels >= 3 * ncb * 8 &&
+                    4 * npix >= 3 * tiles * 128;
+    variant = tc ? 12 : 10;
   }
   switch (variant) {
     case 10:
       return npix >= 1024 ? launch_t<128, 8, 3, 4>(a, sincos_mode, stream)
                           : launch_t<128, 4, 3, 4>(a, sincos_mode, stream);
-    case 11: case 12: case 13: case 14: case 15:   // 12..15: part of the phasors by FP32 polynomial
+    case 11: case 12: case 13: case 14: case 15:   // 12..15: 4, 5, 6, 8 of 16 phasors by FP32 polynomial
       return sincos_mode == IDGB200_SINCOS_FAST ? launch_gridder_tc(a, variant - 11, stream)
-                                                : cudaErrorInvalidValue;
-    case 16: case 17: case 18: case 19: case 20: case 21:   // self-issuing producer warps
-      return sincos_mode == IDGB200_SINCOS_FAST ? launch_gridder_tc2(a, variant - 16, stream)
                                                 : cudaErrorInvalidValue;
     case 1: return launch_t<256, 4, 1, 2>(a, sincos_mode, stream);
     case 2: return launch_t<256, 4, 3, 2>(a, sincos_mode, stream);

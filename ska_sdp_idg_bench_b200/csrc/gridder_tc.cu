@@ -5,27 +5,31 @@
 // (profiles/r01_tc_*.log): the FP32 kernel (gridder.cu) is bound by the
 // dispatch port at ~26 cycles per (pixel, timestep, channel) item, of which 16 are the
 // complex multiply-adds; moving those onto the tensor pipe leaves 2 MUFU + 3 FP32-pipe
-// instructions per item, i.e. the XU (16 cycles/item) becomes the roof.
+// instructions per item, i.e. the XU (17.3 cycles/item, tools/xu_mix.cu) becomes the roof.
 //
-//   D[pixel][n] += A[pixel][k] * B[k][n]           one CTA = one slab of <= 512 pixels
-//     k = (visibility v, {cos, sin})                  A: fp16 phasors, produced by MUFU
+//   D[pixel][n] += A[pixel][k] * B[k][n]           one CTA = one slab of <= 8 tiles x 128 pixels
+//     k = (visibility v, {cos, sin})                  A: fp16 phasors, produced by MUFU / FP32 polynomial
 //     n = (hi|lo, pol, re|im)  -> N = 16              B: visibilities split into fp16 hi + lo
 //       B[(v,cos)][re,pol] =  vr    B[(v,sin)][re,pol] = -vi
 //       B[(v,cos)][im,pol] =  vi    B[(v,sin)][im,pol] =  vr
-//     D: fp32 accumulators in TMEM, <= 4 tiles x 16 columns; hi and lo columns are added in
+//     D: fp32 accumulators in TMEM, 16 columns per tile; hi and lo columns are added in
 //        the epilogue, so the visibilities keep ~22 significant bits; the phasors are rounded
 //        to fp16 (11 bits: 2.4e-4 relative, better than TF32's 10), which adds ~6e-5 rel-RMS
 //        to the result - the same class as the fast-sincos error (tests: FAST tolerance only).
 //
-// Roles (warp specialised, no block-wide barrier in the main loop):
-//   8 producer warps: warp w owns rows (w&1)*64 + lane + 32 j (j = 0,1) of tile w>>1; per stage
-//     (timestep, block of 16 channels) each thread makes 32 phasors: phase exactly as in the
-//     FP32 kernel (bit-identical angle), __sincosf, pack to half2, one 16-byte st.shared per
-//     4 visibilities into the K-major, no-swizzle core-matrix layout; then fence.proxy.async +
-//     mbarrier arrive on full[stage];
-//   1 MMA warp: builds the 1 KB B operand of the stage (raw visibilities prefetched one stage
-//     ahead), waits full[stage], one lane issues <= 8 tcgen05.mma (M=128, N=16, K=16, fp16 in,
-//     fp32 out) and commits them to empty[stage];
+// Every producer warp is its own pipeline (no block-wide or cross-warp barrier in the main loop):
+//   producer warp w owns the whole 128-pixel tile w (rows lane + 32 j, j = 0..3).  Per stage =
+//     (timestep, block of 8 channels) each thread makes 32 phasors: phase exactly as in the FP32
+//     kernel (bit-identical angle), __sincosf or the polynomial, pack to half2, one 16-byte
+//     st.shared per 4 visibilities into the K-major, no-swizzle core-matrix layout; then
+//     fence.proxy.async, and one elected lane of the same warp issues the tcgen05.mma of the stage
+//     (M=128, N=16, K=16, fp16 in, fp32 out) and commits it to the warp's private empty barrier.
+//     A producer only ever waits for its own MMA of two stages ago, which has long retired.
+//     (The first version of this kernel - one MMA warp, one full[] barrier per stage for all
+//     producers - spent 29 % of its issue slots in try_wait spins that share the MIO queue with
+//     the MUFUs: profiles/r01_tc_gen1_ncu.txt; this layout runs the XU at 85 %.)
+//   B builder warp: the only shared state is the B operand, a 16-slot ring (8 KB) released half a
+//     ring at a time by tcgen05.commit from every tile;
 //   epilogue: tcgen05.ld of the accumulators (a warp can only read its own 32-lane quadrant),
 //     A-terms, taper, coalesced stores - identical math to gridder.cu.
 // Every mbarrier wait is bounded (trap instead of hang).
@@ -38,20 +42,15 @@ namespace idgb200 {
 
 namespace {
 
-constexpr int TC_TILES = 4;                                // M-tiles (128 pixels) per CTA
-constexpr int TC_PRODUCER_WARPS = 2 * TC_TILES;
-constexpr int TC_THREADS = (TC_PRODUCER_WARPS + 1) * 32;   // + 1 MMA warp
-constexpr int TC_CB = 16;                                  // channels per stage -> K = 32
-constexpr int A_CHUNK_BYTES = 128 * 16;                    // one 16-byte K-chunk (4 vis) of 128 rows
-constexpr int A_TILE_BYTES = 4 * A_CHUNK_BYTES;
-constexpr int A_STAGE_BYTES = TC_TILES * A_TILE_BYTES;     // 32 KB
+constexpr int A_CHUNK_BYTES = 128 * 16;          // one 16-byte K-chunk (4 vis) of 128 rows
 constexpr int B_CHUNK_BYTES = 16 * 16;
-constexpr int B_STAGE_BYTES = 4 * B_CHUNK_BYTES;           // 1 KB
-#ifndef IDGB200_TC_STAGES
-#define IDGB200_TC_STAGES 2
-#endif
-constexpr int TC_STAGES = IDGB200_TC_STAGES;
-constexpr int TC_TMEM_COLS = 64;                           // 4 tiles x 16 columns (power of two >= 32)
+constexpr int T2_MAX_TILES = 8;                  // M-tiles (128 pixels) = producer warps per CTA
+constexpr int T2_CB = 8;                         // channels per stage -> K = 16
+constexpr int T2_A_STAGE = 2 * A_CHUNK_BYTES;    // 4 KB per tile and stage
+constexpr int T2_STAGES = 2;
+constexpr int T2_B_SLOT = 2 * B_CHUNK_BYTES;     // 512 B
+constexpr int T2_NB = 16;                        // B ring slots
+constexpr int T2_THREADS = (T2_MAX_TILES + 1) * 32;
 
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 
@@ -82,6 +81,11 @@ __device__ __forceinline__ void umma_f16(unsigned tmem_d, unsigned long long da,
                "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
                ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
 }
+__device__ __forceinline__ bool elect_one() {
+  unsigned pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void umma_commit(unsigned long long *bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -107,273 +111,8 @@ __device__ __forceinline__ float2 phasor_poly(float t /* revolutions */) {
   return make_float2(c, __fmul_rn(sn, r));
 }
 
-// POLY_MASK: bit c set -> channel c of every 16-channel block uses phasor_poly instead of MUFU
-template <unsigned POLY_MASK>
-__global__ void __launch_bounds__(TC_THREADS, TC_STAGES == 2 ? 3 : 2)
-gridder_tc_kernel(const KernelArgs a, const int slabs) {
-  extern __shared__ __align__(1024) unsigned char smem[];
-  unsigned char *sA = smem;
-  unsigned char *sB = sA + TC_STAGES * A_STAGE_BYTES;
-  unsigned long long *full = reinterpret_cast<unsigned long long *>(sB + TC_STAGES * B_STAGE_BYTES);
-  unsigned long long *empty = full + TC_STAGES;
-  unsigned long long *done = empty + TC_STAGES;
-  unsigned *s_tmem = reinterpret_cast<unsigned *>(done + 1);
-  float *s_red = reinterpret_cast<float *>(s_tmem + 2);     // [12] block reduction scratch + scale
-  float *s_wn = s_red + 12;                                 // [ncb * 16], zero padded
-
-  const int N = a.subgrid_size, C = a.nr_channels, npix = N * N;
-  const int s_local = blockIdx.x / slabs;
-  const int slab = blockIdx.x - s_local * slabs;
-  const int s = a.subgrid_offset + s_local;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int pix0 = slab * (TC_TILES * 128);
-  const int ntiles = min(TC_TILES, (npix - pix0 + 127) / 128);
-
-  const SubgridCtx ctx = load_ctx(a, s);
-  const int nt = ctx.nr_timesteps;
-  const int ncb = (C + TC_CB - 1) / TC_CB;
-  const int nstages = nt * ncb;
-
-  for (int c = tid; c < ncb * TC_CB; c += TC_THREADS) s_wn[c] = c < C ? a.wavenumbers[c] : 0.f;
-  if (tid == 0) {
-    for (int i = 0; i < TC_STAGES; i++) {
-      mbar_init(&full[i], TC_PRODUCER_WARPS * 32);
-      mbar_init(&empty[i], 1);
-    }
-    mbar_init(done, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(TC_TMEM_COLS));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
-  }
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const unsigned tmem_base = *s_tmem;
-
-  const float *g_uvw = reinterpret_cast<const float *>(a.uvw) + (size_t)ctx.time_offset * 3;
-  const float2 *g_vis = a.visibilities + (size_t)ctx.time_offset * C * NR_POL;
-
-  // fp16 has 5 exponent bits: scale this subgrid's visibilities by a power of two so that the
-  // largest component lands in [2^13, 2^14) (exact; undone in the epilogue).  The pass reads the
-  // bytes the main loop reads anyway (64 KB at the default shape, ~1 % of the CTA's time).
-  {
-    float amax = 0.f;
-    const float4 *v4 = reinterpret_cast<const float4 *>(g_vis);
-    for (int i = tid; i < nt * C * 2; i += TC_THREADS) {
-      const float4 q = __ldg(&v4[i]);
-      amax = fmaxf(fmaxf(amax, fmaxf(fabsf(q.x), fabsf(q.y))), fmaxf(fabsf(q.z), fabsf(q.w)));
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
-    if (lane == 0) s_red[warp] = amax;
-    __syncthreads();
-    if (tid == 0) {
-      for (int i = 1; i <= TC_PRODUCER_WARPS; i++) amax = fmaxf(amax, s_red[i]);
-      const unsigned eb = (__float_as_uint(amax) >> 23) & 0xffu;          // biased exponent
-      const bool ok = eb >= 14u && eb <= 253u;                             // finite, not tiny
-      s_red[10] = ok ? __uint_as_float((267u - eb) << 23) : 1.f;           // 2^(13 - E)
-      s_red[11] = ok ? __uint_as_float((eb - 13u) << 23) : 1.f;            // 2^(E - 13)
-    }
-    __syncthreads();
-  }
-  const float vis_scale = s_red[10], vis_unscale = s_red[11];
-
-  if (warp < TC_PRODUCER_WARPS) {
-    // ------------------------------------------------------------------ producers
-    const int tile = warp >> 1;
-    const bool active = tile < ntiles;
-    float l[2], m[2], n[2], off[2], offr[2];
-    int row[2];
-#pragma unroll
-    for (int j = 0; j < 2; j++) {
-      row[j] = (warp & 1) * 64 + lane + 32 * j;
-      const int q = min(pix0 + tile * 128 + row[j], npix - 1);
-      const int y = q / N, x = q - y * N;
-      l[j] = compute_l(x, N, a.image_size);
-      m[j] = compute_l(y, N, a.image_size);
-      n[j] = compute_n(l[j], m[j]);
-      // gridder_reference.cpp:64 as the CPU binary contracts it
-      off[j] = __fmaf_rn(ctx.w_offset, n[j], __fmaf_rn(ctx.u_offset, l[j], __fmul_rn(ctx.v_offset, m[j])));
-      offr[j] = __fmul_rn(off[j], 0.15915494309189535f);
-    }
-    float un = 0.f, vn = 0.f, wnx = 0.f;   // uvw of the next timestep, fetched one stage ahead
-    if (nt > 0) { un = __ldg(&g_uvw[0]); vn = __ldg(&g_uvw[1]); wnx = __ldg(&g_uvw[2]); }
-    int k = 0;
-    for (int t = 0; t < nt; t++) {
-      const float u = un, v = vn, w = wnx;
-      if (t + 1 < nt) { un = __ldg(&g_uvw[3 * t + 3]); vn = __ldg(&g_uvw[3 * t + 4]); wnx = __ldg(&g_uvw[3 * t + 5]); }
-      float idx[2], idxr[2];
-#pragma unroll
-      for (int j = 0; j < 2; j++) {  // gridder_reference.cpp:61 as contracted by the CPU binary
-        idx[j] = __fmaf_rn(w, n[j], __fmaf_rn(u, l[j], __fmul_rn(v, m[j])));
-        idxr[j] = __fmul_rn(idx[j], 0.15915494309189535f);   // in revolutions, for phasor_poly
-      }
-      for (int cb = 0; cb < ncb; cb++, k++) {
-        const int stage = k % TC_STAGES, use = k / TC_STAGES;
-        if (use >= 1) mbar_wait(&empty[stage], (use - 1) & 1);
-        if (active) {
-          unsigned char *A = sA + stage * A_STAGE_BYTES + tile * A_TILE_BYTES;
-          const float4 *wn4 = reinterpret_cast<const float4 *>(s_wn + cb * TC_CB);
-#pragma unroll
-          for (int kc = 0; kc < 4; kc++) {
-            const float4 wq = wn4[kc];
-            const float wn[4] = {wq.x, wq.y, wq.z, wq.w};
-#pragma unroll
-            for (int j = 0; j < 2; j++) {
-              unsigned pk[4];
-#pragma unroll
-              for (int i = 0; i < 4; i++) {
-                const float2 ph = ((POLY_MASK >> (kc * 4 + i)) & 1u)
-                                      ? phasor_poly(__fmaf_rn(-idxr[j], wn[i], offr[j]))
-                                      : phasor<IDGB200_SINCOS_FAST>(__fmaf_rn(-idx[j], wn[i], off[j]));  // :69
-                const __half2 hh = __floats2half2_rn(ph.x, ph.y);
-                pk[i] = *reinterpret_cast<const unsigned *>(&hh);
-              }
-              *reinterpret_cast<uint4 *>(A + kc * A_CHUNK_BYTES + row[j] * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-            }
-          }
-          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        }
-        mbar_arrive(&full[stage]);
-      }
-    }
-  } else {
-    // ------------------------------------------------------------------ MMA warp
-    // instruction descriptor (cute::UMMA::InstrDescriptor): D = F32 [4,6) = 1, A = B = F16 (0),
-    // both K-major (0), N >> 3 at [17,23), M >> 4 at [24,29)
-    const unsigned idesc = (1u << 4) | ((16u >> 3) << 17) | ((128u >> 4) << 24);
-    // a lane builds two of the 64 16-byte chunks of B: chunk = (kc, n), n = (hi|lo, pol, re|im)
-    auto load_b = [&](int kk, float2 (&raw)[2][4]) {
-      const int t = kk / ncb, cb = kk - t * ncb;
-#pragma unroll
-      for (int h2 = 0; h2 < 2; h2++) {
-        const int chunk = lane + 32 * h2, nrow = chunk & 15, kc = chunk >> 4, p = (nrow >> 1) & 3;
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-          const int c = cb * TC_CB + kc * 4 + i;
-          raw[h2][i] = c < C ? __ldg(&g_vis[((size_t)t * C + c) * NR_POL + p]) : make_float2(0.f, 0.f);
-        }
-      }
-    };
-    float2 raw[2][4];
-    if (nstages > 0) load_b(0, raw);
-    for (int k = 0; k < nstages; k++) {
-      const int stage = k % TC_STAGES, use = k / TC_STAGES;
-      if (use >= 1) mbar_wait(&empty[stage], (use - 1) & 1);
-      unsigned char *B = sB + stage * B_STAGE_BYTES;
-#pragma unroll
-      for (int h2 = 0; h2 < 2; h2++) {
-        const int chunk = lane + 32 * h2, nrow = chunk & 15, kc = chunk >> 4, lo = nrow >> 3, im = nrow & 1;
-        unsigned pk[4];
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-          const float2 vv = raw[h2][i];
-          const float x0 = (im ? vv.y : vv.x) * vis_scale;    // multiplies cos
-          const float x1 = (im ? vv.x : -vv.y) * vis_scale;   // multiplies sin
-          __half h0 = __float2half_rn(x0), h1 = __float2half_rn(x1);
-          if (lo) {
-            h0 = __float2half_rn(x0 - __half2float(h0));
-            h1 = __float2half_rn(x1 - __half2float(h1));
-          }
-          pk[i] = (unsigned)__half_as_ushort(h0) | ((unsigned)__half_as_ushort(h1) << 16);
-        }
-        *reinterpret_cast<uint4 *>(B + kc * B_CHUNK_BYTES + nrow * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-      }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      __syncwarp();
-      if (k + 1 < nstages) load_b(k + 1, raw);
-      if (lane == 0) {
-        mbar_wait(&full[stage], use & 1);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const unsigned a_base = smem_u32(sA + stage * A_STAGE_BYTES), b_base = smem_u32(B);
-        for (int tile = 0; tile < ntiles; tile++)
-#pragma unroll
-          for (int kh = 0; kh < 2; kh++) {
-            const unsigned long long da =
-                smem_desc(a_base + tile * A_TILE_BYTES + kh * 2 * A_CHUNK_BYTES, A_CHUNK_BYTES, 128);
-            const unsigned long long db = smem_desc(b_base + kh * 2 * B_CHUNK_BYTES, B_CHUNK_BYTES, 128);
-            umma_f16(tmem_base + tile * 16, da, db, idesc, (k > 0 || kh > 0) ? 1u : 0u);
-          }
-        umma_commit(&empty[stage]);
-        if (k == nstages - 1) umma_commit(done);
-      }
-      __syncwarp();
-    }
-  }
-
-  // ---- epilogue (producer warps): accumulators -> A-terms, taper, store (gridder_reference.cpp:84-110)
-  if (warp < TC_PRODUCER_WARPS) {
-    if (nstages > 0) {
-      mbar_wait(done, 0);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    }
-    const size_t plane = (size_t)npix;
-    const size_t at1 = ((size_t)ctx.aterm_index * a.nr_stations + ctx.station1) * plane;
-    const size_t at2 = ((size_t)ctx.aterm_index * a.nr_stations + ctx.station2) * plane;
-    float2 *out = const_cast<float2 *>(a.subgrids) + (size_t)s * NR_POL * plane;
-    const int q4 = warp & 3;   // a warp reads TMEM lanes 32 (warp % 4) .. +31
-    for (int tile = warp >> 2; tile < ntiles; tile += TC_PRODUCER_WARPS / 4) {
-      unsigned r[16];
-      if (nstages > 0) {
-        const unsigned taddr = tmem_base + ((unsigned)(q4 * 32) << 16) + tile * 16;
-        asm volatile(
-            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-              "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-            : "r"(taddr));
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      } else {
-#pragma unroll
-        for (int i = 0; i < 16; i++) r[i] = 0u;
-      }
-      const int pixel = pix0 + tile * 128 + q4 * 32 + lane;
-      if (pixel < npix) {
-        float2 px[NR_POL];
-#pragma unroll
-        for (int p = 0; p < NR_POL; p++)
-          px[p] = make_float2((__uint_as_float(r[2 * p]) + __uint_as_float(r[8 + 2 * p])) * vis_unscale,
-                              (__uint_as_float(r[2 * p + 1]) + __uint_as_float(r[8 + 2 * p + 1])) * vis_unscale);
-        float2 a1[4], a2[4];
-        load_jones(a.aterms, (at1 + pixel) * NR_POL, a1);
-        load_jones(a.aterms, (at2 + pixel) * NR_POL, a2);
-        apply_aterm_gridder(px, a1, a2);
-        const float sph = __ldg(&a.spheroidal[pixel]);
-#pragma unroll
-        for (int p = 0; p < NR_POL; p++)
-          out[p * plane + pixel] = make_float2(__fmul_rn(px[p].x, sph), __fmul_rn(px[p].y, sph));
-      }
-    }
-  }
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  if (warp == 0)
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TC_TMEM_COLS));
-}
-
-// ---------------------------------------------------------------------------------------------
-// Second generation: every producer warp is its own pipeline.
-//
-// The kernel above couples all 8 producer warps of a CTA through one full[] barrier per stage
-// and a 2-deep ring, and ncu shows what that costs (profiles/r01_tc_gridder_ncu.txt): 29 % of the
-// issued instructions are try_wait spins on empty[], and they travel through the same MIO queue
-// as the MUFUs that bound the kernel.  Here a warp owns a whole 128-pixel tile (4 rows per lane),
-// produces one (timestep, 8 channels) K=16 slice of it, and its own lane 0 issues the
-// tcgen05.mma for that slice and commits it to the warp's private empty barrier - a producer only
-// ever waits for its own MMA of two stages ago, which has long retired.  The only shared state
-// is the B operand: a 16-slot ring (8 KB) filled by one builder warp, released half a ring at a
-// time by tcgen05.commit from every tile.
-constexpr int T2_MAX_TILES = 8;
-constexpr int T2_CB = 8;                         // channels per stage -> K = 16
-constexpr int T2_A_STAGE = 2 * A_CHUNK_BYTES;    // 4 KB per tile and stage
-constexpr int T2_STAGES = 2;
-constexpr int T2_B_SLOT = 2 * B_CHUNK_BYTES;     // 512 B
-constexpr int T2_NB = 16;                        // B ring slots
-constexpr int T2_THREADS = (T2_MAX_TILES + 1) * 32;
-
 template <unsigned MASK8>
-__device__ __forceinline__ void tc2_produce(unsigned char *A, const float *wn8, const float (&idx)[4],
+__device__ __forceinline__ void tc_produce(unsigned char *A, const float *wn8, const float (&idx)[4],
                                             const float (&idxr)[4], const float (&off)[4],
                                             const float (&offr)[4], const int lane) {
 #pragma unroll
@@ -399,13 +138,14 @@ __device__ __forceinline__ void tc2_produce(unsigned char *A, const float *wn8, 
 // MASK16: bit c set -> channel c of every 16-channel group uses phasor_poly instead of MUFU
 template <unsigned MASK16>
 __global__ void __launch_bounds__(T2_THREADS, 3)
-gridder_tc2_kernel(const KernelArgs a, const int slabs, const int tiles_per_cta, const int tmem_cols) {
+gridder_tc_kernel(const KernelArgs a, const int slabs, const int tiles_per_cta, const int tmem_cols) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const int N = a.subgrid_size, C = a.nr_channels, npix = N * N;
   const int s_local = blockIdx.x / slabs;
   const int slab = blockIdx.x - s_local * slabs;
   const int s = a.subgrid_offset + s_local;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);     // warp-uniform for the compiler too
   const int nwarps = blockDim.x >> 5, NW = nwarps - 1;        // producer warps; warp NW builds B
   const int pix0 = slab * tiles_per_cta * 128;
   const int ntiles = min(tiles_per_cta, (npix - pix0 + 127) / 128);
@@ -491,6 +231,9 @@ gridder_tc2_kernel(const KernelArgs a, const int slabs, const int tiles_per_cta,
       }
       unsigned char *A_tile = sA + tile * T2_STAGES * T2_A_STAGE;
       unsigned long long *my_empty = aempty + tile * T2_STAGES;
+      const unsigned long long da0 = smem_desc(smem_u32(A_tile), A_CHUNK_BYTES, 128);
+      const unsigned long long db0 = smem_desc(smem_u32(sB), B_CHUNK_BYTES, 128);
+      const unsigned tmem_d = tmem_base + tile * 16;
       float un = 0.f, vn = 0.f, wnx = 0.f;   // uvw of the next timestep, fetched one timestep ahead
       if (nt > 0) { un = __ldg(&g_uvw[0]); vn = __ldg(&g_uvw[1]); wnx = __ldg(&g_uvw[2]); }
       int k = 0;
@@ -508,18 +251,19 @@ gridder_tc2_kernel(const KernelArgs a, const int slabs, const int tiles_per_cta,
           if (use >= 1) mbar_wait(&my_empty[stage], (use - 1) & 1);
           unsigned char *A = A_tile + stage * T2_A_STAGE;
           if ((MASK16 >> 8) == (MASK16 & 0xffu) || !(cb & 1))
-            tc2_produce<(MASK16 & 0xffu)>(A, s_wn + cb * T2_CB, idx, idxr, off, offr, lane);
+            tc_produce<(MASK16 & 0xffu)>(A, s_wn + cb * T2_CB, idx, idxr, off, offr, lane);
           else
-            tc2_produce<(MASK16 >> 8)>(A, s_wn + cb * T2_CB, idx, idxr, off, offr, lane);
+            tc_produce<(MASK16 >> 8)>(A, s_wn + cb * T2_CB, idx, idxr, off, offr, lane);
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          // the whole warp waits for the B slot (one SYNCS either way) and stays converged, so the
+          // descriptors live in uniform registers and one elected lane issues MMA + commits
+          const int slot = k % T2_NB;
+          mbar_wait(&bfull[slot], (k / T2_NB) & 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           __syncwarp();
-          if (lane == 0) {
-            const int slot = k % T2_NB;
-            mbar_wait(&bfull[slot], (k / T2_NB) & 1);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const unsigned long long da = smem_desc(smem_u32(A), A_CHUNK_BYTES, 128);
-            const unsigned long long db = smem_desc(smem_u32(sB + slot * T2_B_SLOT), B_CHUNK_BYTES, 128);
-            umma_f16(tmem_base + tile * 16, da, db, idesc, k > 0 ? 1u : 0u);
+          if (elect_one()) {
+            umma_f16(tmem_d, da0 + (unsigned long long)(stage * (T2_A_STAGE >> 4)),
+                     db0 + (unsigned long long)(slot * (T2_B_SLOT >> 4)), idesc, k > 0 ? 1u : 0u);
             umma_commit(&my_empty[stage]);
             if ((k & 7) == 7) umma_commit(&bempty[(k >> 3) & 1]);
             if (k == nstages - 1) umma_commit(done);
@@ -619,32 +363,8 @@ gridder_tc2_kernel(const KernelArgs a, const int slabs, const int tiles_per_cta,
 }  // namespace
 
 // FAST sincos only: the fp16 phasor operand is a FAST-class approximation.
-// poly: 0 = all phasors by MUFU; 1..4 = 5, 6, 7, 4 of every 16 channels by polynomial
+// poly: 0 = all phasors by MUFU; 1..4 = 4, 5, 6, 8 of every 16 channels by FP32 polynomial
 cudaError_t launch_gridder_tc(const KernelArgs &a, int poly, cudaStream_t stream) {
-  if (a.nr_subgrids == 0) return cudaSuccess;
-  const int npix = a.subgrid_size * a.subgrid_size;
-  const int slabs = (npix + TC_TILES * 128 - 1) / (TC_TILES * 128);
-  const int ncb = (a.nr_channels + TC_CB - 1) / TC_CB;
-  const size_t smem = (size_t)TC_STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + (2 * TC_STAGES + 1) * 8 + 8 + 48 +
-                      (size_t)ncb * TC_CB * 4;
-  if (smem > 200 * 1024) return cudaErrorInvalidValue;
-  void (*k)(const KernelArgs, int) = nullptr;
-  switch (poly) {
-    case 0: k = gridder_tc_kernel<0x0000u>; break;
-    case 1: k = gridder_tc_kernel<0x2492u>; break;   // 5 of 16: channels 1,4,7,10,13
-    case 2: k = gridder_tc_kernel<0x4A52u>; break;   // 6 of 16: 1,4,6,9,11,14
-    case 3: k = gridder_tc_kernel<0x5552u>; break;   // 7 of 16: 1,4,6,8,10,12,14
-    case 4: k = gridder_tc_kernel<0x4444u>; break;   // 4 of 16: 2,6,10,14
-    default: return cudaErrorInvalidValue;
-  }
-  cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
-  k<<<dim3((unsigned)a.nr_subgrids * slabs), dim3(TC_THREADS), smem, stream>>>(a, slabs);
-  return cudaGetLastError();
-}
-
-// second-generation kernel (self-issuing producer warps); poly as above
-cudaError_t launch_gridder_tc2(const KernelArgs &a, int poly, cudaStream_t stream) {
   if (a.nr_subgrids == 0) return cudaSuccess;
   const int npix = a.subgrid_size * a.subgrid_size;
   const int tiles_total = (npix + 127) / 128;
@@ -660,12 +380,11 @@ cudaError_t launch_gridder_tc2(const KernelArgs &a, int poly, cudaStream_t strea
   if (smem > 200 * 1024) return cudaErrorInvalidValue;
   void (*k)(const KernelArgs, int, int, int) = nullptr;
   switch (poly) {
-    case 0: k = gridder_tc2_kernel<0x0000u>; break;
-    case 1: k = gridder_tc2_kernel<0x2492u>; break;   // 5 of 16: channels 1,4,7,10,13
-    case 2: k = gridder_tc2_kernel<0x4A52u>; break;   // 6 of 16: 1,4,6,9,11,14
-    case 3: k = gridder_tc2_kernel<0x5252u>; break;   // 6 of 16, 3 per half: 1,4,6 | 9,12,14
-    case 4: k = gridder_tc2_kernel<0x4444u>; break;   // 4 of 16: 2,6,10,14
-    case 5: k = gridder_tc2_kernel<0x5555u>; break;   // 8 of 16
+    case 0: k = gridder_tc_kernel<0x0000u>; break;
+    case 1: k = gridder_tc_kernel<0x4444u>; break;   // 4 of 16: channels 2,6,10,14
+    case 2: k = gridder_tc_kernel<0x2492u>; break;   // 5 of 16: 1,4,7,10,13
+    case 3: k = gridder_tc_kernel<0x5252u>; break;   // 6 of 16: 1,4,6 | 9,12,14
+    case 4: k = gridder_tc_kernel<0x5555u>; break;   // 8 of 16
     default: return cudaErrorInvalidValue;
   }
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -12,6 +12,5 @@ cudaError_t launch_degridder(const KernelArgs &a, int sincos_mode, int variant, 
 
 // tcgen05 / TMEM gridder (gridder_tc.cu); FAST sincos only
 cudaError_t launch_gridder_tc(const KernelArgs &a, int poly, cudaStream_t stream);
-cudaError_t launch_gridder_tc2(const KernelArgs &a, int poly, cudaStream_t stream);
 
 }  // namespace idgb200
