@@ -218,6 +218,9 @@ cudaError_t launch_degridder(const KernelArgs &a, int sincos_mode, int variant, 
     case 1: return launch_t<256, 4, 1, 2>(a, sincos_mode, stream);
     case 2: return launch_t<256, 4, 3, 3>(a, sincos_mode, stream);
     case 3: return launch_t<128, 8, 3, 3>(a, sincos_mode, stream);
+    case 11: case 12: case 13: case 14:   // tensor-core kernel; 12..14: 2, 3, 4 of 8 pixels by FP32 polynomial
+      return sincos_mode == IDGB200_SINCOS_FAST ? launch_degridder_tc(a, variant - 11, stream)
+                                                : cudaErrorInvalidValue;
     default: return cudaErrorInvalidValue;
   }
 }

@@ -37,13 +37,12 @@
 
 #include "common.cuh"
 #include "kernels.h"
+#include "tc_common.cuh"
 
 namespace idgb200 {
 
 namespace {
 
-constexpr int A_CHUNK_BYTES = 128 * 16;          // one 16-byte K-chunk (4 vis) of 128 rows
-constexpr int B_CHUNK_BYTES = 16 * 16;
 constexpr int T2_MAX_TILES = 8;                  // M-tiles (128 pixels) = producer warps per CTA
 constexpr int T2_CB = 8;                         // channels per stage -> K = 16
 constexpr int T2_A_STAGE = 2 * A_CHUNK_BYTES;    // 4 KB per tile and stage
@@ -51,65 +50,6 @@ constexpr int T2_STAGES = 2;
 constexpr int T2_B_SLOT = 2 * B_CHUNK_BYTES;     // 512 B
 constexpr int T2_NB = 16;                        // B ring slots
 constexpr int T2_THREADS = (T2_MAX_TILES + 1) * 32;
-
-__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
-  unsigned done = 0;
-  for (int spin = 0; !done; spin++) {
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                 : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-    if (spin > (1 << 22)) __trap();   // a lost arrival must fail loudly, not hang the GPU
-  }
-}
-// cute::UMMA::SmemDescriptor (cute/arch/mma_sm100_desc.hpp): start[0,14) LBO[16,30) SBO[32,46),
-// all >> 4; version[46,48) = 1; layout[61,64) = 0 (no swizzle).  K-major canonical layout:
-// 8 rows x 16 B core matrices; SBO = distance of 8-row groups, LBO = distance of 16-byte K chunks.
-__device__ __forceinline__ unsigned long long smem_desc(unsigned addr, unsigned lbo, unsigned sbo) {
-  return (unsigned long long)((addr >> 4) & 0x3FFF) | ((unsigned long long)((lbo >> 4) & 0x3FFF) << 16) |
-         ((unsigned long long)((sbo >> 4) & 0x3FFF) << 32) | (1ull << 46);
-}
-__device__ __forceinline__ void umma_f16(unsigned tmem_d, unsigned long long da, unsigned long long db,
-                                         unsigned idesc, unsigned accumulate) {
-  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-               "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-               ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ bool elect_one() {
-  unsigned pred;
-  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
-  return pred != 0;
-}
-__device__ __forceinline__ void umma_commit(unsigned long long *bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-
-// sin / cos of 2 pi r, |r| <= 0.5, on the FP32 pipe: the tensor-core kernel leaves that pipe idle
-// while the XU (2 MUFU per item) is the roof, so a compile-time subset of the channels of every
-// 16-channel block gets its phasor from these polynomials instead (near-minimax fits, max error
-// 6.4e-6 / 4.1e-5 in fp32 - below the fp16 rounding of the operand), after an exact
-// round-to-nearest range reduction in revolutions.  Cost: 14 FP32-pipe instructions per item
-// against FFMA + FMUL + 2 MUFU.
-__device__ __forceinline__ float2 phasor_poly(float t /* revolutions */) {
-  const float k = __fadd_rn(__fadd_rn(t, 12582912.0f), -12582912.0f);   // rint(t), |t| < 2^22
-  const float r = __fsub_rn(t, k);
-  const float x = __fmul_rn(r, r);
-  float c = __fmaf_rn(45.64655685424805f, x, -82.40354919433594f);
-  c = __fmaf_rn(c, x, 64.67343139648438f);
-  c = __fmaf_rn(c, x, -19.731040954589844f);
-  c = __fmaf_rn(c, x, 0.9999597668647766f);
-  float sn = __fmaf_rn(32.7813835144043f, x, -74.47799682617188f);
-  sn = __fmaf_rn(sn, x, 81.36681365966797f);
-  sn = __fmaf_rn(sn, x, -41.331214904785156f);
-  sn = __fmaf_rn(sn, x, 6.283055782318115f);
-  return make_float2(c, __fmul_rn(sn, r));
-}
 
 template <unsigned MASK8>
 __device__ __forceinline__ void tc_produce(unsigned char *A, const float *wn8, const float (&idx)[4],

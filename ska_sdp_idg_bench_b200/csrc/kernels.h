@@ -12,5 +12,6 @@ cudaError_t launch_degridder(const KernelArgs &a, int sincos_mode, int variant, 
 
 // tcgen05 / TMEM gridder (gridder_tc.cu); FAST sincos only
 cudaError_t launch_gridder_tc(const KernelArgs &a, int poly, cudaStream_t stream);
+cudaError_t launch_degridder_tc(const KernelArgs &a, int poly, cudaStream_t stream);
 
 }  // namespace idgb200
