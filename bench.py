@@ -36,6 +36,10 @@ DEFAULT_SHAPE = dict(nr_stations=50, nr_timeslots=20, nr_timesteps=128, nr_chann
                      subgrid_size=32, grid_size=1024, image_size=0.01)
 SM_FP32_LANES = 128   # FP32 FMA lanes per SM (B200)
 SM_XU_LANES = 16      # MUFU lanes per SM
+# tensor-core gridder variants -> fraction of the phasors that come from the FP32 polynomial
+# instead of 2 MUFUs (gridder_tc.cu, launch_gridder_tc)
+TC_GRIDDER_POLY = {11: 0.0, 12: 4 / 16, 13: 5 / 16, 14: 6 / 16, 15: 8 / 16}
+TC_DEGRIDDER_POLY = {11: 0.0, 12: 2 / 8, 13: 3 / 8, 14: 4 / 8}
 
 
 # ----------------------------------------------------------------- shared helpers
@@ -315,11 +319,21 @@ def run_ours(args) -> None:
         sec = e0.elapsed_time(e1) * 1e-3
         return reduce_max_time(sec, dev), idg.launch_count() - l0
 
+    # which kernels variant 0 selects for this shape (idgb200_resolve_variant)
+    g_variant = idg.resolve_variant(N, C_, sincos, args.variant, gridder=True)
+    d_variant = idg.resolve_variant(N, C_, sincos, args.degridder_variant, gridder=False)
+
+    def step_gridder_fp32():
+        idg.gridder(*scal, *tens, sincos=sincos, variant=10)
+
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     sec_g, launches_g = timed(step_gridder, args.steps, args.warmup)
     sec_d, launches_d = timed(step_degridder, args.steps, args.warmup)
+    # the FP32/SFU gridder next to the tensor-core one (north_star: tensor cores only if they win)
+    sec_g32 = timed(step_gridder_fp32, args.steps, args.warmup)[0] if g_variant in TC_GRIDDER_POLY else None
+    step_gridder()   # leave the default kernel's result in prob["subgrids"] for the parity sample
     clocks = sampler.stop() if rank == 0 else {}
 
     # ---- e2e through the host-pointer C ABI, pinned host buffers
@@ -409,43 +423,72 @@ def run_ours(args) -> None:
         nbytes = idg.bytes_gridder(C_, tt, S, N)
         hbm_peak = float(peaks.get("hbm_gbs") or 6650.0)
 
-        def roof(sec, steps, traffic_per_subgrid):
+        def roof(sec, steps, traffic_per_subgrid, poly):
+            """poly None: FP32 kernel (bound = the FP32 issue port); else the tensor-core kernel,
+            whose MACs run on tcgen05 and whose roof is the XU (MUFU) pipe; poly = fraction of
+            the phasors computed by FP32 polynomial instead of MUFU."""
             t = sec / steps
             tf = flops / t * 1e-12
-            # dram bytes of one launch from the round-1 `ncu --set full` capture
-            # (profiles/r01_*_ncu_full.txt: 1740-subgrid launch, read+write 145.2 MB gridder /
-            # 128.3 MB degridder), scaled to this launch's subgrid count
-            r = {"bound": "fp32", "achieved": tf, "peak": p_fp32, "unit": "TFLOP/s",
-                 "frac": tf / p_fp32, "traffic": traffic_per_subgrid * S,
-                 "traffic_note": "DRAM bytes/launch from ncu on a 1740-subgrid launch, scaled by subgrid count; "
-                                 "algorithmic bytes (bytes_gridder) = %.3f GB/launch" % (nbytes * 1e-9),
-                 "bound_note": "CUDA-core FP32 bound (359 flop/B): neither HBM nor tensor is the roof",
-                 "peak_source": f"{sms} SMs x 128 FP32 lanes x 2 x {f_max:.0f} MHz (sm_max_mhz of "
-                                "MEASURED_PEAKS.json; the file holds no FP32 figure)",
-                 "kernel_ms": t * 1e3,
-                 "sfu_frac": 2.0 * N * N * (tt * C_) / t / p_xu,
-                 "hbm": {"achieved": nbytes / t * 1e-9, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": nbytes / t * 1e-9 / hbm_peak,
-                         "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks.get("hbm_gbs")
-                         else "fallback 6650"}}
+            items = float(N) * N * tt * C_                     # (pixel, visibility) pairs per launch
+            hbm = {"achieved": nbytes / t * 1e-9, "peak": hbm_peak, "unit": "GB/s",
+                   "frac": nbytes / t * 1e-9 / hbm_peak,
+                   "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks.get("hbm_gbs") else "fallback 6650"}
+            common = {"traffic": traffic_per_subgrid * S,
+                      "traffic_note": "DRAM bytes/launch (dram__bytes_read+write) from the ncu --set full capture "
+                                      "under profiles/, scaled by subgrid count; algorithmic bytes "
+                                      "(bytes_gridder) = %.3f GB/launch" % (nbytes * 1e-9),
+                      "kernel_ms": t * 1e3, "hbm": hbm,
+                      "fp32_model_tflops": tf, "fp32_model_frac": tf / p_fp32,
+                      "fp32_model_note": f"reference flop model (flops_gridder) / ({sms} SMs x 128 FP32 lanes x 2 x "
+                                         f"{f_max:.0f} MHz): the north_star's 'fraction of the FP32+SFU roofline'"}
+            if poly is None:
+                r = dict({"bound": "fp32", "achieved": tf, "peak": p_fp32, "unit": "TFLOP/s", "frac": tf / p_fp32,
+                          "bound_note": "CUDA-core FP32 issue bound (359 flop/B): neither HBM nor tensor is the roof",
+                          "peak_source": f"{sms} SMs x 128 FP32 lanes x 2 x {f_max:.0f} MHz (sm_max_mhz of "
+                                         "MEASURED_PEAKS.json; the file holds no FP32 figure)",
+                          "sfu_frac": 2.0 * items / t / p_xu}, **common)
+            else:
+                mufu = 2.0 * (1.0 - poly) * items / t          # MUFU.SIN + MUFU.COS actually executed per second
+                r = dict({"bound": "sfu", "achieved": mufu * 1e-12, "peak": p_xu * 1e-12, "unit": "TMUFU/s",
+                          "frac": mufu / p_xu,
+                          "bound_note": "tcgen05 kernel: the complex MACs run on the tensor pipe (~5 % busy), the "
+                                        "phasors bound it: 2 MUFU per (pixel, visibility) on the XU pipe, "
+                                        f"{poly:.3f} of them replaced by an FP32-pipe polynomial "
+                                        "(fp32_model_frac > 1 is the flop model's MACs having left the FP32 pipe)",
+                          "peak_source": f"{sms} SMs x 16 MUFU lanes x {f_max:.0f} MHz",
+                          "phasor_rate_frac": 2.0 * items / t / p_xu}, **common)
             if clocks.get("sm_mhz"):
-                r["frac_at_measured_clock"] = tf / (p_fp32 * clocks["sm_mhz"] / f_max)
+                r["frac_at_measured_clock"] = r["frac"] * f_max / clocks["sm_mhz"]
             return r
 
+        tc_g, tc_d = TC_GRIDDER_POLY.get(g_variant), TC_DEGRIDDER_POLY.get(d_variant)
         total_mvis = world * shape["mvis"]
         out = {
             "metric": "gridder_mvis_per_s", "value": total_mvis * args.steps / sec_g,
             "unit": "MVis/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": sec_g / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "vs_baseline": None,
+            "dtype": "f32 (phasors and accumulation), fp16 x fp16 -> f32 tcgen05 operands" if tc_g is not None
+                     else "f32",
+            "data": "synthetic",
             "config": dict(workload_config(shape, world), sincos=args.sincos,
-                           gridder_variant=args.variant, degridder_variant=args.degridder_variant),
+                           gridder_variant=g_variant, degridder_variant=d_variant,
+                           gridder_kernel=("tcgen05: fp16 phasor tile x fp16 hi+lo visibilities, f32 accumulate in "
+                                           "TMEM" if tc_g is not None else "FP32 FFMA2 + MUFU"),
+                           degridder_kernel=("tcgen05 (opt-in, outside the stated tolerance)" if tc_d is not None
+                                             else "FP32 FFMA2 + MUFU")),
             "tflops": world * flops * args.steps / sec_g * 1e-12,
-            "roofline": roof(sec_g, args.steps, 145.165e6 / 1740),
+            # ncu --set full, 3675-subgrid launches: 341.6 MB (tcgen05 gridder), FP32 kernels from the
+            # 1740-subgrid captures (profiles/)
+            "roofline": roof(sec_g, args.steps, 341.6e6 / 3675 if tc_g is not None else 145.165e6 / 1740, tc_g),
             "degridder": {"value": total_mvis * args.steps / sec_d, "unit": "MVis/s",
                           "ms_per_step": sec_d / args.steps * 1e3,
                           "tflops": world * flops * args.steps / sec_d * 1e-12,
-                          "roofline": roof(sec_d, args.steps, 128.329e6 / 1740)},
+                          "roofline": roof(sec_d, args.steps, 128.329e6 / 1740, tc_d)},
+            "gridder_fp32": None if sec_g32 is None else {
+                "value": total_mvis * args.steps / sec_g32, "unit": "MVis/s", "variant": 10,
+                "ms_per_step": sec_g32 / args.steps * 1e3,
+                "roofline": roof(sec_g32, args.steps, 145.165e6 / 1740, None)},
             "cpu_baseline": cpu_baseline, "parity": parity, "e2e": e2e,
             "gpu_launches": int(launches_g), "degridder_gpu_launches": int(launches_d),
             "clocks": clocks, "device": idg.device_name(),

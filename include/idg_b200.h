@@ -127,6 +127,13 @@ int idgb200_degridder(const idgb200_params *params, const idgb200_uvw *d_uvw,
  * (bench.py reports it as gpu_launches). */
 uint64_t idgb200_launch_count(void);
 
+/* The kernel variant params->variant == 0 resolves to for this shape and sincos
+ * mode (gridder != 0: the gridder, else the degridder); a non-zero variant is
+ * returned unchanged.  Gridder: 12 = tcgen05 kernel (FAST sincos, shapes that fill
+ * its tiles), 10 = FP32 kernel.  Degridder: 0 = FP32 kernel (the tcgen05 degridder,
+ * variants 11..14, is opt-in: DESIGN.md 4.6).  IDGB200_EINVAL on bad params. */
+int idgb200_resolve_variant(const idgb200_params *params, int gridder);
+
 /* ---- host-pointer API --------------------------------------------------------
  * Replaces cuda::c_run_gridder_ / c_run_degridder_ (app/CUDA/util.cpp:251-307,
  * 388-444): device allocation, host->device copies, the kernel, device->host

@@ -12,7 +12,7 @@ built library raises, and calling it without a CUDA device raises IdgError.
 from .api import (IdgError, SINCOS_ACCURATE, SINCOS_FAST, SINCOS_REDUCED, bytes_gridder,
                   c_run_degridder, c_run_gridder, degridder, device_name, flops_gridder, gridder,
                   init_problem_device, launch_count, p_run_degridder, p_run_gridder,
-                  print_device_info, sm_count)
+                  print_device_info, resolve_variant, sm_count)
 from .layout import BASELINE_DTYPE, METADATA_DTYPE, NR_CORRELATIONS, IMAGE_SIZE, W_STEP
 from .shard import partition_subgrids, shard_metadata
 
@@ -20,6 +20,6 @@ __all__ = [
     "IdgError", "SINCOS_FAST", "SINCOS_REDUCED", "SINCOS_ACCURATE", "c_run_gridder",
     "c_run_degridder", "gridder", "degridder", "p_run_gridder", "p_run_degridder",
     "flops_gridder", "bytes_gridder", "print_device_info", "device_name", "sm_count",
-    "launch_count", "init_problem_device", "METADATA_DTYPE", "BASELINE_DTYPE",
+    "launch_count", "resolve_variant", "init_problem_device", "METADATA_DTYPE", "BASELINE_DTYPE",
     "NR_CORRELATIONS", "IMAGE_SIZE", "W_STEP", "partition_subgrids", "shard_metadata",
 ]

@@ -34,6 +34,7 @@ SYMBOLS = {
     "idgb200_gridder": (C.c_int, [C.POINTER(Params)] + [_P] * 8),
     "idgb200_degridder": (C.c_int, [C.POINTER(Params)] + [_P] * 8),
     "idgb200_launch_count": (C.c_uint64, []),
+    "idgb200_resolve_variant": (C.c_int, [C.POINTER(Params), C.c_int]),
     "idgb200_c_run_gridder": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int,
                                         C.c_int, C.c_int64, C.c_int] + [_P] * 7),
     "idgb200_c_run_degridder": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int,

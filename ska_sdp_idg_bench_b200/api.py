@@ -68,6 +68,15 @@ def launch_count() -> int:
     return int(lib.idgb200_launch_count())
 
 
+def resolve_variant(subgrid_size, nr_channels, sincos=SINCOS_FAST, variant=0, gridder=True) -> int:
+    """The kernel variant `variant=0` selects for this shape (idgb200_resolve_variant)."""
+    p = _params(1, max(subgrid_size, 1), subgrid_size, 1.0, 0.0, nr_channels, 1, sincos, variant)
+    rc = lib.idgb200_resolve_variant(C.byref(p), 1 if gridder else 0)
+    if rc < 0:
+        _check(rc)
+    return rc
+
+
 def _params(nr_subgrids, grid_size, subgrid_size, image_size, w_step_in_lambda, nr_channels,
             nr_stations, sincos, variant) -> Params:
     p = Params()

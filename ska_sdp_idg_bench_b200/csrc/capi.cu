@@ -671,6 +671,13 @@ int idgb200_degridder(const idgb200_params *p, const idgb200_uvw *d_uvw, const f
 
 uint64_t idgb200_launch_count(void) { return g_launches.load(); }
 
+int idgb200_resolve_variant(const idgb200_params *p, int gridder) {
+  int rc = check_params(p);
+  if (rc) return rc;
+  return gridder ? resolve_gridder_variant(p->subgrid_size, p->nr_channels, p->sincos_mode, p->variant)
+                 : resolve_degridder_variant(p->subgrid_size, p->nr_channels, p->sincos_mode, p->variant);
+}
+
 int idgb200_c_run_gridder_ex(const idgb200_params *p, int64_t total_timesteps, int nr_aterm_slots,
                              const idgb200_uvw *uvw, const float *wn, const idgb200_cfloat *vis,
                              const float *sph, const idgb200_cfloat *at, const idgb200_metadata *meta,

@@ -211,6 +211,11 @@ cudaError_t launch_t(const KernelArgs &a, int mode, cudaStream_t stream) {
 //          1 scalar-FFMA baseline (256 threads, 4 channels per task)
 //          2 swizzled FFMA2, 4 channels per task (3 blocks/SM)
 //          3 swizzled FFMA2, 128 threads, 8 channels per task, 3 blocks/SM
+//         11 tensor-core kernel (degridder_tc.cu; FAST sincos only; opt-in: its fp16 phasors are
+//            outside the stated tolerance on smooth images); 12..14 with 2, 3, 4 of
+//            every 8 pixels' phasors from the FP32 polynomial
+int resolve_degridder_variant(int, int, int, int variant) { return variant; }
+
 cudaError_t launch_degridder(const KernelArgs &a, int sincos_mode, int variant, cudaStream_t stream) {
   if (a.nr_subgrids == 0) return cudaSuccess;
   switch (variant) {

@@ -361,16 +361,20 @@ cudaError_t launch_t(const KernelArgs &a, int mode, cudaStream_t stream) {
 //          3 swizzled FFMA2, 256 threads x 8 pixels
 //          4 first design: FFMA2 on duplicated records, rotated sums, software pipelined (256 x 4)
 //          5 swizzled FFMA2, 128 threads x 8 pixels, 3 blocks/SM (more registers)
+int resolve_gridder_variant(int subgrid_size, int nr_channels, int sincos_mode, int variant) {
+  if (variant != 0) return variant;
+  // the tensor kernel pads the channels to blocks of 8 (K = 16) and the pixels to tiles of 128
+  const int npix = subgrid_size * subgrid_size;
+  const int ncb = (nr_channels + 7) / 8, tiles = (npix + 127) / 128;
+  const bool tc = sincos_mode == IDGB200_SINCOS_FAST && 4 * nr_channels >= 3 * ncb * 8 &&
+                  4 * npix >= 3 * tiles * 128;
+  return tc ? 12 : 10;
+}
+
 cudaError_t launch_gridder(const KernelArgs &a, int sincos_mode, int variant, cudaStream_t stream) {
   if (a.nr_subgrids == 0) return cudaSuccess;
   const int npix = a.subgrid_size * a.subgrid_size;
-  if (variant == 0) {
-    // the tensor kernel pads the channels to blocks of 8 (K = 16) and the pixels to tiles of 128
-    const int ncb = (a.nr_channels + 7) / 8, tiles = (npix + 127) / 128;
-    const bool tc = sincos_mode == IDGB200_SINCOS_FAST && 4 * a.nr_channels >= 3 * ncb * 8 &&
-                    4 * npix >= 3 * tiles * 128;
-    variant = tc ? 12 : 10;
-  }
+  variant = resolve_gridder_variant(a.subgrid_size, a.nr_channels, sincos_mode, variant);
   switch (variant) {
     case 10:
       return npix >= 1024 ? launch_t<128, 8, 3, 4>(a, sincos_mode, stream)

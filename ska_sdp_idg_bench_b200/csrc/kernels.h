@@ -10,6 +10,10 @@ namespace idgb200 {
 cudaError_t launch_gridder(const KernelArgs &a, int sincos_mode, int variant, cudaStream_t stream);
 cudaError_t launch_degridder(const KernelArgs &a, int sincos_mode, int variant, cudaStream_t stream);
 
+// what variant 0 means for this shape / sincos mode (other values are returned unchanged)
+int resolve_gridder_variant(int subgrid_size, int nr_channels, int sincos_mode, int variant);
+int resolve_degridder_variant(int subgrid_size, int nr_channels, int sincos_mode, int variant);
+
 // tcgen05 / TMEM gridder (gridder_tc.cu); FAST sincos only
 cudaError_t launch_gridder_tc(const KernelArgs &a, int poly, cudaStream_t stream);
 cudaError_t launch_degridder_tc(const KernelArgs &a, int poly, cudaStream_t stream);

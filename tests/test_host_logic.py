@@ -100,6 +100,20 @@ def test_argument_validation():
 
 
 # ------------------------------------------------------------------------ sharding
+def test_default_variant_selection():
+    """variant 0: tcgen05 gridder only for FAST sincos and shapes that fill its 8-channel /
+    128-pixel tiles; the degridder default is always the FP32 kernel."""
+    assert idg.resolve_variant(32, 16, idg.SINCOS_FAST) == 12
+    assert idg.resolve_variant(24, 16, idg.SINCOS_FAST) == 12
+    assert idg.resolve_variant(32, 16, idg.SINCOS_ACCURATE) == 10
+    assert idg.resolve_variant(32, 16, idg.SINCOS_REDUCED) == 10
+    assert idg.resolve_variant(8, 1, idg.SINCOS_FAST) == 10      # 1 of 8 channels, 64 of 128 pixels
+    assert idg.resolve_variant(32, 9, idg.SINCOS_FAST) == 10     # 9 of 16 channels
+    assert idg.resolve_variant(32, 16, idg.SINCOS_FAST, variant=3) == 3
+    for mode in (idg.SINCOS_FAST, idg.SINCOS_ACCURATE):
+        assert idg.resolve_variant(32, 16, mode, gridder=False) == 0
+
+
 def test_partition_balanced_and_contiguous():
     rng = np.random.default_rng(0)
     nt = rng.integers(0, 200, 1000)
