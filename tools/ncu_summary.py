@@ -16,7 +16,12 @@ WANT = [
     "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
     "smsp__sass_thread_inst_executed_op_ffma", "smsp__sass_thread_inst_executed_op_fp32",
     "sm__sass_thread_inst_executed_op_ffma_pred_on.sum", "smsp__inst_executed_op_shared",
+    "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_tc.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_uniform.avg.pct_of_peak_sustained_active",
+    "sm__issue_active.avg.pct_of_peak_sustained_elapsed",
 ]
+ALSO = ["l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
+        "l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed"]
 rep = sys.argv[1]
 out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
@@ -26,6 +31,6 @@ for r in rows[2:]:
     print(f"== {name[:110]}")
     print(f"   grid {r[hdr.index('Grid Size')]} block {r[hdr.index('Block Size')]}")
     for h, u, v in zip(hdr, units, r):
-        if any(h.startswith(w) for w in WANT) and not h.endswith((".max", ".min")) and ".max." not in h and ".min." not in h \
-                and ".sum.pct" not in h:
+        if h in ALSO or any(h.startswith(w) for w in WANT) and not h.endswith((".max", ".min")) and ".max." not in h \
+                and ".min." not in h and ".sum.pct" not in h:
             print(f"   {h:92s} {v:>16s} {u}")
