@@ -382,6 +382,9 @@ cudaError_t launch_gridder(const KernelArgs &a, int sincos_mode, int variant, cu
     case 11: case 12: case 13: case 14: case 15:   // 12..15: 4, 5, 6, 8 of 16 phasors by FP32 polynomial
       return sincos_mode == IDGB200_SINCOS_FAST ? launch_gridder_tc(a, variant - 11, stream)
                                                 : cudaErrorInvalidValue;
+    case 16: case 17: case 18: case 19:   // phasor tile in TMEM; 18, 19: fp16 hi + lo phasors
+      return sincos_mode == IDGB200_SINCOS_FAST ? launch_gridder_tc3(a, variant - 16, stream)
+                                                : cudaErrorInvalidValue;
     case 1: return launch_t<256, 4, 1, 2>(a, sincos_mode, stream);
     case 2: return launch_t<256, 4, 3, 2>(a, sincos_mode, stream);
     case 3: return launch_t<256, 8, 3, 1>(a, sincos_mode, stream);
