@@ -39,14 +39,6 @@ __device__ __forceinline__ void tmem_st8(unsigned taddr, const unsigned (&r)[8])
                ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
                : "memory");
 }
-// one non-blocking probe of an mbarrier phase
-__device__ __forceinline__ bool mbar_test(unsigned long long *bar, unsigned parity) {
-  unsigned ok;
-  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-               : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-  return ok != 0;
-}
-
 // the 8 phasors of one stage of one pixel as packed half2 (cos, sin): hi, and with SPLIT the
 // rounding residual lo.  MASK8 bit i set -> channel i from phasor_poly instead of MUFU.
 template <unsigned MASK8, bool SPLIT>

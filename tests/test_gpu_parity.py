@@ -195,6 +195,9 @@ def test_golden_ragged(name, sincos):
     dict(subgrid_size=64, nr_channels=9, max_timesteps=17, nr_subgrids=2),
     dict(subgrid_size=16, nr_channels=70, max_timesteps=5, nr_subgrids=4),
     dict(subgrid_size=18, nr_channels=300, max_timesteps=2, nr_subgrids=2),
+    # BASELINE config 4 in miniature: 64 channels, subgrid 32; config 5: subgrid 64, per-slot A-terms
+    dict(subgrid_size=32, nr_channels=64, max_timesteps=24, nr_subgrids=3, nr_stations=8),
+    dict(subgrid_size=64, nr_channels=16, max_timesteps=20, nr_subgrids=2, nr_stations=6, nr_slots=3),
 ])
 def test_shapes_vs_oracle(shape):
     o = oracle()
