@@ -366,10 +366,24 @@ def run_ours(args) -> None:
         sec_e = reduce_max_time(time.perf_counter() - t0, dev)
         h2d = sum(npy[k].nbytes for k in ("uvw", "wavenumbers", "visibilities", "spheroidal",
                                           "aterms", "metadata"))
+        # what the link gives: one pinned 1 GiB host->device copy on this rank, CUDA events
+        probe_h = torch.empty(1 << 30, dtype=torch.uint8, pin_memory=True)
+        probe_d = torch.empty(1 << 30, dtype=torch.uint8, device=dev)
+        probe_d.copy_(probe_h, non_blocking=True)
+        torch.cuda.synchronize()
+        pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        pe0.record()
+        probe_d.copy_(probe_h, non_blocking=True)
+        pe1.record()
+        torch.cuda.synchronize()
+        h2d_gbs = (1 << 30) / (pe0.elapsed_time(pe1) * 1e-3) * 1e-9
+        del probe_h, probe_d
         e2e = {"value": world * shape["mvis"] * e_steps / sec_e, "unit": "MVis/s",
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(npy["subgrids"].nbytes),
                "ms_per_step": sec_e / e_steps * 1e3, "steps": e_steps,
-               "api": "idgb200_c_run_gridder_ex (host pointers, pinned; chunked H2D/kernel/D2H on 3 streams)"}
+               "api": "idgb200_c_run_gridder_ex (host pointers, pinned; chunked H2D/kernel/D2H on 3 streams)",
+               "pcie_h2d_gbs_measured": h2d_gbs, "h2d_floor_ms": h2d / (h2d_gbs * 1e9) * 1e3,
+               "note": "copy-bound: the step cannot be faster than its host->device bytes over the measured link"}
 
     # ---- CPU baseline + parity sample, rank 0 at N=1 only
     cpu_baseline, parity = None, None

@@ -203,9 +203,12 @@ int host_run(bool gridding, const idgb200_params *p, int64_t total_timesteps, in
                      cudaMemcpyHostToDevice, s_in));
   CK(cudaMemcpyAsync(d_meta, meta, (size_t)S * sizeof(idgb200_metadata), cudaMemcpyHostToDevice, s_in));
 
-  // chunking: ~16 chunks, at least 256 subgrids each
-  int chunk = (S + 15) / 16;
+  // chunking: ~IDGB200_CHUNKS chunks (default 16), at least 256 subgrids each
+  long want = env_long("IDGB200_CHUNKS", 16);
+  if (want < 1) want = 1;
+  int chunk = (int)((S + want - 1) / want);
   if (chunk < 256) chunk = 256;
+  if (env_long("IDGB200_CHUNK_SUBGRIDS", 0) > 0) chunk = (int)env_long("IDGB200_CHUNK_SUBGRIDS", 0);
   const int nchunks = (S + chunk - 1) / chunk;
   std::vector<cudaEvent_t> ev_in(nchunks), ev_k(nchunks);
   for (int i = 0; i < nchunks; i++) {
