@@ -38,8 +38,12 @@ SM_FP32_LANES = 128   # FP32 FMA lanes per SM (B200)
 SM_XU_LANES = 16      # MUFU lanes per SM
 # tensor-core gridder variants -> fraction of the phasors that come from the FP32 polynomial
 # instead of 2 MUFUs (gridder_tc.cu, launch_gridder_tc)
-TC_GRIDDER_POLY = {11: 0.0, 12: 4 / 16, 13: 5 / 16, 14: 6 / 16, 15: 8 / 16}
-TC_DEGRIDDER_POLY = {11: 0.0, 12: 2 / 8, 13: 3 / 8, 14: 4 / 8}
+# tensor-core gridder variants -> (MUFU per (pixel, visibility) item, warp instructions per warp-item
+# counted by ncu on the committed captures under profiles/).  11..15: 2 MUFU per item minus the share
+# replaced by an FP32 polynomial; 21 (equally spaced channels): per pixel one sincos per 8-channel block
+# (its first channel) and one per timestep (the rotation step), the rest by complex multiplication.
+TC_GRIDDER = {11: (2.0, 10.1), 12: (1.5, 12.6), 13: (1.375, 12.9), 14: (1.25, 13.3), 15: (1.0, 14.2), 21: (0.375, 10.0)}
+TC_DEGRIDDER = {11: (2.0, 11.0), 12: (1.5, 13.0), 13: (1.25, 14.0), 14: (1.0, 15.0)}
 
 
 # ----------------------------------------------------------------- shared helpers
@@ -332,7 +336,7 @@ def run_ours(args) -> None:
     sec_g, launches_g = timed(step_gridder, args.steps, args.warmup)
     sec_d, launches_d = timed(step_degridder, args.steps, args.warmup)
     # the FP32/SFU gridder next to the tensor-core one (north_star: tensor cores only if they win)
-    sec_g32 = timed(step_gridder_fp32, args.steps, args.warmup)[0] if g_variant in TC_GRIDDER_POLY else None
+    sec_g32 = timed(step_gridder_fp32, args.steps, args.warmup)[0] if g_variant in TC_GRIDDER else None
     step_gridder()   # leave the default kernel's result in prob["subgrids"] for the parity sample
     clocks = sampler.stop() if rank == 0 else {}
 
@@ -437,10 +441,10 @@ def run_ours(args) -> None:
         nbytes = idg.bytes_gridder(C_, tt, S, N)
         hbm_peak = float(peaks.get("hbm_gbs") or 6650.0)
 
-        def roof(sec, steps, traffic_per_subgrid, poly):
-            """poly None: FP32 kernel (bound = the FP32 issue port); else the tensor-core kernel,
-            whose MACs run on tcgen05 and whose roof is the XU (MUFU) pipe; poly = fraction of
-            the phasors computed by FP32 polynomial instead of MUFU."""
+        def roof(sec, steps, traffic_per_subgrid, tc):
+            """tc None: FP32 kernel (bound = the FP32 issue port); else (MUFU per item, warp
+            instructions per warp-item) of a tensor-core kernel, whose MACs run on tcgen05 and whose
+            roof is the XU (MUFU) pipe or the instruction issue port, whichever is busier."""
             t = sec / steps
             tf = flops / t * 1e-12
             items = float(N) * N * tt * C_                     # (pixel, visibility) pairs per launch
@@ -455,27 +459,36 @@ def run_ours(args) -> None:
                       "fp32_model_tflops": tf, "fp32_model_frac": tf / p_fp32,
                       "fp32_model_note": f"reference flop model (flops_gridder) / ({sms} SMs x 128 FP32 lanes x 2 x "
                                          f"{f_max:.0f} MHz): the north_star's 'fraction of the FP32+SFU roofline'"}
-            if poly is None:
+            if tc is None:
                 r = dict({"bound": "fp32", "achieved": tf, "peak": p_fp32, "unit": "TFLOP/s", "frac": tf / p_fp32,
                           "bound_note": "CUDA-core FP32 issue bound (359 flop/B): neither HBM nor tensor is the roof",
                           "peak_source": f"{sms} SMs x 128 FP32 lanes x 2 x {f_max:.0f} MHz (sm_max_mhz of "
                                          "MEASURED_PEAKS.json; the file holds no FP32 figure)",
                           "sfu_frac": 2.0 * items / t / p_xu}, **common)
             else:
-                mufu = 2.0 * (1.0 - poly) * items / t          # MUFU.SIN + MUFU.COS actually executed per second
-                r = dict({"bound": "sfu", "achieved": mufu * 1e-12, "peak": p_xu * 1e-12, "unit": "TMUFU/s",
-                          "frac": mufu / p_xu,
-                          "bound_note": "tcgen05 kernel: the complex MACs run on the tensor pipe (~5 % busy), the "
-                                        "phasors bound it: 2 MUFU per (pixel, visibility) on the XU pipe, "
-                                        f"{poly:.3f} of them replaced by an FP32-pipe polynomial "
-                                        "(fp32_model_frac > 1 is the flop model's MACs having left the FP32 pipe)",
-                          "peak_source": f"{sms} SMs x 16 MUFU lanes x {f_max:.0f} MHz",
-                          "phasor_rate_frac": 2.0 * items / t / p_xu}, **common)
+                mufu_per_item, inst_per_item = tc
+                mufu = mufu_per_item * items / t               # MUFU.SIN + MUFU.COS executed per second
+                p_issue = sms * 4 * f_max * 1e6                 # warp instructions / s (1 per SMSP and cycle)
+                issue = inst_per_item * items / 32.0 / t
+                sfu_frac, issue_frac = mufu / p_xu, issue / p_issue
+                note = ("tcgen05 kernel: the complex MACs run on the tensor pipe (6-8 %% busy); what bounds it is "
+                        "generating the phasor operand: %.2f MUFU and %.1f warp instructions per (pixel, "
+                        "visibility) against the XU pipe and the issue port (fp32_model_frac > 1 is the flop "
+                        "model's MACs having left the FP32 pipe)" % (mufu_per_item, inst_per_item))
+                if sfu_frac >= issue_frac:
+                    r = dict({"bound": "sfu", "achieved": mufu * 1e-12, "peak": p_xu * 1e-12, "unit": "TMUFU/s",
+                              "frac": sfu_frac, "peak_source": f"{sms} SMs x 16 MUFU lanes x {f_max:.0f} MHz"})
+                else:
+                    r = dict({"bound": "issue", "achieved": issue * 1e-12, "peak": p_issue * 1e-12,
+                              "unit": "T warp-inst/s", "frac": issue_frac,
+                              "peak_source": f"{sms} SMs x 4 sub-partitions x 1 instruction/clk x {f_max:.0f} MHz; "
+                                             "instructions per item from the ncu capture under profiles/"})
+                r.update({"bound_note": note, "sfu_frac": sfu_frac, "issue_frac": issue_frac}, **common)
             if clocks.get("sm_mhz"):
                 r["frac_at_measured_clock"] = r["frac"] * f_max / clocks["sm_mhz"]
             return r
 
-        tc_g, tc_d = TC_GRIDDER_POLY.get(g_variant), TC_DEGRIDDER_POLY.get(d_variant)
+        tc_g, tc_d = TC_GRIDDER.get(g_variant), TC_DEGRIDDER.get(d_variant)
         total_mvis = world * shape["mvis"]
         out = {
             "metric": "gridder_mvis_per_s", "value": total_mvis * args.steps / sec_g,
@@ -488,7 +501,10 @@ def run_ours(args) -> None:
             "config": dict(workload_config(shape, world), sincos=args.sincos,
                            gridder_variant=g_variant, degridder_variant=d_variant,
                            gridder_kernel=("tcgen05: fp16 phasor tile x fp16 hi+lo visibilities, f32 accumulate in "
-                                           "TMEM" if tc_g is not None else "FP32 FFMA2 + MUFU"),
+                                           "TMEM" + ("; phasors of equally spaced channels by rotation from the "
+                                                     "first channel of each 8-channel block (as the reference's "
+                                                     "gridder_v8)" if g_variant == 21 else "")
+                                           if tc_g is not None else "FP32 FFMA2 + MUFU"),
                            degridder_kernel=("tcgen05 (opt-in, outside the stated tolerance)" if tc_d is not None
                                              else "FP32 FFMA2 + MUFU")),
             "tflops": world * flops * args.steps / sec_g * 1e-12,

@@ -350,12 +350,15 @@ cudaError_t launch_t(const KernelArgs &a, int mode, cudaStream_t stream) {
 }  // namespace
 
 // variant: 0 default: FAST sincos and a shape that fills >= 3/4 of its 8-channel blocks and
-//            128-pixel tiles -> tensor-core kernel (= variant 12, gridder_tc.cu); otherwise the
+//            128-pixel tiles -> tensor-core kernel (= variant 21, gridder_tc.cu); otherwise the
 //            FP32 kernel (= variant 10)
 //         10 FP32 kernel: swizzled FFMA2; 128 threads x 8 pixels (x 4 blocks/SM) when the
 //            subgrid has >= 1024 pixels, 128 x 4 below that
 //         11 tensor-core kernel (FAST sincos only), every phasor by MUFU
 //         12 tensor-core kernel, 4 of every 16 channels' phasors by FP32 polynomial (13: 5, 14: 6, 15: 8)
+//         21 tensor-core kernel; blocks of 8 equally spaced channels get their phasors by complex
+//            rotation from the block's first channel (2 sincos per pixel and block instead of 8, as
+//            the reference's gridder_v8.cu does unconditionally), other blocks as variant 12
 //          1 scalar-FFMA baseline (256 x 4)
 //          2 swizzled FFMA2, 256 threads x 4 pixels
 //          3 swizzled FFMA2, 256 threads x 8 pixels
@@ -368,7 +371,7 @@ int resolve_gridder_variant(int subgrid_size, int nr_channels, int sincos_mode, 
   const int ncb = (nr_channels + 7) / 8, tiles = (npix + 127) / 128;
   const bool tc = sincos_mode == IDGB200_SINCOS_FAST && 4 * nr_channels >= 3 * ncb * 8 &&
                   4 * npix >= 3 * tiles * 128;
-  return tc ? 12 : 10;
+  return tc ? 21 : 10;
 }
 
 cudaError_t launch_gridder(const KernelArgs &a, int sincos_mode, int variant, cudaStream_t stream) {
@@ -380,8 +383,10 @@ cudaError_t launch_gridder(const KernelArgs &a, int sincos_mode, int variant, cu
       return npix >= 1024 ? launch_t<128, 8, 3, 4>(a, sincos_mode, stream)
                           : launch_t<128, 4, 3, 4>(a, sincos_mode, stream);
     case 11: case 12: case 13: case 14: case 15:   // 12..15: 4, 5, 6, 8 of 16 phasors by FP32 polynomial
-      return sincos_mode == IDGB200_SINCOS_FAST ? launch_gridder_tc(a, variant - 11, stream)
+      return sincos_mode == IDGB200_SINCOS_FAST ? launch_gridder_tc(a, variant - 11, false, stream)
                                                 : cudaErrorInvalidValue;
+    case 21:   // tensor-core kernel, phasors of equally spaced channel blocks by rotation (else as 12)
+      return sincos_mode == IDGB200_SINCOS_FAST ? launch_gridder_tc(a, 1, true, stream) : cudaErrorInvalidValue;
     case 16: case 17: case 18: case 19:   // phasor tile in TMEM; 18, 19: fp16 hi + lo phasors
       return sincos_mode == IDGB200_SINCOS_FAST ? launch_gridder_tc3(a, variant - 16, stream)
                                                 : cudaErrorInvalidValue;
