@@ -204,13 +204,18 @@ gridder_tc_kernel(const KernelArgs a, const int slabs, const int tiles_per_cta, 
         offr[j] = __fmul_rn(off[j], 0.15915494309189535f);
       }
       unsigned char *A_tile = sA + tile * T2_STAGES * T2_A_STAGE;
-      unsigned long long *my_empty = aempty + tile * T2_STAGES;
-      const unsigned long long da0 = smem_desc(smem_u32(A_tile), A_CHUNK_BYTES, 128);
-      const unsigned long long db0 = smem_desc(smem_u32(sB), B_CHUNK_BYTES, 128);
-      const unsigned tmem_d = tmem_base + tile * 16;
+      unsigned long long da0 = smem_desc(smem_u32(A_tile), A_CHUNK_BYTES, 128);
+      unsigned long long db0 = smem_desc(smem_u32(sB), B_CHUNK_BYTES, 128);
+      unsigned tmem_d = tmem_base + tile * 16;
+      // barrier addresses as 32-bit shared addresses, computed once; the empty asm statements make
+      // the values opaque, so that the compiler keeps them instead of recomputing ~30 uniform
+      // instructions per stage in the issue path (which is what bounds this kernel)
+      unsigned my_empty_u = smem_u32(aempty + tile * T2_STAGES), bfull_u = smem_u32(bfull),
+               bempty_u = smem_u32(bempty), done_u = smem_u32(done);
+      asm volatile("" : "+l"(da0), "+l"(db0), "+r"(tmem_d), "+r"(my_empty_u), "+r"(bfull_u), "+r"(bempty_u), "+r"(done_u));
       float un = 0.f, vn = 0.f, wnx = 0.f;   // uvw of the next timestep, fetched one timestep ahead
       if (nt > 0) { un = __ldg(&g_uvw[0]); vn = __ldg(&g_uvw[1]); wnx = __ldg(&g_uvw[2]); }
-      int k = 0;
+      unsigned k = 0;   // unsigned: slot / parity are masks and shifts, not signed divisions
       for (int t = 0; t < nt; t++) {
         const float u = un, v = vn, w = wnx;
         if (t + 1 < nt) { un = __ldg(&g_uvw[3 * t + 3]); vn = __ldg(&g_uvw[3 * t + 4]); wnx = __ldg(&g_uvw[3 * t + 5]); }
@@ -224,8 +229,8 @@ gridder_tc_kernel(const KernelArgs a, const int slabs, const int tiles_per_cta, 
 #pragma unroll
         for (int j = 0; j < 4; j++) rot[j] = make_float2(1.f, 0.f);
         for (int cb = 0; cb < ncb; cb++, k++) {
-          const int stage = k & 1, use = k >> 1;
-          if (use >= 1) mbar_wait(&my_empty[stage], (use - 1) & 1);
+          const unsigned stage = k & 1u, use = k >> 1;
+          if (use >= 1) mbar_wait_u(my_empty_u + stage * 8, (use - 1) & 1);
           unsigned char *A = A_tile + stage * T2_A_STAGE;
           if (s_lin[cb]) {
             // the rotation step -idx * dw: once per timestep when every block has the same spacing
@@ -242,16 +247,16 @@ gridder_tc_kernel(const KernelArgs a, const int slabs, const int tiles_per_cta, 
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           // the whole warp waits for the B slot (one SYNCS either way) and stays converged, so the
           // descriptors live in uniform registers and one elected lane issues MMA + commits
-          const int slot = k % T2_NB;
-          mbar_wait(&bfull[slot], (k / T2_NB) & 1);
+          const unsigned slot = k % (unsigned)T2_NB;
+          mbar_wait_u(bfull_u + slot * 8, (k / (unsigned)T2_NB) & 1u);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           __syncwarp();
           if (elect_one()) {
             umma_f16(tmem_d, da0 + (unsigned long long)(stage * (T2_A_STAGE >> 4)),
                      db0 + (unsigned long long)(slot * (T2_B_SLOT >> 4)), idesc, k > 0 ? 1u : 0u);
-            umma_commit(&my_empty[stage]);
-            if ((k & 7) == 7) umma_commit(&bempty[(k >> 3) & 1]);
-            if (k == nstages - 1) umma_commit(done);
+            umma_commit_u(my_empty_u + stage * 8);
+            if ((k & 7) == 7) umma_commit_u(bempty_u + ((k >> 3) & 1) * 8);
+            if (k == (unsigned)(nstages - 1)) umma_commit_u(done_u);
           }
           __syncwarp();
         }

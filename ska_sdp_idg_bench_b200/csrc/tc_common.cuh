@@ -27,6 +27,21 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned pari
     if (spin > (1 << 22)) __trap();   // a lost arrival must fail loudly, not hang the GPU
   }
 }
+// The same on a 32-bit shared address computed once outside a hot loop: one try_wait and one branch
+// when the phase is already complete, the bounded spin (trap on a lost arrival) only otherwise.
+__device__ __forceinline__ void mbar_wait_u(unsigned bar, unsigned parity) {
+  unsigned done;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+               : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+  for (int spin = 0; !done; spin++) {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    if (spin > (1 << 22)) __trap();
+  }
+}
+__device__ __forceinline__ void umma_commit_u(unsigned bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
 // cute::UMMA::SmemDescriptor (cute/arch/mma_sm100_desc.hpp): start[0,14) LBO[16,30) SBO[32,46),
 // all >> 4; version[46,48) = 1; layout[61,64) = 0 (no swizzle).  K-major canonical layout:
 // 8 rows x 16 B core matrices; SBO = distance of 8-row groups, LBO = distance of 16-byte K chunks.
