@@ -43,7 +43,10 @@ SM_XU_LANES = 16      # MUFU lanes per SM
 # replaced by an FP32 polynomial; 21 (equally spaced channels): per pixel one sincos per 8-channel block
 # (its first channel) and one per timestep (the rotation step), the rest by complex multiplication.
 TC_GRIDDER = {11: (2.0, 10.1), 12: (1.5, 12.6), 13: (1.375, 12.9), 14: (1.25, 13.3), 15: (1.0, 14.2), 21: (0.375, 10.0)}
-TC_DEGRIDDER = {11: (2.0, 11.0), 12: (1.5, 13.0), 13: (1.25, 14.0), 14: (1.0, 15.0)}
+# degridder: 11..14 fp16 phasors (13: profiles/r01_degridder_tc_ncu_full.txt), 22: hi + lo phasors with the
+# channel rotation (profiles/r01_degridder_tc_split_ncu_full.txt); instruction counts of the others estimated
+TC_DEGRIDDER = {11: (2.0, 11.5), 12: (1.5, 13.5), 13: (1.25, 13.2), 14: (1.0, 15.5), 21: (1.0, 10.5),
+                22: (1.0, 16.5), 23: (2.0, 17.5)}
 
 
 # ----------------------------------------------------------------- shared helpers
@@ -330,6 +333,10 @@ def run_ours(args) -> None:
     def step_gridder_fp32():
         idg.gridder(*scal, *tens, sincos=sincos, variant=10)
 
+    def step_degridder_fp32():
+        idg.degridder(*scal, prob["uvw"], prob["wavenumbers"], vis_out, prob["spheroidal"],
+                      prob["aterms"], prob["metadata"], sub_in, sincos=sincos, variant=4)
+
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -337,7 +344,9 @@ def run_ours(args) -> None:
     sec_d, launches_d = timed(step_degridder, args.steps, args.warmup)
     # the FP32/SFU gridder next to the tensor-core one (north_star: tensor cores only if they win)
     sec_g32 = timed(step_gridder_fp32, args.steps, args.warmup)[0] if g_variant in TC_GRIDDER else None
-    step_gridder()   # leave the default kernel's result in prob["subgrids"] for the parity sample
+    sec_d32 = timed(step_degridder_fp32, args.steps, args.warmup)[0] if d_variant in TC_DEGRIDDER else None
+    step_gridder()   # leave the default kernels' results in prob["subgrids"] / vis_out for the parity sample
+    step_degridder()
     clocks = sampler.stop() if rank == 0 else {}
 
     # ---- e2e through the host-pointer C ABI, pinned host buffers
@@ -505,8 +514,10 @@ def run_ours(args) -> None:
                                                      "first channel of each 8-channel block (as the reference's "
                                                      "gridder_v8)" if g_variant == 21 else "")
                                            if tc_g is not None else "FP32 FFMA2 + MUFU"),
-                           degridder_kernel=("tcgen05 (opt-in, outside the stated tolerance)" if tc_d is not None
-                                             else "FP32 FFMA2 + MUFU")),
+                           degridder_kernel=(("tcgen05: fp16 hi+lo phasor tile x fp16 hi+lo pixels, f32 accumulate in "
+                                              "TMEM; phasors of equally spaced channel quads by rotation"
+                                              if d_variant == 22 else "tcgen05, opt-in variant")
+                                             if tc_d is not None else "FP32 FFMA2 + MUFU")),
             "tflops": world * flops * args.steps / sec_g * 1e-12,
             # ncu --set full, 3675-subgrid launches: 341.6 MB (tcgen05 gridder), FP32 kernels from the
             # 1740-subgrid captures (profiles/)
@@ -514,11 +525,16 @@ def run_ours(args) -> None:
             "degridder": {"value": total_mvis * args.steps / sec_d, "unit": "MVis/s",
                           "ms_per_step": sec_d / args.steps * 1e3,
                           "tflops": world * flops * args.steps / sec_d * 1e-12,
-                          "roofline": roof(sec_d, args.steps, 128.329e6 / 1740, tc_d)},
+                          "roofline": roof(sec_d, args.steps, 315.8e6 / 3675 if tc_d is not None
+                                           else 128.329e6 / 1740, tc_d)},
             "gridder_fp32": None if sec_g32 is None else {
                 "value": total_mvis * args.steps / sec_g32, "unit": "MVis/s", "variant": 10,
                 "ms_per_step": sec_g32 / args.steps * 1e3,
                 "roofline": roof(sec_g32, args.steps, 145.165e6 / 1740, None)},
+            "degridder_fp32": None if sec_d32 is None else {
+                "value": total_mvis * args.steps / sec_d32, "unit": "MVis/s", "variant": 4,
+                "ms_per_step": sec_d32 / args.steps * 1e3,
+                "roofline": roof(sec_d32, args.steps, 128.329e6 / 1740, None)},
             "cpu_baseline": cpu_baseline, "parity": parity, "e2e": e2e,
             "gpu_launches": int(launches_g), "degridder_gpu_launches": int(launches_d),
             "clocks": clocks, "device": idg.device_name(),

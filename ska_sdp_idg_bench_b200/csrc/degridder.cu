@@ -207,25 +207,42 @@ cudaError_t launch_t(const KernelArgs &a, int mode, cudaStream_t stream) {
 
 }  // namespace
 
-// variant: 0 default: swizzled FFMA2, 256 threads, 8 channels per task, 2 blocks/SM
+// variant: 0 default: FAST sincos and a shape that fills its channel quads -> tensor-core kernel with
+//            fp16 hi + lo phasors (= variant 22, degridder_tc.cu); otherwise the FP32 kernel (= variant 4)
+//          4 FP32 kernel: swizzled FFMA2, 256 threads, 8 channels per task, 2 blocks/SM
 //          1 scalar-FFMA baseline (256 threads, 4 channels per task)
 //          2 swizzled FFMA2, 4 channels per task (3 blocks/SM)
 //          3 swizzled FFMA2, 128 threads, 8 channels per task, 3 blocks/SM
-//         11 tensor-core kernel (degridder_tc.cu; FAST sincos only; opt-in: its fp16 phasors are
-//            outside the stated tolerance on smooth images); 12..14 with 2, 3, 4 of
-//            every 8 pixels' phasors from the FP32 polynomial
-int resolve_degridder_variant(int, int, int, int variant) { return variant; }
+//         11 tensor-core kernel with fp16 phasors (FAST sincos only; opt-in: outside the stated
+//            tolerance on smooth images); 12..14 with 2, 3, 4 of every 8 pixels'
+//            phasors from the FP32 polynomial; 21 with the channel rotation of variant 22
+//         22 tensor-core kernel, fp16 hi + lo phasors (FP32-class accuracy), phasors of equally
+//            spaced channel quads by rotation from the quad's first channel; 23 without the rotation
+int resolve_degridder_variant(int subgrid_size, int nr_channels, int sincos_mode, int variant) {
+  if (variant != 0) return variant;
+  // the tensor kernel pads the channels to quads of 4 and the pixels to stages of 8
+  const int npix = subgrid_size * subgrid_size, ncg = (nr_channels + 3) / 4;
+  const bool tc = sincos_mode == IDGB200_SINCOS_FAST && 4 * nr_channels >= 3 * ncg * 4 && npix >= 256;
+  return tc ? 22 : 4;
+}
 
 cudaError_t launch_degridder(const KernelArgs &a, int sincos_mode, int variant, cudaStream_t stream) {
   if (a.nr_subgrids == 0) return cudaSuccess;
+  variant = resolve_degridder_variant(a.subgrid_size, a.nr_channels, sincos_mode, variant);
   switch (variant) {
-    case 0: return launch_t<256, 8, 3, 2>(a, sincos_mode, stream);
+    case 4: return launch_t<256, 8, 3, 2>(a, sincos_mode, stream);
     case 1: return launch_t<256, 4, 1, 2>(a, sincos_mode, stream);
     case 2: return launch_t<256, 4, 3, 3>(a, sincos_mode, stream);
     case 3: return launch_t<128, 8, 3, 3>(a, sincos_mode, stream);
     case 11: case 12: case 13: case 14:   // tensor-core kernel; 12..14: 2, 3, 4 of 8 pixels by FP32 polynomial
-      return sincos_mode == IDGB200_SINCOS_FAST ? launch_degridder_tc(a, variant - 11, stream)
+      return sincos_mode == IDGB200_SINCOS_FAST ? launch_degridder_tc(a, variant - 11, false, stream)
                                                 : cudaErrorInvalidValue;
+    case 21:   // tensor-core kernel, fp16 phasors, rotation recurrence over each quad of channels
+      return sincos_mode == IDGB200_SINCOS_FAST ? launch_degridder_tc(a, 0, true, stream) : cudaErrorInvalidValue;
+    case 22:   // the same with fp16 hi + lo phasors (FP32-class accuracy); 23: hi + lo without the recurrence
+      return sincos_mode == IDGB200_SINCOS_FAST ? launch_degridder_tc(a, 10, true, stream) : cudaErrorInvalidValue;
+    case 23:
+      return sincos_mode == IDGB200_SINCOS_FAST ? launch_degridder_tc(a, 10, false, stream) : cudaErrorInvalidValue;
     default: return cudaErrorInvalidValue;
   }
 }

@@ -57,13 +57,14 @@ __device__ __forceinline__ void pixel_after_aterms(const KernelArgs &a, const fl
 }
 
 // one stage of one thread: 8 pixels x 4 channels.  MASK8 bit i set -> pixel i of the stage gets
-// its phasors from phasor_poly (FP32 pipe) instead of MUFU.
-template <unsigned MASK8>
+// its phasors from phasor_poly (FP32 pipe) instead of MUFU.  SPLIT: the rounding residual of the
+// fp16 phasor goes to the tile's second A buffer (see gridder_tc.cu: pack_phasor).
+template <unsigned MASK8, bool SPLIT>
 __device__ __forceinline__ void dtc_produce(unsigned char *A, const float4 *geo, const float u, const float v,
                                             const float w, const float (&wn)[4], const int lane) {
 #pragma unroll
   for (int kc = 0; kc < 2; kc++) {
-    unsigned pk[4][4];   // [row j][pixel i]
+    unsigned pk[4][4], pl[4][4];   // [row j][pixel i]
 #pragma unroll
     for (int i = 0; i < 4; i++) {
       const float4 g = geo[kc * 4 + i];   // broadcast: all lanes read the same 16 bytes
@@ -72,30 +73,62 @@ __device__ __forceinline__ void dtc_produce(unsigned char *A, const float4 *geo,
       if ((MASK8 >> (kc * 4 + i)) & 1u) {
         const float idxr = __fmul_rn(idx, 0.15915494309189535f), offr = __fmul_rn(g.w, 0.15915494309189535f);
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-          const float2 ph = phasor_poly(__fmaf_rn(idxr, wn[j], -offr));
-          const __half2 hh = __floats2half2_rn(ph.x, ph.y);
-          pk[j][i] = *reinterpret_cast<const unsigned *>(&hh);
-        }
+        for (int j = 0; j < 4; j++) pack_phasor<SPLIT>(phasor_poly(__fmaf_rn(idxr, wn[j], -offr)), pk[j][i], pl[j][i]);
       } else {
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-          const float2 ph = phasor<IDGB200_SINCOS_FAST>(__fmaf_rn(idx, wn[j], -g.w));  // :112, (cos, sin)
-          const __half2 hh = __floats2half2_rn(ph.x, ph.y);
-          pk[j][i] = *reinterpret_cast<const unsigned *>(&hh);
-        }
+        for (int j = 0; j < 4; j++)   // :112, (cos, sin)
+          pack_phasor<SPLIT>(phasor<IDGB200_SINCOS_FAST>(__fmaf_rn(idx, wn[j], -g.w)), pk[j][i], pl[j][i]);
       }
     }
 #pragma unroll
-    for (int j = 0; j < 4; j++)
+    for (int j = 0; j < 4; j++) {
       *reinterpret_cast<uint4 *>(A + kc * A_CHUNK_BYTES + (lane + 32 * j) * 16) =
           make_uint4(pk[j][0], pk[j][1], pk[j][2], pk[j][3]);
+      if (SPLIT)
+        *reinterpret_cast<uint4 *>(A + D_A_STAGE + kc * A_CHUNK_BYTES + (lane + 32 * j) * 16) =
+            make_uint4(pl[j][0], pl[j][1], pl[j][2], pl[j][3]);
+    }
   }
 }
 
-template <unsigned MASK8>
+// The same stage when the thread's four channels are equally spaced (common.cuh: linear_channels):
+// per pixel one sincos for the first channel (the reference's angle, bit for bit), one for the
+// rotation e^{i idx dw}, and 3 complex multiplications.
+template <bool SPLIT>
+__device__ __forceinline__ void dtc_produce_linear(unsigned char *A, const float4 *geo, const float u, const float v,
+                                                   const float w, const float wn0, const float dw, const int lane) {
+#pragma unroll
+  for (int kc = 0; kc < 2; kc++) {
+    unsigned pk[4][4], pl[4][4];   // [row j][pixel i]
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const float4 g = geo[kc * 4 + i];
+      const float idx = __fadd_rn(__fmaf_rn(u, g.x, __fmul_rn(v, g.y)), __fmul_rn(w, g.z));
+      float2 ph = phasor<IDGB200_SINCOS_FAST>(__fmaf_rn(idx, wn0, -g.w));
+      const float2 d = phasor<IDGB200_SINCOS_FAST>(__fmul_rn(idx, dw));
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        pack_phasor<SPLIT>(ph, pk[j][i], pl[j][i]);
+        if (j < 3) ph = make_float2(__fmaf_rn(ph.x, d.x, -__fmul_rn(ph.y, d.y)), __fmaf_rn(ph.x, d.y, __fmul_rn(ph.y, d.x)));
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      *reinterpret_cast<uint4 *>(A + kc * A_CHUNK_BYTES + (lane + 32 * j) * 16) =
+          make_uint4(pk[j][0], pk[j][1], pk[j][2], pk[j][3]);
+      if (SPLIT)
+        *reinterpret_cast<uint4 *>(A + D_A_STAGE + kc * A_CHUNK_BYTES + (lane + 32 * j) * 16) =
+            make_uint4(pl[j][0], pl[j][1], pl[j][2], pl[j][3]);
+    }
+  }
+}
+
+// SPLIT: fp16 hi + lo phasors: the tile's two A buffers hold the hi and the lo block of ONE stage (two
+//        MMAs against the same B slot; a warp then waits for its own MMAs every stage)
+// recur: quads of equally spaced channels get their phasors by rotation from the quad's first channel
+template <unsigned MASK8, bool SPLIT>
 __global__ void __launch_bounds__(D_THREADS, 3)
-degridder_tc_kernel(const KernelArgs a) {
+degridder_tc_kernel(const KernelArgs a, const int recur) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const int N = a.subgrid_size, C = a.nr_channels, npix = N * N;
   const int s = a.subgrid_offset + blockIdx.x;
@@ -199,18 +232,27 @@ degridder_tc_kernel(const KernelArgs a) {
         float wn[4];
 #pragma unroll
         for (int j = 0; j < 4; j++) wn[j] = (4 * cg + j < C) ? __ldg(&a.wavenumbers[4 * cg + j]) : 0.f;
+        float dw;
+        const bool lin = linear_channels(wn, 0, min(4, C - 4 * cg), &dw);
+        const bool warp_lin = recur && __all_sync(0xffffffffu, lin);   // warp-uniform choice of the path
         for (int k = 0; k < nstages; k++, kk++) {
-          const int stage = kk & 1, use = kk >> 1;
+          const int stage = SPLIT ? 0 : (kk & 1), use = SPLIT ? kk : (kk >> 1);
           const int G = GG + (k >> 2), grp = G % D_NG, slot = grp * D_GROUP + (k & (D_GROUP - 1));
           if ((k & (D_GROUP - 1)) == 0) mbar_wait(&bfull[grp], (G / D_NG) & 1);
           if (use >= 1) mbar_wait(&my_empty[stage], (use - 1) & 1);
-          dtc_produce<MASK8>(A_tile + stage * D_A_STAGE, sG + slot * D_PB, u, v, w, wn, lane);
+          if (warp_lin)
+            dtc_produce_linear<SPLIT>(A_tile + stage * D_A_STAGE, sG + slot * D_PB, u, v, w, wn[0], dw, lane);
+          else
+            dtc_produce<MASK8, SPLIT>(A_tile + stage * D_A_STAGE, sG + slot * D_PB, u, v, w, wn, lane);
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           __syncwarp();
           if (elect_one()) {
             umma_f16(tmem_d, da0 + (unsigned long long)(stage * (D_A_STAGE >> 4)),
                      db0 + (unsigned long long)(slot * (D_B_SLOT >> 4)), idesc, k > 0 ? 1u : 0u);
+            if (SPLIT)
+              umma_f16(tmem_d, da0 + (unsigned long long)(D_A_STAGE >> 4),
+                       db0 + (unsigned long long)(slot * (D_B_SLOT >> 4)), idesc, 1u);
             umma_commit(&my_empty[stage]);
             if ((k & (D_GROUP - 1)) == D_GROUP - 1 || k == nstages - 1) umma_commit(&bempty[grp]);
             if (k == nstages - 1) umma_commit(done);
@@ -323,22 +365,25 @@ degridder_tc_kernel(const KernelArgs a) {
 
 }  // namespace
 
-// poly: 0 = all phasors by MUFU; 1..3 = 2, 3, 4 of every 8 pixels by FP32 polynomial
-cudaError_t launch_degridder_tc(const KernelArgs &a, int poly, cudaStream_t stream) {
+// poly: 0 = all phasors by MUFU; 1..3 = 2, 3, 4 of every 8 pixels by FP32 polynomial;
+//       10 = fp16 hi + lo phasors (FP32-class accuracy)
+// recur: quads of equally spaced channels get their phasors by rotation
+cudaError_t launch_degridder_tc(const KernelArgs &a, int poly, bool recur, cudaStream_t stream) {
   if (a.nr_subgrids == 0) return cudaSuccess;
   const size_t smem = (size_t)D_MAX_TILES * D_STAGES * D_A_STAGE + D_NG * D_GROUP * (D_B_SLOT + D_G_SLOT) + 32 * 8 * 4 +
                       (D_MAX_TILES * D_STAGES + 2 * D_NG + 1) * 8 + 8 + 48;
-  void (*k)(const KernelArgs) = nullptr;
+  void (*k)(const KernelArgs, int) = nullptr;
   switch (poly) {
-    case 0: k = degridder_tc_kernel<0x00u>; break;
-    case 1: k = degridder_tc_kernel<0x44u>; break;   // 2 of 8 pixels
-    case 2: k = degridder_tc_kernel<0x92u>; break;   // 3 of 8
-    case 3: k = degridder_tc_kernel<0xAAu>; break;   // 4 of 8
+    case 0: k = degridder_tc_kernel<0x00u, false>; break;
+    case 1: k = degridder_tc_kernel<0x44u, false>; break;   // 2 of 8 pixels
+    case 2: k = degridder_tc_kernel<0x92u, false>; break;   // 3 of 8
+    case 3: k = degridder_tc_kernel<0xAAu, false>; break;   // 4 of 8
+    case 10: k = degridder_tc_kernel<0x00u, true>; break;   // hi + lo phasors
     default: return cudaErrorInvalidValue;
   }
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  k<<<dim3((unsigned)a.nr_subgrids), dim3(D_THREADS), smem, stream>>>(a);
+  k<<<dim3((unsigned)a.nr_subgrids), dim3(D_THREADS), smem, stream>>>(a, recur ? 1 : 0);
   return cudaGetLastError();
 }
 

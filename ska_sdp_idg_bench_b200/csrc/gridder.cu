@@ -385,6 +385,10 @@ cudaError_t launch_gridder(const KernelArgs &a, int sincos_mode, int variant, cu
     case 11: case 12: case 13: case 14: case 15:   // 12..15: 4, 5, 6, 8 of 16 phasors by FP32 polynomial
       return sincos_mode == IDGB200_SINCOS_FAST ? launch_gridder_tc(a, variant - 11, false, stream)
                                                 : cudaErrorInvalidValue;
+    case 22:   // as 21 with fp16 hi + lo phasors (FP32-class accuracy); 23: the same without the rotation
+      return sincos_mode == IDGB200_SINCOS_FAST ? launch_gridder_tc(a, 10, true, stream) : cudaErrorInvalidValue;
+    case 23:
+      return sincos_mode == IDGB200_SINCOS_FAST ? launch_gridder_tc(a, 10, false, stream) : cudaErrorInvalidValue;
     case 21:   // tensor-core kernel, phasors of equally spaced channel blocks by rotation (else as 12)
       return sincos_mode == IDGB200_SINCOS_FAST ? launch_gridder_tc(a, 1, true, stream) : cudaErrorInvalidValue;
     case 16: case 17: case 18: case 19:   // phasor tile in TMEM; 18, 19: fp16 hi + lo phasors

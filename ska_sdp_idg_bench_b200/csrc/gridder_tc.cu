@@ -51,54 +51,63 @@ constexpr int T2_B_SLOT = 2 * B_CHUNK_BYTES;     // 512 B
 constexpr int T2_NB = 16;                        // B ring slots
 constexpr int T2_THREADS = (T2_MAX_TILES + 1) * 32;
 
-template <unsigned MASK8>
+template <unsigned MASK8, bool SPLIT>
 __device__ __forceinline__ void tc_produce(unsigned char *A, const float *wn8, const float (&idx)[4],
-                                            const float (&idxr)[4], const float (&off)[4],
-                                            const float (&offr)[4], const int lane) {
+                                           const float (&idxr)[4], const float (&off)[4],
+                                           const float (&offr)[4], const int lane) {
 #pragma unroll
   for (int kc = 0; kc < 2; kc++) {
     const float4 wq = *reinterpret_cast<const float4 *>(wn8 + 4 * kc);
     const float wn[4] = {wq.x, wq.y, wq.z, wq.w};
 #pragma unroll
     for (int j = 0; j < 4; j++) {
-      unsigned pk[4];
+      unsigned pk[4], pl[4];
 #pragma unroll
       for (int i = 0; i < 4; i++) {
         const float2 ph = ((MASK8 >> (kc * 4 + i)) & 1u)
                               ? phasor_poly(__fmaf_rn(-idxr[j], wn[i], offr[j]))
                               : phasor<IDGB200_SINCOS_FAST>(__fmaf_rn(-idx[j], wn[i], off[j]));  // :69
-        const __half2 hh = __floats2half2_rn(ph.x, ph.y);
-        pk[i] = *reinterpret_cast<const unsigned *>(&hh);
+        pack_phasor<SPLIT>(ph, pk[i], pl[i]);
       }
       *reinterpret_cast<uint4 *>(A + kc * A_CHUNK_BYTES + (lane + 32 * j) * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      if (SPLIT)
+        *reinterpret_cast<uint4 *>(A + T2_A_STAGE + kc * A_CHUNK_BYTES + (lane + 32 * j) * 16) =
+            make_uint4(pl[0], pl[1], pl[2], pl[3]);
     }
   }
 }
 
 // The same stage for a block of equally spaced channels (common.cuh: linear_channels): one sincos
-// for the first channel (the same angle as above, bit for bit), one for the per-channel rotation
-// -idx * dw, then 7 complex multiplications - 4 MUFU + 28 FMA per pixel instead of 16 MUFU.
+// for the first channel (the same angle as above, bit for bit), the per-channel rotation
+// e^{-i idx dw} (rot), then 7 complex multiplications - 28 FMA per pixel instead of 14 MUFU.
+template <bool SPLIT>
 __device__ __forceinline__ void tc_produce_linear(unsigned char *A, const float wn0, const float2 (&rot)[4],
                                                   const float (&idx)[4], const float (&off)[4], const int lane) {
 #pragma unroll
   for (int j = 0; j < 4; j++) {
     float2 ph = phasor<IDGB200_SINCOS_FAST>(__fmaf_rn(-idx[j], wn0, off[j]));   // :69
     const float2 d = rot[j];
-    unsigned pk[8];
+    unsigned pk[8], pl[8];
 #pragma unroll
     for (int i = 0; i < 8; i++) {
-      const __half2 hh = __floats2half2_rn(ph.x, ph.y);
-      pk[i] = *reinterpret_cast<const unsigned *>(&hh);
+      pack_phasor<SPLIT>(ph, pk[i], pl[i]);
       if (i < 7) ph = make_float2(__fmaf_rn(ph.x, d.x, -__fmul_rn(ph.y, d.y)), __fmaf_rn(ph.x, d.y, __fmul_rn(ph.y, d.x)));
     }
     *reinterpret_cast<uint4 *>(A + (lane + 32 * j) * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
     *reinterpret_cast<uint4 *>(A + A_CHUNK_BYTES + (lane + 32 * j) * 16) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+    if (SPLIT) {
+      *reinterpret_cast<uint4 *>(A + T2_A_STAGE + (lane + 32 * j) * 16) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+      *reinterpret_cast<uint4 *>(A + T2_A_STAGE + A_CHUNK_BYTES + (lane + 32 * j) * 16) = make_uint4(pl[4], pl[5], pl[6], pl[7]);
+    }
   }
 }
 
 // MASK16: bit c set -> channel c of every 16-channel group uses phasor_poly instead of MUFU
 // recur: blocks of equally spaced channels use the rotation recurrence instead
-template <unsigned MASK16>
+// SPLIT: fp16 hi + lo phasors: the tile's two A buffers hold the hi and the lo block of ONE stage (two
+//        MMAs against the same B slot), so a warp waits for its own MMAs every stage - the other
+//        warps of the sub-partition cover that latency
+template <unsigned MASK16, bool SPLIT>
 __global__ void __launch_bounds__(T2_THREADS, 3)
 gridder_tc_kernel(const KernelArgs a, const int slabs, const int tiles_per_cta, const int tmem_cols, const int recur) {
   extern __shared__ __align__(1024) unsigned char smem[];
@@ -229,7 +238,7 @@ gridder_tc_kernel(const KernelArgs a, const int slabs, const int tiles_per_cta, 
 #pragma unroll
         for (int j = 0; j < 4; j++) rot[j] = make_float2(1.f, 0.f);
         for (int cb = 0; cb < ncb; cb++, k++) {
-          const unsigned stage = k & 1u, use = k >> 1;
+          const unsigned stage = SPLIT ? 0u : (k & 1u), use = SPLIT ? k : (k >> 1);
           if (use >= 1) mbar_wait_u(my_empty_u + stage * 8, (use - 1) & 1);
           unsigned char *A = A_tile + stage * T2_A_STAGE;
           if (s_lin[cb]) {
@@ -238,12 +247,12 @@ gridder_tc_kernel(const KernelArgs a, const int slabs, const int tiles_per_cta, 
 #pragma unroll
               for (int j = 0; j < 4; j++) rot[j] = phasor<IDGB200_SINCOS_FAST>(__fmul_rn(-idx[j], s_dw[cb]));
             }
-            tc_produce_linear(A, s_wn[cb * T2_CB], rot, idx, off, lane);
+            tc_produce_linear<SPLIT>(A, s_wn[cb * T2_CB], rot, idx, off, lane);
           }
           else if ((MASK16 >> 8) == (MASK16 & 0xffu) || !(cb & 1))
-            tc_produce<(MASK16 & 0xffu)>(A, s_wn + cb * T2_CB, idx, idxr, off, offr, lane);
+            tc_produce<(MASK16 & 0xffu), SPLIT>(A, s_wn + cb * T2_CB, idx, idxr, off, offr, lane);
           else
-            tc_produce<(MASK16 >> 8)>(A, s_wn + cb * T2_CB, idx, idxr, off, offr, lane);
+            tc_produce<(MASK16 >> 8), SPLIT>(A, s_wn + cb * T2_CB, idx, idxr, off, offr, lane);
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           // the whole warp waits for the B slot (one SYNCS either way) and stays converged, so the
           // descriptors live in uniform registers and one elected lane issues MMA + commits
@@ -254,6 +263,9 @@ gridder_tc_kernel(const KernelArgs a, const int slabs, const int tiles_per_cta, 
           if (elect_one()) {
             umma_f16(tmem_d, da0 + (unsigned long long)(stage * (T2_A_STAGE >> 4)),
                      db0 + (unsigned long long)(slot * (T2_B_SLOT >> 4)), idesc, k > 0 ? 1u : 0u);
+            if (SPLIT)
+              umma_f16(tmem_d, da0 + (unsigned long long)(T2_A_STAGE >> 4),
+                       db0 + (unsigned long long)(slot * (T2_B_SLOT >> 4)), idesc, 1u);
             umma_commit_u(my_empty_u + stage * 8);
             if ((k & 7) == 7) umma_commit_u(bempty_u + ((k >> 3) & 1) * 8);
             if (k == (unsigned)(nstages - 1)) umma_commit_u(done_u);
@@ -353,7 +365,8 @@ gridder_tc_kernel(const KernelArgs a, const int slabs, const int tiles_per_cta, 
 }  // namespace
 
 // FAST sincos only: the fp16 phasor operand is a FAST-class approximation.
-// poly: 0 = all phasors by MUFU; 1..4 = 4, 5, 6, 8 of every 16 channels by FP32 polynomial
+// poly: 0 = all phasors by MUFU; 1..4 = 4, 5, 6, 8 of every 16 channels by FP32 polynomial;
+//       10 = fp16 hi + lo phasors (FP32-class accuracy), all by MUFU / rotation
 // recur: blocks of 8 equally spaced channels get their phasors by rotation from the first one
 cudaError_t launch_gridder_tc(const KernelArgs &a, int poly, bool recur, cudaStream_t stream) {
   if (a.nr_subgrids == 0) return cudaSuccess;
@@ -371,11 +384,12 @@ cudaError_t launch_gridder_tc(const KernelArgs &a, int poly, bool recur, cudaStr
   if (smem > 200 * 1024) return cudaErrorInvalidValue;
   void (*k)(const KernelArgs, int, int, int, int) = nullptr;
   switch (poly) {
-    case 0: k = gridder_tc_kernel<0x0000u>; break;
-    case 1: k = gridder_tc_kernel<0x4444u>; break;   // 4 of 16: channels 2,6,10,14
-    case 2: k = gridder_tc_kernel<0x2492u>; break;   // 5 of 16: 1,4,7,10,13
-    case 3: k = gridder_tc_kernel<0x5252u>; break;   // 6 of 16: 1,4,6 | 9,12,14
-    case 4: k = gridder_tc_kernel<0x5555u>; break;   // 8 of 16
+    case 0: k = gridder_tc_kernel<0x0000u, false>; break;
+    case 1: k = gridder_tc_kernel<0x4444u, false>; break;   // 4 of 16: channels 2,6,10,14
+    case 2: k = gridder_tc_kernel<0x2492u, false>; break;   // 5 of 16: 1,4,7,10,13
+    case 3: k = gridder_tc_kernel<0x5252u, false>; break;   // 6 of 16: 1,4,6 | 9,12,14
+    case 4: k = gridder_tc_kernel<0x5555u, false>; break;   // 8 of 16
+    case 10: k = gridder_tc_kernel<0x0000u, true>; break;   // fp16 hi + lo phasors
     default: return cudaErrorInvalidValue;
   }
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

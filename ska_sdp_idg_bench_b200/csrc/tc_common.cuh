@@ -85,4 +85,17 @@ __device__ __forceinline__ float2 phasor_poly(float t /* revolutions */) {
   return make_float2(c, __fmul_rn(sn, r));
 }
 
+// (cos, sin) -> packed half2; with SPLIT also the rounding residual as a second half2, which goes
+// to a second A buffer and a second MMA against the same B slot: the operand then keeps ~22 bits
+template <bool SPLIT>
+__device__ __forceinline__ void pack_phasor(const float2 ph, unsigned &hi, unsigned &lo) {
+  const __half2 hh = __floats2half2_rn(ph.x, ph.y);
+  hi = *reinterpret_cast<const unsigned *>(&hh);
+  if (SPLIT) {
+    const float2 hf = __half22float2(hh);
+    const __half2 ll = __floats2half2_rn(__fsub_rn(ph.x, hf.x), __fsub_rn(ph.y, hf.y));
+    lo = *reinterpret_cast<const unsigned *>(&ll);
+  }
+}
+
 }  // namespace idgb200

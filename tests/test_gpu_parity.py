@@ -135,7 +135,7 @@ def test_gridder_tensor_core_variant(config1):
     """variant 11 = tcgen05 kernel (what variant 0 picks for FAST sincos), variant 10 = FP32
     kernel: both inside the FAST tolerance; the tensor kernel refuses the other sincos modes."""
     p, ref_g, _ = config1
-    for v in (11, 12, 13, 14, 15, 16, 17, 18, 19, 21):   # 12..15: part of the phasors from the FP32 polynomial; 16..19: phasor tile in TMEM
+    for v in (11, 12, 13, 14, 15, 16, 17, 18, 19, 21, 22, 23):   # 12..15: part of the phasors from the FP32 polynomial; 16..19: phasor tile in TMEM
         mx, rms = assert_close(run_gridder(p, idg.SINCOS_FAST, v), ref_g, 1, idg.SINCOS_FAST, f"gridder tcgen05 v{v}")
         print(f"tcgen05 gridder v{v}: per-pol max rel {mx}, rel rms {rms}")
     mx, rms = assert_close(run_gridder(p, idg.SINCOS_FAST, 10), ref_g, 1, idg.SINCOS_FAST, "gridder fp32")
@@ -144,7 +144,7 @@ def test_gridder_tensor_core_variant(config1):
         run_gridder(p, idg.SINCOS_ACCURATE, 11)
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4])
 def test_degridder_variants(config1, variant):
     p, _, ref_d = config1
     assert_close(run_degridder(p, idg.SINCOS_ACCURATE, variant), ref_d, 2, idg.SINCOS_ACCURATE,
@@ -169,8 +169,15 @@ def test_degridder_tensor_core_variant(config1):
         mx, rms = per_pol_errors(got, ref_d, 2)
         print(f"tcgen05 degridder v{v}: per-pol max rel {mx}, rel rms {rms}")
         assert (mx <= TOL_TC_DEGRIDDER[0]).all() and (rms <= TOL_TC_DEGRIDDER[1]).all(), (v, mx, rms)
-    mx, rms = assert_close(run_degridder(p, idg.SINCOS_FAST, 0), ref_d, 2, idg.SINCOS_FAST, "degridder fp32")
-    print(f"fp32 degridder (default): per-pol max rel {mx}, rel rms {rms}")
+    got = run_degridder(p, idg.SINCOS_FAST, 21)   # fp16 phasors + channel rotation: same class
+    mx, rms = per_pol_errors(got, ref_d, 2)
+    print(f"tcgen05 degridder v21: per-pol max rel {mx}, rel rms {rms}")
+    assert (mx <= TOL_TC_DEGRIDDER[0]).all() and (rms <= TOL_TC_DEGRIDDER[1]).all(), (21, mx, rms)
+    for v in (22, 23):   # fp16 hi + lo phasors: inside the stated FAST tolerance
+        mx, rms = assert_close(run_degridder(p, idg.SINCOS_FAST, v), ref_d, 2, idg.SINCOS_FAST, f"degridder tcgen05 v{v}")
+        print(f"tcgen05 degridder v{v} (hi+lo phasors): per-pol max rel {mx}, rel rms {rms}")
+    mx, rms = assert_close(run_degridder(p, idg.SINCOS_FAST, 4), ref_d, 2, idg.SINCOS_FAST, "degridder fp32")
+    print(f"fp32 degridder: per-pol max rel {mx}, rel rms {rms}")
     with pytest.raises(idg.IdgError):
         run_degridder(p, idg.SINCOS_ACCURATE, 11)
 
@@ -206,14 +213,14 @@ def test_shapes_vs_oracle(shape):
     for variant in (0, 2):
         assert_close(run_gridder(p, idg.SINCOS_ACCURATE, variant), ref_g, 1, idg.SINCOS_ACCURATE,
                      f"gridder {shape} v{variant}")
-    for variant in (11, 12, 17, 19, 21):
+    for variant in (11, 12, 17, 19, 21, 22):
         assert_close(run_gridder(p, idg.SINCOS_FAST, variant), ref_g, 1, idg.SINCOS_FAST,
                      f"gridder tcgen05 {shape} v{variant}")
     rows = covered_rows(p)
     for variant in (0, 2):
         got = run_degridder(p, idg.SINCOS_ACCURATE, variant)
         assert_close(got[rows], ref_d[rows], 2, idg.SINCOS_ACCURATE, f"degridder {shape} v{variant}")
-    for variant in (11, 12):   # random pixels: no cancellation, the fp16 phasors stay inside FAST
+    for variant in (11, 12, 21, 22):   # random pixels: no cancellation, the fp16 phasors stay inside FAST
         got = run_degridder(p, idg.SINCOS_FAST, variant)
         assert_close(got[rows], ref_d[rows], 2, idg.SINCOS_FAST, f"degridder tcgen05 {shape} v{variant}")
 

@@ -102,7 +102,7 @@ def test_argument_validation():
 # ------------------------------------------------------------------------ sharding
 def test_default_variant_selection():
     """variant 0: tcgen05 gridder only for FAST sincos and shapes that fill its 8-channel /
-    128-pixel tiles; the degridder default is always the FP32 kernel."""
+    128-pixel tiles; tcgen05 degridder (fp16 hi + lo phasors) likewise."""
     assert idg.resolve_variant(32, 16, idg.SINCOS_FAST) == 21
     assert idg.resolve_variant(24, 16, idg.SINCOS_FAST) == 21
     assert idg.resolve_variant(32, 16, idg.SINCOS_ACCURATE) == 10
@@ -110,8 +110,10 @@ def test_default_variant_selection():
     assert idg.resolve_variant(8, 1, idg.SINCOS_FAST) == 10      # 1 of 8 channels, 64 of 128 pixels
     assert idg.resolve_variant(32, 9, idg.SINCOS_FAST) == 10     # 9 of 16 channels
     assert idg.resolve_variant(32, 16, idg.SINCOS_FAST, variant=3) == 3
-    for mode in (idg.SINCOS_FAST, idg.SINCOS_ACCURATE):
-        assert idg.resolve_variant(32, 16, mode, gridder=False) == 0
+    assert idg.resolve_variant(32, 16, idg.SINCOS_FAST, gridder=False) == 22
+    assert idg.resolve_variant(32, 16, idg.SINCOS_ACCURATE, gridder=False) == 4
+    assert idg.resolve_variant(32, 1, idg.SINCOS_FAST, gridder=False) == 4     # 1 of 4 channels
+    assert idg.resolve_variant(8, 16, idg.SINCOS_FAST, gridder=False) == 4     # 64 pixels
 
 
 def test_partition_balanced_and_contiguous():
