@@ -225,6 +225,39 @@ def test_shapes_vs_oracle(shape):
         assert_close(got[rows], ref_d[rows], 2, idg.SINCOS_FAST, f"degridder tcgen05 {shape} v{variant}")
 
 
+def test_channel_rotation_is_checked_per_block():
+    """The default FAST kernels step through equally spaced channels by complex rotation
+    (DESIGN.md 4.5); the spacing is tested per block of 8 (gridder) / quad of 4 (degridder)
+    channels, so an array that is linear in one block and arbitrary in the next must take both
+    paths and still match the oracle; a single perturbed wavenumber must switch its block off."""
+    o = oracle()
+    p = random_problem(55, subgrid_size=32, nr_channels=16, max_timesteps=40, nr_subgrids=4)
+    wn = p.wavenumbers.copy()
+    wn[:8] = (2.6 + 0.013 * np.arange(8)).astype(np.float32)      # block 0: equally spaced
+    p.wavenumbers[:] = wn                                         # block 1: the random sorted values
+    ref_g, ref_d = o.gridder(p), o.degridder(p)
+    rows = covered_rows(p)
+    assert_close(run_gridder(p, idg.SINCOS_FAST), ref_g, 1, idg.SINCOS_FAST, "gridder mixed blocks")
+    assert_close(run_degridder(p, idg.SINCOS_FAST)[rows], ref_d[rows], 2, idg.SINCOS_FAST, "degridder mixed blocks")
+    # all 16 equally spaced except one channel moved by 1e-4 relative (far above 1.5 ulp): the
+    # rotation would be off by ~0.1 rad at |phase index| ~ 400; the check must catch it
+    q = random_problem(56, subgrid_size=32, nr_channels=16, max_timesteps=40, nr_subgrids=4)
+    q.wavenumbers[:] = (2.6 + 0.013 * np.arange(16)).astype(np.float32)
+    q.wavenumbers[5] *= np.float32(1.0001)
+    q.wavenumbers[14] *= np.float32(0.9999)
+    ref_g, ref_d = o.gridder(q), o.degridder(q)
+    rows = covered_rows(q)
+    assert_close(run_gridder(q, idg.SINCOS_FAST), ref_g, 1, idg.SINCOS_FAST, "gridder perturbed channel")
+    assert_close(run_degridder(q, idg.SINCOS_FAST)[rows], ref_d[rows], 2, idg.SINCOS_FAST, "degridder perturbed channel")
+    # and a fully linear array must agree with the per-channel kernels to rotation accuracy
+    q.wavenumbers[:] = (2.6 + 0.013 * np.arange(16)).astype(np.float32)
+    ref_g = o.gridder(q)
+    a, b = run_gridder(q, idg.SINCOS_FAST, 21), run_gridder(q, idg.SINCOS_FAST, 12)
+    assert_close(a, ref_g, 1, idg.SINCOS_FAST, "gridder rotation")
+    assert_close(b, ref_g, 1, idg.SINCOS_FAST, "gridder per-channel")
+    assert not np.array_equal(a, b), "variant 21 did not take the rotation path on equally spaced channels"
+
+
 def test_empty_inputs():
     p = random_problem(7, nr_subgrids=3)
     p.metadata["nr_timesteps"] = 0
