@@ -106,10 +106,12 @@ __device__ __forceinline__ void dtc_produce_linear(unsigned char *A, const float
       const float idx = __fadd_rn(__fmaf_rn(u, g.x, __fmul_rn(v, g.y)), __fmul_rn(w, g.z));
       float2 ph = phasor<IDGB200_SINCOS_FAST>(__fmaf_rn(idx, wn0, -g.w));
       const float2 d = phasor<IDGB200_SINCOS_FAST>(__fmul_rn(idx, dw));
+      const float2 dxx = make_float2(d.x, d.x), dny = make_float2(-d.y, d.y);
 #pragma unroll
       for (int j = 0; j < 4; j++) {
         pack_phasor<SPLIT>(ph, pk[j][i], pl[j][i]);
-        if (j < 3) ph = make_float2(__fmaf_rn(ph.x, d.x, -__fmul_rn(ph.y, d.y)), __fmaf_rn(ph.x, d.y, __fmul_rn(ph.y, d.x)));
+        // (x, y) * d = (x, y) * (dx, dx) + (y, x) * (-dy, dy): FMUL2 + FFMA2 (gridder_tc.cu)
+        if (j < 3) ph = ffma2(make_float2(ph.y, ph.x), dny, __fmul2_rn(ph, dxx));
       }
     }
 #pragma unroll

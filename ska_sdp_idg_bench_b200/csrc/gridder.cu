@@ -389,6 +389,8 @@ cudaError_t launch_gridder(const KernelArgs &a, int sincos_mode, int variant, cu
       return sincos_mode == IDGB200_SINCOS_FAST ? launch_gridder_tc(a, 10, true, stream) : cudaErrorInvalidValue;
     case 23:
       return sincos_mode == IDGB200_SINCOS_FAST ? launch_gridder_tc(a, 10, false, stream) : cudaErrorInvalidValue;
+    case 24:   // as 21 with 16 channels (K = 32) per stage, single-buffered
+      return sincos_mode == IDGB200_SINCOS_FAST ? launch_gridder_tc(a, 11, true, stream) : cudaErrorInvalidValue;
     case 21:   // tensor-core kernel, phasors of equally spaced channel blocks by rotation (else as 12)
       return sincos_mode == IDGB200_SINCOS_FAST ? launch_gridder_tc(a, 1, true, stream) : cudaErrorInvalidValue;
     case 16: case 17: case 18: case 19:   // phasor tile in TMEM; 18, 19: fp16 hi + lo phasors

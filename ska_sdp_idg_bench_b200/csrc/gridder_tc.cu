@@ -79,7 +79,7 @@ __device__ __forceinline__ void tc_produce(unsigned char *A, const float *wn8, c
 
 // The same stage for a block of equally spaced channels (common.cuh: linear_channels): one sincos
 // for the first channel (the same angle as above, bit for bit), the per-channel rotation
-// e^{-i idx dw} (rot), then 7 complex multiplications - 28 FMA per pixel instead of 14 MUFU.
+// e^{-i idx dw} (rot), then 7 complex multiplications (FMUL2 + FFMA2 each) instead of 14 MUFU.
 template <bool SPLIT>
 __device__ __forceinline__ void tc_produce_linear(unsigned char *A, const float wn0, const float2 (&rot)[4],
                                                   const float (&idx)[4], const float (&off)[4], const int lane) {
@@ -87,11 +87,14 @@ __device__ __forceinline__ void tc_produce_linear(unsigned char *A, const float 
   for (int j = 0; j < 4; j++) {
     float2 ph = phasor<IDGB200_SINCOS_FAST>(__fmaf_rn(-idx[j], wn0, off[j]));   // :69
     const float2 d = rot[j];
+    const float2 dxx = make_float2(d.x, d.x), dny = make_float2(-d.y, d.y);
     unsigned pk[8], pl[8];
 #pragma unroll
     for (int i = 0; i < 8; i++) {
       pack_phasor<SPLIT>(ph, pk[i], pl[i]);
-      if (i < 7) ph = make_float2(__fmaf_rn(ph.x, d.x, -__fmul_rn(ph.y, d.y)), __fmaf_rn(ph.x, d.y, __fmul_rn(ph.y, d.x)));
+      // (x, y) * d = (x, y) * (dx, dx) + (y, x) * (-dy, dy): FMUL2 + FFMA2 with free operand modes
+      // (broadcast scalar, LO_HI swizzle) - 2 issue slots instead of 4 in an issue-bound loop
+      if (i < 7) ph = ffma2(make_float2(ph.y, ph.x), dny, __fmul2_rn(ph, dxx));
     }
     *reinterpret_cast<uint4 *>(A + (lane + 32 * j) * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
     *reinterpret_cast<uint4 *>(A + A_CHUNK_BYTES + (lane + 32 * j) * 16) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
@@ -107,7 +110,9 @@ __device__ __forceinline__ void tc_produce_linear(unsigned char *A, const float 
 // SPLIT: fp16 hi + lo phasors: the tile's two A buffers hold the hi and the lo block of ONE stage (two
 //        MMAs against the same B slot), so a warp waits for its own MMAs every stage - the other
 //        warps of the sub-partition cover that latency
-template <unsigned MASK16, bool SPLIT>
+// WIDE:  the two A buffers hold the two channel blocks of one K = 32 stage (16 channels): the
+//        per-stage bookkeeping is amortised over 64 items instead of 32, single-buffered like SPLIT
+template <unsigned MASK16, bool SPLIT, bool WIDE = false>
 __global__ void __launch_bounds__(T2_THREADS, 3)
 gridder_tc_kernel(const KernelArgs a, const int slabs, const int tiles_per_cta, const int tmem_cols, const int recur) {
   extern __shared__ __align__(1024) unsigned char smem[];
@@ -224,7 +229,7 @@ gridder_tc_kernel(const KernelArgs a, const int slabs, const int tiles_per_cta, 
       asm volatile("" : "+l"(da0), "+l"(db0), "+r"(tmem_d), "+r"(my_empty_u), "+r"(bfull_u), "+r"(bempty_u), "+r"(done_u));
       float un = 0.f, vn = 0.f, wnx = 0.f;   // uvw of the next timestep, fetched one timestep ahead
       if (nt > 0) { un = __ldg(&g_uvw[0]); vn = __ldg(&g_uvw[1]); wnx = __ldg(&g_uvw[2]); }
-      unsigned k = 0;   // unsigned: slot / parity are masks and shifts, not signed divisions
+      unsigned k = 0, sk = 0;   // channel blocks (= B slots) and stages done; unsigned: masks and shifts
       for (int t = 0; t < nt; t++) {
         const float u = un, v = vn, w = wnx;
         if (t + 1 < nt) { un = __ldg(&g_uvw[3 * t + 3]); vn = __ldg(&g_uvw[3 * t + 4]); wnx = __ldg(&g_uvw[3 * t + 5]); }
@@ -237,40 +242,57 @@ gridder_tc_kernel(const KernelArgs a, const int slabs, const int tiles_per_cta, 
         float2 rot[4];
 #pragma unroll
         for (int j = 0; j < 4; j++) rot[j] = make_float2(1.f, 0.f);
-        for (int cb = 0; cb < ncb; cb++, k++) {
-          const unsigned stage = SPLIT ? 0u : (k & 1u), use = SPLIT ? k : (k >> 1);
+        for (int cb0 = 0; cb0 < ncb; cb0 += WIDE ? 2 : 1, sk++) {
+          const int nb = WIDE ? min(2, ncb - cb0) : 1;           // channel blocks of this stage
+          const unsigned stage = (SPLIT || WIDE) ? 0u : (sk & 1u), use = (SPLIT || WIDE) ? sk : (sk >> 1);
           if (use >= 1) mbar_wait_u(my_empty_u + stage * 8, (use - 1) & 1);
-          unsigned char *A = A_tile + stage * T2_A_STAGE;
-          if (s_lin[cb]) {
-            // the rotation step -idx * dw: once per timestep when every block has the same spacing
-            if (!same_dw || cb == 0) {
 #pragma unroll
-              for (int j = 0; j < 4; j++) rot[j] = phasor<IDGB200_SINCOS_FAST>(__fmul_rn(-idx[j], s_dw[cb]));
+          for (int b = 0; b < (WIDE ? 2 : 1); b++) {
+            if (b < nb) {
+              const int cb = cb0 + b;
+              unsigned char *A = A_tile + (stage + b) * T2_A_STAGE;
+              if (s_lin[cb]) {
+                // the rotation step -idx * dw: once per timestep when every block has the same spacing
+                if (!same_dw || cb == 0) {
+#pragma unroll
+                  for (int j = 0; j < 4; j++) rot[j] = phasor<IDGB200_SINCOS_FAST>(__fmul_rn(-idx[j], s_dw[cb]));
+                }
+                tc_produce_linear<SPLIT>(A, s_wn[cb * T2_CB], rot, idx, off, lane);
+              }
+              else if ((MASK16 >> 8) == (MASK16 & 0xffu) || !(cb & 1))
+                tc_produce<(MASK16 & 0xffu), SPLIT>(A, s_wn + cb * T2_CB, idx, idxr, off, offr, lane);
+              else
+                tc_produce<(MASK16 >> 8), SPLIT>(A, s_wn + cb * T2_CB, idx, idxr, off, offr, lane);
             }
-            tc_produce_linear<SPLIT>(A, s_wn[cb * T2_CB], rot, idx, off, lane);
           }
-          else if ((MASK16 >> 8) == (MASK16 & 0xffu) || !(cb & 1))
-            tc_produce<(MASK16 & 0xffu), SPLIT>(A, s_wn + cb * T2_CB, idx, idxr, off, offr, lane);
-          else
-            tc_produce<(MASK16 >> 8), SPLIT>(A, s_wn + cb * T2_CB, idx, idxr, off, offr, lane);
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          // the whole warp waits for the B slot (one SYNCS either way) and stays converged, so the
+          // the whole warp waits for the B slot(s) (one SYNCS either way) and stays converged, so the
           // descriptors live in uniform registers and one elected lane issues MMA + commits
-          const unsigned slot = k % (unsigned)T2_NB;
-          mbar_wait_u(bfull_u + slot * 8, (k / (unsigned)T2_NB) & 1u);
+#pragma unroll
+          for (int b = 0; b < (WIDE ? 2 : 1); b++)
+            if (b < nb) mbar_wait_u(bfull_u + ((k + b) % (unsigned)T2_NB) * 8, ((k + b) / (unsigned)T2_NB) & 1u);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           __syncwarp();
           if (elect_one()) {
-            umma_f16(tmem_d, da0 + (unsigned long long)(stage * (T2_A_STAGE >> 4)),
-                     db0 + (unsigned long long)(slot * (T2_B_SLOT >> 4)), idesc, k > 0 ? 1u : 0u);
-            if (SPLIT)
-              umma_f16(tmem_d, da0 + (unsigned long long)(T2_A_STAGE >> 4),
-                       db0 + (unsigned long long)(slot * (T2_B_SLOT >> 4)), idesc, 1u);
+#pragma unroll
+            for (int b = 0; b < (WIDE ? 2 : 1); b++) {
+              if (b < nb) {
+                const unsigned kb = k + b, slot = kb % (unsigned)T2_NB;
+                umma_f16(tmem_d, da0 + (unsigned long long)((stage + b) * (T2_A_STAGE >> 4)),
+                         db0 + (unsigned long long)(slot * (T2_B_SLOT >> 4)), idesc, kb > 0 ? 1u : 0u);
+                if (SPLIT)
+                  umma_f16(tmem_d, da0 + (unsigned long long)(T2_A_STAGE >> 4),
+                           db0 + (unsigned long long)(slot * (T2_B_SLOT >> 4)), idesc, 1u);
+              }
+            }
             umma_commit_u(my_empty_u + stage * 8);
-            if ((k & 7) == 7) umma_commit_u(bempty_u + ((k >> 3) & 1) * 8);
-            if (k == (unsigned)(nstages - 1)) umma_commit_u(done_u);
+#pragma unroll
+            for (int b = 0; b < (WIDE ? 2 : 1); b++)
+              if (b < nb && ((k + b) & 7) == 7) umma_commit_u(bempty_u + (((k + b) >> 3) & 1) * 8);
+            if (k + nb == (unsigned)nstages) umma_commit_u(done_u);
           }
           __syncwarp();
+          k += nb;
         }
       }
     }
@@ -366,7 +388,8 @@ gridder_tc_kernel(const KernelArgs a, const int slabs, const int tiles_per_cta, 
 
 // FAST sincos only: the fp16 phasor operand is a FAST-class approximation.
 // poly: 0 = all phasors by MUFU; 1..4 = 4, 5, 6, 8 of every 16 channels by FP32 polynomial;
-//       10 = fp16 hi + lo phasors (FP32-class accuracy), all by MUFU / rotation
+//       10 = fp16 hi + lo phasors (FP32-class accuracy), all by MUFU / rotation;
+//       11 = as 1 with 16 channels (K = 32) per stage
 // recur: blocks of 8 equally spaced channels get their phasors by rotation from the first one
 cudaError_t launch_gridder_tc(const KernelArgs &a, int poly, bool recur, cudaStream_t stream) {
   if (a.nr_subgrids == 0) return cudaSuccess;
@@ -390,6 +413,7 @@ cudaError_t launch_gridder_tc(const KernelArgs &a, int poly, bool recur, cudaStr
     case 3: k = gridder_tc_kernel<0x5252u, false>; break;   // 6 of 16: 1,4,6 | 9,12,14
     case 4: k = gridder_tc_kernel<0x5555u, false>; break;   // 8 of 16
     case 10: k = gridder_tc_kernel<0x0000u, true>; break;   // fp16 hi + lo phasors
+    case 11: k = gridder_tc_kernel<0x4444u, false, true>; break;   // as 1 with K = 32 stages
     default: return cudaErrorInvalidValue;
   }
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

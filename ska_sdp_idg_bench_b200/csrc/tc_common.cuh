@@ -93,7 +93,8 @@ __device__ __forceinline__ void pack_phasor(const float2 ph, unsigned &hi, unsig
   hi = *reinterpret_cast<const unsigned *>(&hh);
   if (SPLIT) {
     const float2 hf = __half22float2(hh);
-    const __half2 ll = __floats2half2_rn(__fsub_rn(ph.x, hf.x), __fsub_rn(ph.y, hf.y));
+    const float2 rs = __fadd2_rn(ph, make_float2(-hf.x, -hf.y));   // one packed FADD2 (exact: Sterbenz)
+    const __half2 ll = __floats2half2_rn(rs.x, rs.y);
     lo = *reinterpret_cast<const unsigned *>(&ll);
   }
 }
