@@ -38,15 +38,16 @@ SM_FP32_LANES = 128   # FP32 FMA lanes per SM (B200)
 SM_XU_LANES = 16      # MUFU lanes per SM
 # tensor-core gridder variants -> fraction of the phasors that come from the FP32 polynomial
 # instead of 2 MUFUs (gridder_tc.cu, launch_gridder_tc)
-# tensor-core gridder variants -> (MUFU per (pixel, visibility) item, warp instructions per warp-item
-# counted by ncu on the committed captures under profiles/).  11..15: 2 MUFU per item minus the share
-# replaced by an FP32 polynomial; 21 (equally spaced channels): per pixel one sincos per 8-channel block
-# (its first channel) and one per timestep (the rotation step), the rest by complex multiplication.
-TC_GRIDDER = {11: (2.0, 10.1), 12: (1.5, 12.6), 13: (1.375, 12.9), 14: (1.25, 13.3), 15: (1.0, 14.2), 21: (0.375, 10.0)}
-# degridder: 11..14 fp16 phasors (13: profiles/r01_degridder_tc_ncu_full.txt), 22: hi + lo phasors with the
-# channel rotation (profiles/r01_degridder_tc_split_ncu_full.txt); instruction counts of the others estimated
+# tensor-core kernel variants -> (MUFU per (pixel, visibility) item, dispatch cycles per warp-item).
+# Dispatch cycles = warp instructions + 1 per packed fp32x2 instruction (FFMA2 / FMUL2 / FADD2 hold the
+# sub-partition's dispatch port for two cycles: DESIGN.md 3), counted by ncu on the committed captures
+# under profiles/ (gridder 24, 12, 11; degridder 22, 13); the other variants' figures are estimates.
+# Gridder 11..15: 2 MUFU per item minus the share replaced by an FP32 polynomial; 21 / 24 (equally
+# spaced channels): per pixel one sincos per 8-channel block and one per timestep, the rest by rotation.
+TC_GRIDDER = {11: (2.0, 10.1), 12: (1.5, 12.6), 13: (1.375, 12.9), 14: (1.25, 13.3), 15: (1.0, 14.2),
+              21: (0.375, 10.0), 22: (0.375, 15.2), 23: (2.0, 17.1), 24: (0.375, 9.25)}
 TC_DEGRIDDER = {11: (2.0, 11.5), 12: (1.5, 13.5), 13: (1.25, 13.2), 14: (1.0, 15.5), 21: (1.0, 10.5),
-                22: (1.0, 16.5), 23: (2.0, 17.5)}
+                22: (1.0, 16.9), 23: (2.0, 18.5)}
 
 
 # ----------------------------------------------------------------- shared helpers
@@ -451,9 +452,9 @@ def run_ours(args) -> None:
         hbm_peak = float(peaks.get("hbm_gbs") or 6650.0)
 
         def roof(sec, steps, traffic_per_subgrid, tc):
-            """tc None: FP32 kernel (bound = the FP32 issue port); else (MUFU per item, warp
-            instructions per warp-item) of a tensor-core kernel, whose MACs run on tcgen05 and whose
-            roof is the XU (MUFU) pipe or the instruction issue port, whichever is busier."""
+            """tc None: FP32 kernel (bound = the FP32 issue port); else (MUFU per item, dispatch
+            cycles per warp-item) of a tensor-core kernel, whose MACs run on tcgen05 and whose roof
+            is the XU (MUFU) pipe or the instruction dispatch port, whichever is busier."""
             t = sec / steps
             tf = flops / t * 1e-12
             items = float(N) * N * tt * C_                     # (pixel, visibility) pairs per launch
@@ -477,21 +478,22 @@ def run_ours(args) -> None:
             else:
                 mufu_per_item, inst_per_item = tc
                 mufu = mufu_per_item * items / t               # MUFU.SIN + MUFU.COS executed per second
-                p_issue = sms * 4 * f_max * 1e6                 # warp instructions / s (1 per SMSP and cycle)
+                p_issue = sms * 4 * f_max * 1e6                 # dispatch cycles / s (1 per SMSP and clock)
                 issue = inst_per_item * items / 32.0 / t
                 sfu_frac, issue_frac = mufu / p_xu, issue / p_issue
                 note = ("tcgen05 kernel: the complex MACs run on the tensor pipe (6-8 %% busy); what bounds it is "
-                        "generating the phasor operand: %.2f MUFU and %.1f warp instructions per (pixel, "
-                        "visibility) against the XU pipe and the issue port (fp32_model_frac > 1 is the flop "
-                        "model's MACs having left the FP32 pipe)" % (mufu_per_item, inst_per_item))
+                        "generating the phasor operand: %.3f MUFU and %.2f dispatch cycles (instructions + 1 per "
+                        "packed fp32x2 instruction) per (pixel, visibility) against the XU pipe and the "
+                        "sub-partition's dispatch port (fp32_model_frac > 1 is the flop model's MACs and most of "
+                        "its sincos having left the FP32 / XU pipes)" % (mufu_per_item, inst_per_item))
                 if sfu_frac >= issue_frac:
                     r = dict({"bound": "sfu", "achieved": mufu * 1e-12, "peak": p_xu * 1e-12, "unit": "TMUFU/s",
                               "frac": sfu_frac, "peak_source": f"{sms} SMs x 16 MUFU lanes x {f_max:.0f} MHz"})
                 else:
                     r = dict({"bound": "issue", "achieved": issue * 1e-12, "peak": p_issue * 1e-12,
-                              "unit": "T warp-inst/s", "frac": issue_frac,
-                              "peak_source": f"{sms} SMs x 4 sub-partitions x 1 instruction/clk x {f_max:.0f} MHz; "
-                                             "instructions per item from the ncu capture under profiles/"})
+                              "unit": "T dispatch-cycles/s", "frac": issue_frac,
+                              "peak_source": f"{sms} SMs x 4 sub-partitions x {f_max:.0f} MHz; dispatch cycles per "
+                                             "item from the ncu capture under profiles/"})
                 r.update({"bound_note": note, "sfu_frac": sfu_frac, "issue_frac": issue_frac}, **common)
             if clocks.get("sm_mhz"):
                 r["frac_at_measured_clock"] = r["frac"] * f_max / clocks["sm_mhz"]
@@ -512,7 +514,7 @@ def run_ours(args) -> None:
                            gridder_kernel=("tcgen05: fp16 phasor tile x fp16 hi+lo visibilities, f32 accumulate in "
                                            "TMEM" + ("; phasors of equally spaced channels by rotation from the "
                                                      "first channel of each 8-channel block (as the reference's "
-                                                     "gridder_v8)" if g_variant == 21 else "")
+                                                     "gridder_v8)" if g_variant in (21, 24) else "")
                                            if tc_g is not None else "FP32 FFMA2 + MUFU"),
                            degridder_kernel=(("tcgen05: fp16 hi+lo phasor tile x fp16 hi+lo pixels, f32 accumulate in "
                                               "TMEM; phasors of equally spaced channel quads by rotation"

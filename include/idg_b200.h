@@ -129,7 +129,7 @@ uint64_t idgb200_launch_count(void);
 
 /* The kernel variant params->variant == 0 resolves to for this shape and sincos
  * mode (gridder != 0: the gridder, else the degridder); a non-zero variant is
- * returned unchanged.  Gridder: 21 = tcgen05 kernel (FAST sincos, shapes that fill
+ * returned unchanged.  Gridder: 24 / 21 = tcgen05 kernel (FAST sincos, shapes that fill
  * its tiles), 10 = FP32 kernel.  Degridder: 22 = tcgen05 kernel with fp16 hi + lo
  * phasors (FAST sincos), 4 = FP32 kernel.  IDGB200_EINVAL on bad params. */
 int idgb200_resolve_variant(const idgb200_params *params, int gridder);

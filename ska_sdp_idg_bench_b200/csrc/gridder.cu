@@ -350,8 +350,8 @@ cudaError_t launch_t(const KernelArgs &a, int mode, cudaStream_t stream) {
 }  // namespace
 
 // variant: 0 default: FAST sincos and a shape that fills >= 3/4 of its 8-channel blocks and
-//            128-pixel tiles -> tensor-core kernel (= variant 21, gridder_tc.cu); otherwise the
-//            FP32 kernel (= variant 10)
+//            128-pixel tiles -> tensor-core kernel (= variant 24, or 21 for an odd number of
+//            8-channel blocks; gridder_tc.cu); otherwise the FP32 kernel (= variant 10)
 //         10 FP32 kernel: swizzled FFMA2; 128 threads x 8 pixels (x 4 blocks/SM) when the
 //            subgrid has >= 1024 pixels, 128 x 4 below that
 //         11 tensor-core kernel (FAST sincos only), every phasor by MUFU
@@ -359,6 +359,8 @@ cudaError_t launch_t(const KernelArgs &a, int mode, cudaStream_t stream) {
 //         21 tensor-core kernel; blocks of 8 equally spaced channels get their phasors by complex
 //            rotation from the block's first channel (2 sincos per pixel and block instead of 8, as
 //            the reference's gridder_v8.cu does unconditionally), other blocks as variant 12
+//         24 the same with two channel blocks (K = 32) per stage, single-buffered
+//         22 / 23 as 21 / 11 with fp16 hi + lo phasors (FP32-class accuracy)
 //          1 scalar-FFMA baseline (256 x 4)
 //          2 swizzled FFMA2, 256 threads x 4 pixels
 //          3 swizzled FFMA2, 256 threads x 8 pixels
@@ -371,7 +373,8 @@ int resolve_gridder_variant(int subgrid_size, int nr_channels, int sincos_mode, 
   const int ncb = (nr_channels + 7) / 8, tiles = (npix + 127) / 128;
   const bool tc = sincos_mode == IDGB200_SINCOS_FAST && 4 * nr_channels >= 3 * ncb * 8 &&
                   4 * npix >= 3 * tiles * 128;
-  return tc ? 21 : 10;
+  if (!tc) return 10;
+  return ncb % 2 == 0 ? 24 : 21;   // K = 32 stages when the channel blocks pair up
 }
 
 cudaError_t launch_gridder(const KernelArgs &a, int sincos_mode, int variant, cudaStream_t stream) {
