@@ -203,13 +203,33 @@ int host_run(bool gridding, const idgb200_params *p, int64_t total_timesteps, in
                      cudaMemcpyHostToDevice, s_in));
   CK(cudaMemcpyAsync(d_meta, meta, (size_t)S * sizeof(idgb200_metadata), cudaMemcpyHostToDevice, s_in));
 
-  // chunking: ~IDGB200_CHUNKS chunks (default 16), at least 256 subgrids each
+  // chunking: ~IDGB200_CHUNKS chunks (default 16) of at least 256 subgrids in the body of the run;
+  // the first chunks ramp up from 256 subgrids by doubling and the last ones ramp down the same way,
+  // so that the copy that nothing overlaps (first upload, last kernel + download) is short
   long want = env_long("IDGB200_CHUNKS", 16);
   if (want < 1) want = 1;
   int chunk = (int)((S + want - 1) / want);
   if (chunk < 256) chunk = 256;
   if (env_long("IDGB200_CHUNK_SUBGRIDS", 0) > 0) chunk = (int)env_long("IDGB200_CHUNK_SUBGRIDS", 0);
-  const int nchunks = (S + chunk - 1) / chunk;
+  std::vector<int> bounds;   // chunk i = subgrids [bounds[i], bounds[i + 1])
+  {
+    std::vector<int> head, tail;
+    int lo = 0, hi = S;
+    if (env_long("IDGB200_CHUNK_RAMP", 1) != 0)
+      for (int c = 256; c < chunk && hi - lo > 2 * chunk; c *= 2) {
+        head.push_back(lo + c);
+        lo += c;
+        tail.push_back(hi - c);
+        hi -= c;
+      }
+    bounds.push_back(0);
+    for (int b : head) bounds.push_back(b);
+    for (int b = lo + chunk; b < hi; b += chunk) bounds.push_back(b);
+    for (int i = (int)tail.size() - 1; i >= 0; i--)
+      if (tail[i] > bounds.back()) bounds.push_back(tail[i]);
+    if (bounds.back() != S) bounds.push_back(S);
+  }
+  const int nchunks = (int)bounds.size() - 1;
   std::vector<cudaEvent_t> ev_in(nchunks), ev_k(nchunks);
   for (int i = 0; i < nchunks; i++) {
     CK(cudaEventCreateWithFlags(&ev_in[i], cudaEventDisableTiming));
@@ -241,7 +261,7 @@ int host_run(bool gridding, const idgb200_params *p, int64_t total_timesteps, in
                            (size_t)(r1 - r0) * C * NR_POL * sizeof(float2), cudaMemcpyDeviceToHost, s_out);
   };
   for (int i = 0; i < nchunks && !status; i++) {
-    const int s0 = i * chunk, s1 = (s0 + chunk < S) ? s0 + chunk : S;
+    const int s0 = bounds[i], s1 = bounds[i + 1];
     int64_t t0, t1;
     time_range(meta, s0, s1, &t0, &t1);
     if (t1 > t0) {
