@@ -371,8 +371,9 @@ int resolve_gridder_variant(int subgrid_size, int nr_channels, int sincos_mode, 
   // the tensor kernel pads the channels to blocks of 8 (K = 16) and the pixels to tiles of 128
   const int npix = subgrid_size * subgrid_size;
   const int ncb = (nr_channels + 7) / 8, tiles = (npix + 127) / 128;
+  // (and keeps 10 floats per channel block in shared memory: beyond 1024 channels the FP32 kernel)
   const bool tc = sincos_mode == IDGB200_SINCOS_FAST && 4 * nr_channels >= 3 * ncb * 8 &&
-                  4 * npix >= 3 * tiles * 128;
+                  4 * npix >= 3 * tiles * 128 && nr_channels <= 1024;
   if (!tc) return 10;
   return ncb % 2 == 0 ? 24 : 21;   // K = 32 stages when the channel blocks pair up
 }

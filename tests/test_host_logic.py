@@ -110,6 +110,7 @@ def test_default_variant_selection():
     assert idg.resolve_variant(32, 16, idg.SINCOS_REDUCED) == 10
     assert idg.resolve_variant(8, 1, idg.SINCOS_FAST) == 10      # 1 of 8 channels, 64 of 128 pixels
     assert idg.resolve_variant(32, 9, idg.SINCOS_FAST) == 10     # 9 of 16 channels
+    assert idg.resolve_variant(32, 4096, idg.SINCOS_FAST) == 10  # wavenumber tables beyond the smem budget
     assert idg.resolve_variant(32, 16, idg.SINCOS_FAST, variant=3) == 3
     assert idg.resolve_variant(32, 16, idg.SINCOS_FAST, gridder=False) == 22
     assert idg.resolve_variant(32, 16, idg.SINCOS_ACCURATE, gridder=False) == 4
