@@ -358,7 +358,7 @@ cudaError_t launch_t(const KernelArgs &a, int mode, cudaStream_t stream) {
 //         12 tensor-core kernel, 4 of every 16 channels' phasors by FP32 polynomial (13: 5, 14: 6, 15: 8)
 //         21 tensor-core kernel; blocks of 8 equally spaced channels get their phasors by complex
 //            rotation from the block's first channel (2 sincos per pixel and block instead of 8, as
-//            the reference's gridder_v8.cu does unconditionally), other blocks as variant 12
+//            the reference's gridder_v8.cu does unconditionally), other blocks as variant 14
 //         24 the same with two channel blocks (K = 32) per stage, single-buffered
 //         22 / 23 as 21 / 11 with fp16 hi + lo phasors (FP32-class accuracy)
 //          1 scalar-FFMA baseline (256 x 4)
@@ -396,7 +396,7 @@ cudaError_t launch_gridder(const KernelArgs &a, int sincos_mode, int variant, cu
     case 24:   // as 21 with 16 channels (K = 32) per stage, single-buffered
       return sincos_mode == IDGB200_SINCOS_FAST ? launch_gridder_tc(a, 11, true, stream) : cudaErrorInvalidValue;
     case 21:   // tensor-core kernel, phasors of equally spaced channel blocks by rotation (else as 12)
-      return sincos_mode == IDGB200_SINCOS_FAST ? launch_gridder_tc(a, 1, true, stream) : cudaErrorInvalidValue;
+      return sincos_mode == IDGB200_SINCOS_FAST ? launch_gridder_tc(a, 3, true, stream) : cudaErrorInvalidValue;
     case 16: case 17: case 18: case 19:   // phasor tile in TMEM; 18, 19: fp16 hi + lo phasors
       return sincos_mode == IDGB200_SINCOS_FAST ? launch_gridder_tc3(a, variant - 16, stream)
                                                 : cudaErrorInvalidValue;

@@ -389,7 +389,7 @@ gridder_tc_kernel(const KernelArgs a, const int slabs, const int tiles_per_cta, 
 // FAST sincos only: the fp16 phasor operand is a FAST-class approximation.
 // poly: 0 = all phasors by MUFU; 1..4 = 4, 5, 6, 8 of every 16 channels by FP32 polynomial;
 //       10 = fp16 hi + lo phasors (FP32-class accuracy), all by MUFU / rotation;
-//       11 = as 1 with 16 channels (K = 32) per stage
+//       11 = as 3 with 16 channels (K = 32) per stage
 // recur: blocks of 8 equally spaced channels get their phasors by rotation from the first one
 cudaError_t launch_gridder_tc(const KernelArgs &a, int poly, bool recur, cudaStream_t stream) {
   if (a.nr_subgrids == 0) return cudaSuccess;
@@ -413,7 +413,7 @@ cudaError_t launch_gridder_tc(const KernelArgs &a, int poly, bool recur, cudaStr
     case 3: k = gridder_tc_kernel<0x5252u, false>; break;   // 6 of 16: 1,4,6 | 9,12,14
     case 4: k = gridder_tc_kernel<0x5555u, false>; break;   // 8 of 16
     case 10: k = gridder_tc_kernel<0x0000u, true>; break;   // fp16 hi + lo phasors
-    case 11: k = gridder_tc_kernel<0x4444u, false, true>; break;   // as 1 with K = 32 stages
+    case 11: k = gridder_tc_kernel<0x5252u, false, true>; break;   // as 3 with K = 32 stages
     default: return cudaErrorInvalidValue;
   }
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
