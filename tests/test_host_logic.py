@@ -118,6 +118,26 @@ def test_default_variant_selection():
     assert idg.resolve_variant(8, 16, idg.SINCOS_FAST, gridder=False) == 4     # 64 pixels
 
 
+def test_ska_low_scale_chunk_plan_covers_the_observation_once():
+    """tools/ska_low_scale.py (BASELINE config 4): the chunks dealt to the ranks are disjoint and
+    add up to the 8,372,224 subgrids of the observation, for every world size the bench uses."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ska_low_scale", os.path.join(ROOT, "tools", "ska_low_scale.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    assert mod.TOTAL_SUBGRIDS == 8372224
+    for world in (1, 2, 4, 8):
+        seen, total = set(), 0
+        for rank in range(world):
+            mine, sizes, n = mod.chunk_plan(32704, world, rank)
+            assert not (seen & set(mine))
+            seen |= set(mine)
+            total += sum(sizes)
+        assert len(seen) == n and total == mod.TOTAL_SUBGRIDS
+    mine, sizes, _ = mod.chunk_plan(32704, 8, 3, chunks_per_rank=2)
+    assert len(mine) == 2 and all(0 < s <= 32704 for s in sizes)
+
+
 def test_partition_balanced_and_contiguous():
     rng = np.random.default_rng(0)
     nt = rng.integers(0, 200, 1000)
