@@ -175,6 +175,38 @@ def cpu_problem(oracle_lib, shape: dict, nr_subgrids: int):
         subgrids=np.ascontiguousarray(p.subgrids[:S]))
 
 
+def reference_gpu_kernels() -> dict | None:
+    """The reference's own fastest CUDA kernels (app/CUDA/kernels/gridder_v8.cu, degridder_v6.cu with
+    its own host runner and main, compiled in place for sm_100a by oracle/Makefile `refcuda`) in their
+    performance mode on this box: the same-box GPU comparator of BASELINE.md 1.  Not the `--impl
+    reference` arm (that is the CPU path); reported beside it.  None if the binaries are absent."""
+    import re
+    import subprocess
+    import tempfile
+    out = {}
+    for key, exe in (("gridder", "refcuda-gridder_v8"), ("degridder", "refcuda-degridder_v6")):
+        path = os.path.join(ROOT, "oracle", "_ref", exe)
+        if not os.path.exists(path):
+            return None
+        with tempfile.TemporaryDirectory() as tmp:
+            env = dict(os.environ, OUTPUT_PATH=tmp)
+            for k in ("NR_STATIONS", "NR_TIMESLOTS", "NR_CHANNELS", "SUBGRID_SIZE", "GRID_SIZE",
+                      "NR_TIMESTEPS_SUBGRID", "NR_ITERATIONS", "NR_WARM_UP_RUNS"):
+                env.pop(k, None)     # the reference's default perf shape = bench config 2
+            try:
+                txt = subprocess.run([path], env=env, capture_output=True, text=True, timeout=300).stdout
+            except (OSError, subprocess.TimeoutExpired):
+                return None
+        m = re.search(r"(\w+):\s+([0-9.]+) ms,\s+([0-9.]+) GFLOP/s,.*?([0-9.]+) MVis/s", txt)
+        if not m:
+            return None
+        out[key] = {"kernel": m.group(1), "ms_per_launch": float(m.group(2)),
+                    "tflops": float(m.group(3)) * 1e-3, "mvis_per_s": float(m.group(4))}
+    out["what"] = ("the reference's unmodified gridder_v8 / degridder_v6 (sources compiled where they lie, "
+                   "sm_100a) through its own p_run_* at its default shape (= this workload), 5 launches")
+    return out
+
+
 def host_threads() -> int:
     """Cores this process may use.  torchrun exports OMP_NUM_THREADS=1, which is not what
     "all the host threads it can use" means, so the CPU arm sets the count explicitly."""
@@ -441,6 +473,8 @@ def run_ours(args) -> None:
                                                 np.abs(ref_d[..., p]).max()) for p in range(4)],
         }
 
+    ref_gpu = reference_gpu_kernels() if (rank == 0 and world == 1 and not args.no_cpu) else None
+
     if rank == 0:
         peaks = measured_peaks()
         sms = idg.sm_count()
@@ -537,6 +571,7 @@ def run_ours(args) -> None:
                 "value": total_mvis * args.steps / sec_d32, "unit": "MVis/s", "variant": 4,
                 "ms_per_step": sec_d32 / args.steps * 1e3,
                 "roofline": roof(sec_d32, args.steps, 128.329e6 / 1740, None)},
+            "reference_gpu": ref_gpu,
             "cpu_baseline": cpu_baseline, "parity": parity, "e2e": e2e,
             "gpu_launches": int(launches_g), "degridder_gpu_launches": int(launches_d),
             "clocks": clocks, "device": idg.device_name(),
