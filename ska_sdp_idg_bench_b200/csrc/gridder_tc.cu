@@ -33,6 +33,16 @@
 //   epilogue: tcgen05.ld of the accumulators (a warp can only read its own 32-lane quadrant),
 //     A-terms, taper, coalesced stores - identical math to gridder.cu.
 // Every mbarrier wait is bounded (trap instead of hang).
+//
+// On top of that, selected by template / launch parameters:
+//   recur - blocks of 8 equally spaced channels (checked per block, common.cuh: linear_channels) get
+//           their phasors by complex rotation from the block's first channel, FMUL2 + FFMA2 per
+//           step, as the reference's gridder_v8 assumes unconditionally: the XU stops being the
+//           roof, the dispatch port takes over;
+//   WIDE  - both channel blocks of a timestep in the tile's two A buffers as one K = 32 stage;
+//   SPLIT - fp16 hi + lo phasors (second A buffer, second MMA): FP32-class accuracy;
+//   MASK16 - where the recurrence does not apply, part of the channels' phasors from an FP32
+//           polynomial instead of MUFU.
 #include <cuda_fp16.h>
 
 #include "common.cuh"
