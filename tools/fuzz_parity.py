@@ -1,0 +1,52 @@
+"""Randomised parity run (not part of the pytest suite): many random ragged shapes through the
+default FAST kernels (tcgen05 where the shape qualifies) and a few explicit variants, against the
+oracle.  Usage: python tools/fuzz_parity.py [n_cases] [seed]"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import ska_sdp_idg_bench_b200 as idg  # noqa: E402
+from oracle_lib import oracle, random_problem  # noqa: E402
+from test_gpu_parity import TOL, covered_rows, per_pol_errors, run_degridder, run_gridder  # noqa: E402
+
+n_cases = int(sys.argv[1]) if len(sys.argv) > 1 else 40
+rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 1)
+o = oracle()
+o.set_threads(o.max_threads())
+tmx, trms = TOL[idg.SINCOS_FAST]
+worst = 0.0
+for case in range(n_cases):
+    N = int(rng.choice([16, 20, 24, 32, 40, 48, 64]))
+    C = int(rng.choice([4, 8, 12, 16, 24, 32, 33, 64]))
+    T = int(rng.integers(1, 70))
+    S = int(rng.integers(1, 6))
+    linear = bool(rng.integers(0, 2))
+    p = random_problem(int(rng.integers(1 << 30)), subgrid_size=N, nr_channels=C, max_timesteps=T, nr_subgrids=S,
+                       nr_stations=int(rng.integers(2, 7)), nr_slots=int(rng.integers(1, 4)))
+    if linear:
+        p.wavenumbers[:] = (2.5 + rng.uniform(0.001, 0.02) * np.arange(C)).astype(np.float32)
+    ref_g, ref_d = o.gridder(p), o.degridder(p)
+    rows = covered_rows(p)
+    for gv in (0, 22):
+        mx, rms = per_pol_errors(run_gridder(p, idg.SINCOS_FAST, gv), ref_g, 1)
+        ok = (mx <= tmx).all() and (rms <= trms).all()
+        worst = max(worst, rms.max() / trms, mx.max() / tmx)
+        if not ok:
+            print("FAIL gridder", gv, dict(N=N, C=C, T=T, S=S, linear=linear), mx, rms)
+            sys.exit(1)
+    if rows.any():
+        for dv in (0, 23):
+            got = run_degridder(p, idg.SINCOS_FAST, dv)
+            mx, rms = per_pol_errors(got[rows], ref_d[rows], 2)
+            ok = (mx <= tmx).all() and (rms <= trms).all() and not got[~rows].any()
+            worst = max(worst, rms.max() / trms, mx.max() / tmx)
+            if not ok:
+                print("FAIL degridder", dv, dict(N=N, C=C, T=T, S=S, linear=linear), mx, rms)
+                sys.exit(1)
+    print(f"case {case}: N={N} C={C} T<={T} S={S} linear={linear} gridder v{idg.resolve_variant(N, C, 0)} "
+          f"degridder v{idg.resolve_variant(N, C, 0, gridder=False)} ok, worst error / tolerance so far {worst:.3f}")
+print(f"{n_cases} cases passed; worst error / tolerance = {worst:.3f}")
