@@ -218,9 +218,14 @@ degridder_tc_kernel(const KernelArgs a, const int recur) {
     const unsigned idesc = (1u << 4) | ((16u >> 3) << 17) | ((128u >> 4) << 24);
     unsigned char *A_tile = sA + warp * D_STAGES * D_A_STAGE;
     unsigned long long *my_empty = aempty + warp * D_STAGES;
-    const unsigned long long da0 = smem_desc(smem_u32(A_tile), A_CHUNK_BYTES, 128);
-    const unsigned long long db0 = smem_desc(smem_u32(sB), B_CHUNK_BYTES, 128);
-    const unsigned tmem_d = tmem_base + warp * 16;
+    unsigned long long da0 = smem_desc(smem_u32(A_tile), A_CHUNK_BYTES, 128);
+    unsigned long long db0 = smem_desc(smem_u32(sB), B_CHUNK_BYTES, 128);
+    unsigned tmem_d = tmem_base + warp * 16;
+    // barrier addresses as 32-bit shared addresses, computed once and made opaque so that the
+    // compiler keeps them instead of rematerialising the address arithmetic in every issue path
+    unsigned my_empty_u = smem_u32(my_empty), bfull_u = smem_u32(bfull), bempty_u = smem_u32(bempty),
+             done_u = smem_u32(done);
+    asm volatile("" : "+l"(da0), "+l"(db0), "+r"(tmem_d), "+r"(my_empty_u), "+r"(bfull_u), "+r"(bempty_u), "+r"(done_u));
     float4 *g_vis = reinterpret_cast<float4 *>(const_cast<float2 *>(a.visibilities)) +
                     (size_t)ctx.time_offset * C * 2;
     int kk = 0, GG = 0;   // running stage / ring-group counters: barrier phases continue across rounds
@@ -240,8 +245,8 @@ degridder_tc_kernel(const KernelArgs a, const int recur) {
         for (int k = 0; k < nstages; k++, kk++) {
           const int stage = SPLIT ? 0 : (kk & 1), use = SPLIT ? kk : (kk >> 1);
           const int G = GG + (k >> 2), grp = G % D_NG, slot = grp * D_GROUP + (k & (D_GROUP - 1));
-          if ((k & (D_GROUP - 1)) == 0) mbar_wait(&bfull[grp], (G / D_NG) & 1);
-          if (use >= 1) mbar_wait(&my_empty[stage], (use - 1) & 1);
+          if ((k & (D_GROUP - 1)) == 0) mbar_wait_u(bfull_u + grp * 8, (G / D_NG) & 1);
+          if (use >= 1) mbar_wait_u(my_empty_u + stage * 8, (use - 1) & 1);
           if (warp_lin)
             dtc_produce_linear<SPLIT>(A_tile + stage * D_A_STAGE, sG + slot * D_PB, u, v, w, wn[0], dw, lane);
           else
@@ -255,9 +260,9 @@ degridder_tc_kernel(const KernelArgs a, const int recur) {
             if (SPLIT)
               umma_f16(tmem_d, da0 + (unsigned long long)(D_A_STAGE >> 4),
                        db0 + (unsigned long long)(slot * (D_B_SLOT >> 4)), idesc, 1u);
-            umma_commit(&my_empty[stage]);
-            if ((k & (D_GROUP - 1)) == D_GROUP - 1 || k == nstages - 1) umma_commit(&bempty[grp]);
-            if (k == nstages - 1) umma_commit(done);
+            umma_commit_u(my_empty_u + stage * 8);
+            if ((k & (D_GROUP - 1)) == D_GROUP - 1 || k == nstages - 1) umma_commit_u(bempty_u + grp * 8);
+            if (k == nstages - 1) umma_commit_u(done_u);
           }
         }
       } else if (warp < tpr) {
