@@ -127,6 +127,20 @@ int idgb200_degridder(const idgb200_params *params, const idgb200_uvw *d_uvw,
  * (bench.py reports it as gpu_launches). */
 uint64_t idgb200_launch_count(void);
 
+/* ---- "next" row: grid adder ------------------------------------
+ * Not in the reference (it only declares idg::Grid, app/common/types.hpp:358-370,
+ * and the subgrid coordinate, types.hpp:11-13); follows the gridder in IDG.
+ *   grid[pol][y0 + y][x0 + x] += d_subgrids[s][pol][y][x]   ((x0, y0) = metadata[s].x/.y,
+ *   pixels outside the grid dropped), for the params->nr_subgrids subgrids.
+ * The grid is cut into nr_parts (<= 16) blocks of rows_per_part rows; grid_parts is
+ * a HOST array of nr_parts device pointers, part r laid out as complex64
+ * [4][rows_per_part][grid_size].  One GPU: nr_parts = 1, rows_per_part = grid_size.
+ * N GPUs: part r may be a peer (NVLink) address of the slice rank r owns - the
+ * kernel's atomics then are the reduce-scatter.  Accumulates (the caller zeroes). */
+int idgb200_adder(const idgb200_params *params, const idgb200_metadata *d_metadata,
+                  const idgb200_cfloat *d_subgrids, idgb200_cfloat *const *grid_parts,
+                  int nr_parts, int rows_per_part, void *stream);
+
 /* The kernel variant params->variant == 0 resolves to for this shape and sincos
  * mode (gridder != 0: the gridder, else the degridder); a non-zero variant is
  * returned unchanged.  Gridder: 24 / 21 = tcgen05 kernel (FAST sincos, shapes that fill

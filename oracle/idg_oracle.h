@@ -61,6 +61,12 @@ void idgo_degridder(int nr_subgrids, int grid_size, int subgrid_size,
                     const float *spheroidal, const float *aterms,
                     const idgo_metadata *metadata, const float *subgrids);
 
+/* "Next" row 8f-1, NOT part of the pinned path (idg_adder_oracle.c: parity UNPINNED - the
+ * reference has no adder): grid[pol][y0 + y][x0 + x] += subgrids[s][pol][y][x], clipped at the
+ * grid edge; grid is complex64 [4][grid_size][grid_size]. */
+void idgo_adder(int nr_subgrids, int grid_size, int subgrid_size, const idgo_metadata *metadata,
+                const float *subgrids, float *grid);
+
 /* Same formulas evaluated in float64 throughout (phase, sincos, sums) from the
  * same float32 inputs: the "truth" used to budget the float32 error.  Outputs
  * are interleaved doubles. */

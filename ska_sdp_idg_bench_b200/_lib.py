@@ -35,6 +35,7 @@ SYMBOLS = {
     "idgb200_degridder": (C.c_int, [C.POINTER(Params)] + [_P] * 8),
     "idgb200_launch_count": (C.c_uint64, []),
     "idgb200_resolve_variant": (C.c_int, [C.POINTER(Params), C.c_int]),
+    "idgb200_adder": (C.c_int, [C.POINTER(Params), _P, _P, C.POINTER(C.c_void_p), C.c_int, C.c_int, _P]),
     "idgb200_c_run_gridder": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int,
                                         C.c_int, C.c_int64, C.c_int] + [_P] * 7),
     "idgb200_c_run_degridder": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int,

@@ -68,6 +68,21 @@ def launch_count() -> int:
     return int(lib.idgb200_launch_count())
 
 
+def adder(nr_subgrids, grid_size, subgrid_size, metadata, subgrids, grid_parts, rows_per_part=None,
+          stream=None) -> None:
+    """Grid adder: accumulate the subgrids (torch CUDA tensors) into the grid.
+
+    ``grid_parts``: one complex64 CUDA tensor [4][grid_size][grid_size] (single GPU), or a list of
+    tensors / integer device addresses, part r = complex64 [4][rows_per_part][grid_size] holding grid
+    rows [r * rows_per_part, ...) - addresses may be peer memory of other GPUs."""
+    parts = grid_parts if isinstance(grid_parts, (list, tuple)) else [grid_parts]
+    rpp = int(grid_size if rows_per_part is None else rows_per_part)
+    arr = (C.c_void_p * len(parts))(*[int(q) if isinstance(q, int) else q.data_ptr() for q in parts])
+    p = _params(nr_subgrids, grid_size, subgrid_size, 1.0, 0.0, 1, 1, SINCOS_FAST, 0)
+    _check(lib.idgb200_adder(C.byref(p), C.c_void_p(metadata.data_ptr()), C.c_void_p(subgrids.data_ptr()),
+                             arr, len(parts), rpp, _stream_ptr(stream)))
+
+
 def resolve_variant(subgrid_size, nr_channels, sincos=SINCOS_FAST, variant=0, gridder=True) -> int:
     """The kernel variant `variant=0` selects for this shape (idgb200_resolve_variant)."""
     p = _params(1, max(subgrid_size, 1), subgrid_size, 1.0, 0.0, nr_channels, 1, sincos, variant)

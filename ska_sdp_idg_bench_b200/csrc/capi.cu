@@ -694,6 +694,25 @@ int idgb200_degridder(const idgb200_params *p, const idgb200_uvw *d_uvw, const f
 
 uint64_t idgb200_launch_count(void) { return g_launches.load(); }
 
+int idgb200_adder(const idgb200_params *p, const idgb200_metadata *d_meta, const idgb200_cfloat *d_sg,
+                  idgb200_cfloat *const *grid_parts, int nr_parts, int rows_per_part, void *stream) {
+  int rc = check_params(p);
+  if (rc) return rc;
+  if (!d_meta || !d_sg || !grid_parts || nr_parts < 1 || nr_parts > 16 || rows_per_part < 1 ||
+      (long long)nr_parts * rows_per_part < p->grid_size)
+    return IDGB200_EINVAL;
+  for (int i = 0; i < nr_parts; i++)
+    if (!grid_parts[i]) return IDGB200_EINVAL;
+  if ((rc = have_device())) return rc;
+  cudaError_t e = launch_adder(p->nr_subgrids, 0, p->grid_size, p->subgrid_size, d_meta,
+                               reinterpret_cast<const float2 *>(d_sg),
+                               reinterpret_cast<float2 *const *>(grid_parts), nr_parts, rows_per_part,
+                               static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return (int)e;
+  g_launches++;
+  return IDGB200_OK;
+}
+
 int idgb200_resolve_variant(const idgb200_params *p, int gridder) {
   int rc = check_params(p);
   if (rc) return rc;

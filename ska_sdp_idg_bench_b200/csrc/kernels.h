@@ -10,6 +10,11 @@ namespace idgb200 {
 cudaError_t launch_gridder(const KernelArgs &a, int sincos_mode, int variant, cudaStream_t stream);
 cudaError_t launch_degridder(const KernelArgs &a, int sincos_mode, int variant, cudaStream_t stream);
 
+// grid adder (adder.cu): parts[r] = base of the r-th block of rows_per_part grid rows (may be a peer address)
+cudaError_t launch_adder(int nr_subgrids, int subgrid_offset, int grid_size, int subgrid_size,
+                         const idgb200_metadata *metadata, const float2 *subgrids, float2 *const *parts,
+                         int nr_parts, int rows_per_part, cudaStream_t stream);
+
 // what variant 0 means for this shape / sincos mode (other values are returned unchanged)
 int resolve_gridder_variant(int subgrid_size, int nr_channels, int sincos_mode, int variant);
 int resolve_degridder_variant(int subgrid_size, int nr_channels, int sincos_mode, int variant);

@@ -89,6 +89,15 @@ class _Lib:
         self._run("gridder", p, p.visibilities, out)
         return out
 
+    def adder(self, p: "Problem", subgrids=None) -> np.ndarray:
+        """Grid adder (oracle only; SURVEY 8f-1, parity unpinned): complex64 [4][G][G]."""
+        assert not self.is_reference, "the reference has no adder"
+        sg = np.ascontiguousarray(p.subgrids if subgrids is None else subgrids)
+        grid = np.zeros((4, p.grid_size, p.grid_size), np.complex64)
+        self._f("adder")(C.c_int(p.nr_subgrids), C.c_int(p.grid_size), C.c_int(p.subgrid_size),
+                         _ptr(p.metadata), _ptr(sg), _ptr(grid))
+        return grid
+
     def degridder(self, p: "Problem") -> np.ndarray:
         out = np.full((p.total_timesteps, p.nr_channels, 4), np.nan, np.complex64)
         self._run("degridder", p, out, p.subgrids)
