@@ -83,8 +83,16 @@ typedef struct {
   int32_t nr_stations;
   int32_t sincos_mode; /* IDGB200_SINCOS_*  */
   int32_t variant;     /* 0 = default kernel; others are documented A/B variants */
-  int32_t reserved[7];
+  int32_t flags;       /* IDGB200_FLAG_*; 0 = the reference's behaviour */
+  int32_t reserved[6];
 } idgb200_params;
+
+/* Subgrid FFT shift.  The bench's kernels store / read subgrid pixel (y, x) at [pol][y][x]
+ * (gridder_reference.cpp:105-109, degridder_reference.cpp:38-46); the full IDG pipeline pairs
+ * subgrid pixel ((y + N/2) mod N, (x + N/2) mod N) with offset (y, x).  With this flag the
+ * gridder stores, the degridder reads, and the adder / splitter address the subgrid at the
+ * shifted index; every value is unchanged.  Default off = the reference's layout. */
+#define IDGB200_FLAG_FFT_SHIFT 1
 
 /* ---- library / device ------------------------------------------------------ */
 int idgb200_version(void);
@@ -127,19 +135,35 @@ int idgb200_degridder(const idgb200_params *params, const idgb200_uvw *d_uvw,
  * (bench.py reports it as gpu_launches). */
 uint64_t idgb200_launch_count(void);
 
-/* ---- "next" row: grid adder ------------------------------------
+/* ---- "next" rows: grid adder, subgrid FFT, splitter ------------
  * Not in the reference (it only declares idg::Grid, app/common/types.hpp:358-370,
- * and the subgrid coordinate, types.hpp:11-13); follows the gridder in IDG.
- *   grid[pol][y0 + y][x0 + x] += d_subgrids[s][pol][y][x]   ((x0, y0) = metadata[s].x/.y,
- *   pixels outside the grid dropped), for the params->nr_subgrids subgrids.
+ * and the subgrid coordinate, types.hpp:11-13); they surround the two kernels in IDG:
+ *   gridder -> subgrid FFT -> adder -> [grid] -> splitter -> inverse FFT -> degridder.
+ *
+ * Adder:    grid[pol][y0 + y][x0 + x] += d_subgrids[s][pol][y'][x']  ((x0, y0) = metadata[s].x/.y,
+ *           pixels outside the grid dropped), for the params->nr_subgrids subgrids.
+ * Splitter: d_subgrids[s][pol][y'][x'] = grid[pol][y0 + y][x0 + x], 0 outside the grid.
+ *           (y', x') = (y, x), or the shifted index with IDGB200_FLAG_FFT_SHIFT in params->flags.
  * The grid is cut into nr_parts (<= 16) blocks of rows_per_part rows; grid_parts is
  * a HOST array of nr_parts device pointers, part r laid out as complex64
  * [4][rows_per_part][grid_size].  One GPU: nr_parts = 1, rows_per_part = grid_size.
  * N GPUs: part r may be a peer (NVLink) address of the slice rank r owns - the
- * kernel's atomics then are the reduce-scatter.  Accumulates (the caller zeroes). */
+ * adder's atomics then are the reduce-scatter, the splitter's loads the all-gather.
+ * The adder accumulates (the caller zeroes); the splitter overwrites every subgrid pixel. */
 int idgb200_adder(const idgb200_params *params, const idgb200_metadata *d_metadata,
                   const idgb200_cfloat *d_subgrids, idgb200_cfloat *const *grid_parts,
                   int nr_parts, int rows_per_part, void *stream);
+int idgb200_splitter(const idgb200_params *params, const idgb200_metadata *d_metadata,
+                     idgb200_cfloat *d_subgrids, const idgb200_cfloat *const *grid_parts,
+                     int nr_parts, int rows_per_part, void *stream);
+
+/* Subgrid FFT: in-place 2-D DFT of each of the nr_subgrids * 4 planes of N x N pixels.
+ *   direction = +1 (forward, after the gridder):  B[ky][kx] = sum A[y][x] exp(-2 pi i (ky y + kx x) / N)
+ *   direction = -1 (backward, before the degridder): exp(+...), scaled by 1 / N^2
+ * so that backward(forward(A)) = A.  Any N >= 1; N = 8, 16, 24, 32, 48, 64 take the
+ * register-resident kernel, other sizes a direct DFT. */
+int idgb200_subgrid_fft(int64_t nr_subgrids, int subgrid_size, int direction,
+                        idgb200_cfloat *d_subgrids, void *stream);
 
 /* The kernel variant params->variant == 0 resolves to for this shape and sincos
  * mode (gridder != 0: the gridder, else the degridder); a non-zero variant is

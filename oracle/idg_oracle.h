@@ -61,11 +61,19 @@ void idgo_degridder(int nr_subgrids, int grid_size, int subgrid_size,
                     const float *spheroidal, const float *aterms,
                     const idgo_metadata *metadata, const float *subgrids);
 
-/* "Next" row 8f-1, NOT part of the pinned path (idg_adder_oracle.c: parity UNPINNED - the
- * reference has no adder): grid[pol][y0 + y][x0 + x] += subgrids[s][pol][y][x], clipped at the
- * grid edge; grid is complex64 [4][grid_size][grid_size]. */
-void idgo_adder(int nr_subgrids, int grid_size, int subgrid_size, const idgo_metadata *metadata,
+/* "Next" rows 8f-1..3, NOT part of the pinned path (idg_next_oracle.c: parity UNPINNED - the
+ * reference has no adder, FFT or splitter).  grid is complex64 [4][grid_size][grid_size].
+ *   adder:    grid[pol][y0 + y][x0 + x] += subgrids[s][pol][y'][x'], clipped at the grid edge
+ *   splitter: subgrids[s][pol][y'][x']   = grid[pol][y0 + y][x0 + x], 0 outside the grid
+ *   (y', x') = (y, x), or ((y + N/2) % N, (x + N/2) % N) with IDGO_FFT_SHIFT
+ *   subgrid_fft: in-place 2-D DFT of nr_planes N x N planes, direction >= 0 forward (exp(-i),
+ *   unscaled), < 0 backward (exp(+i), scaled by 1/N^2); double-precision sums rounded once. */
+#define IDGO_FFT_SHIFT 1
+void idgo_adder(int nr_subgrids, int grid_size, int subgrid_size, int flags, const idgo_metadata *metadata,
                 const float *subgrids, float *grid);
+void idgo_splitter(int nr_subgrids, int grid_size, int subgrid_size, int flags, const idgo_metadata *metadata,
+                   float *subgrids, const float *grid);
+void idgo_subgrid_fft(long nr_planes, int subgrid_size, int direction, float *planes);
 
 /* Same formulas evaluated in float64 throughout (phase, sincos, sums) from the
  * same float32 inputs: the "truth" used to budget the float32 error.  Outputs

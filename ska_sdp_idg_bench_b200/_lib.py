@@ -12,7 +12,7 @@ class Params(C.Structure):  # idgb200_params
         ("nr_subgrids", C.c_int32), ("grid_size", C.c_int32), ("subgrid_size", C.c_int32),
         ("image_size", C.c_float), ("w_step_in_lambda", C.c_float), ("nr_channels", C.c_int32),
         ("nr_stations", C.c_int32), ("sincos_mode", C.c_int32), ("variant", C.c_int32),
-        ("reserved", C.c_int32 * 7),
+        ("flags", C.c_int32), ("reserved", C.c_int32 * 6),
     ]
 
 
@@ -36,6 +36,8 @@ SYMBOLS = {
     "idgb200_launch_count": (C.c_uint64, []),
     "idgb200_resolve_variant": (C.c_int, [C.POINTER(Params), C.c_int]),
     "idgb200_adder": (C.c_int, [C.POINTER(Params), _P, _P, C.POINTER(C.c_void_p), C.c_int, C.c_int, _P]),
+    "idgb200_splitter": (C.c_int, [C.POINTER(Params), _P, _P, C.POINTER(C.c_void_p), C.c_int, C.c_int, _P]),
+    "idgb200_subgrid_fft": (C.c_int, [C.c_int64, C.c_int, C.c_int, _P, _P]),
     "idgb200_c_run_gridder": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int,
                                         C.c_int, C.c_int64, C.c_int] + [_P] * 7),
     "idgb200_c_run_degridder": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int,

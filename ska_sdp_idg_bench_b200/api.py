@@ -21,6 +21,7 @@ from ._lib import Params, Perf, lib
 from .layout import METADATA_DTYPE, NR_CORRELATIONS
 
 SINCOS_FAST, SINCOS_REDUCED, SINCOS_ACCURATE = 0, 1, 2
+FLAG_FFT_SHIFT = 1  # IDGB200_FLAG_FFT_SHIFT
 
 
 class IdgError(RuntimeError):
@@ -68,19 +69,42 @@ def launch_count() -> int:
     return int(lib.idgb200_launch_count())
 
 
+def _grid_parts(grid_parts, grid_size, rows_per_part):
+    parts = grid_parts if isinstance(grid_parts, (list, tuple)) else [grid_parts]
+    rpp = int(grid_size if rows_per_part is None else rows_per_part)
+    arr = (C.c_void_p * len(parts))(*[int(q) if isinstance(q, int) else q.data_ptr() for q in parts])
+    return arr, len(parts), rpp
+
+
 def adder(nr_subgrids, grid_size, subgrid_size, metadata, subgrids, grid_parts, rows_per_part=None,
-          stream=None) -> None:
+          stream=None, flags: int = 0) -> None:
     """Grid adder: accumulate the subgrids (torch CUDA tensors) into the grid.
 
     ``grid_parts``: one complex64 CUDA tensor [4][grid_size][grid_size] (single GPU), or a list of
     tensors / integer device addresses, part r = complex64 [4][rows_per_part][grid_size] holding grid
     rows [r * rows_per_part, ...) - addresses may be peer memory of other GPUs."""
-    parts = grid_parts if isinstance(grid_parts, (list, tuple)) else [grid_parts]
-    rpp = int(grid_size if rows_per_part is None else rows_per_part)
-    arr = (C.c_void_p * len(parts))(*[int(q) if isinstance(q, int) else q.data_ptr() for q in parts])
-    p = _params(nr_subgrids, grid_size, subgrid_size, 1.0, 0.0, 1, 1, SINCOS_FAST, 0)
+    arr, n, rpp = _grid_parts(grid_parts, grid_size, rows_per_part)
+    p = _params(nr_subgrids, grid_size, subgrid_size, 1.0, 0.0, 1, 1, SINCOS_FAST, 0, flags)
     _check(lib.idgb200_adder(C.byref(p), C.c_void_p(metadata.data_ptr()), C.c_void_p(subgrids.data_ptr()),
-                             arr, len(parts), rpp, _stream_ptr(stream)))
+                             arr, n, rpp, _stream_ptr(stream)))
+
+
+def splitter(nr_subgrids, grid_size, subgrid_size, metadata, subgrids, grid_parts, rows_per_part=None,
+             stream=None, flags: int = 0) -> None:
+    """Splitter, the adder's inverse: every pixel of ``subgrids`` is overwritten with
+    the grid value under it (0 outside the grid).  ``grid_parts`` as for :func:`adder`."""
+    arr, n, rpp = _grid_parts(grid_parts, grid_size, rows_per_part)
+    p = _params(nr_subgrids, grid_size, subgrid_size, 1.0, 0.0, 1, 1, SINCOS_FAST, 0, flags)
+    _check(lib.idgb200_splitter(C.byref(p), C.c_void_p(metadata.data_ptr()),
+                                C.c_void_p(subgrids.data_ptr()), arr, n, rpp, _stream_ptr(stream)))
+
+
+def subgrid_fft(nr_subgrids, subgrid_size, subgrids, direction: int = 1, stream=None) -> None:
+    """Subgrid FFT: in-place 2-D DFT of the nr_subgrids * 4 planes of ``subgrids``
+    (complex64 CUDA tensor [S][4][N][N]); direction +1 forward (unscaled), -1 backward (1/N^2)."""
+    N = int(subgrid_size)
+    ptr = _dev_ptr(subgrids, "subgrids", int(nr_subgrids) * N * N * 32)
+    _check(lib.idgb200_subgrid_fft(int(nr_subgrids), N, int(direction), ptr, _stream_ptr(stream)))
 
 
 def resolve_variant(subgrid_size, nr_channels, sincos=SINCOS_FAST, variant=0, gridder=True) -> int:
@@ -93,7 +117,7 @@ def resolve_variant(subgrid_size, nr_channels, sincos=SINCOS_FAST, variant=0, gr
 
 
 def _params(nr_subgrids, grid_size, subgrid_size, image_size, w_step_in_lambda, nr_channels,
-            nr_stations, sincos, variant) -> Params:
+            nr_stations, sincos, variant, flags=0) -> Params:
     p = Params()
     p.nr_subgrids = int(nr_subgrids)
     p.grid_size = int(grid_size)
@@ -104,6 +128,7 @@ def _params(nr_subgrids, grid_size, subgrid_size, image_size, w_step_in_lambda, 
     p.nr_stations = int(nr_stations)
     p.sincos_mode = int(sincos)
     p.variant = int(variant)
+    p.flags = int(flags)
     return p
 
 
@@ -148,27 +173,27 @@ def _host_args(nr_subgrids, subgrid_size, nr_channels, nr_stations, uvw, wavenum
 
 def c_run_gridder(nr_subgrids, grid_size, subgrid_size, image_size, w_step_in_lambda, nr_channels,
                   nr_stations, uvw, wavenumbers, visibilities, spheroidal, aterms, metadata,
-                  subgrids, *, sincos: int = SINCOS_FAST, variant: int = 0) -> None:
+                  subgrids, *, sincos: int = SINCOS_FAST, variant: int = 0, flags: int = 0) -> None:
     """cuda::c_run_gridder (tests/gridder_common.cpp:21-30): host arrays in,
     ``subgrids`` [S][4][N][N] complex64 overwritten."""
     tt, slots, ptrs = _host_args(nr_subgrids, subgrid_size, nr_channels, nr_stations, uvw,
                                  wavenumbers, visibilities, spheroidal, aterms, metadata, subgrids,
                                  vis_out=False, sg_out=True)
     p = _params(nr_subgrids, grid_size, subgrid_size, image_size, w_step_in_lambda, nr_channels,
-                nr_stations, sincos, variant)
+                nr_stations, sincos, variant, flags)
     _check(lib.idgb200_c_run_gridder_ex(C.byref(p), tt, slots, *ptrs))
 
 
 def c_run_degridder(nr_subgrids, grid_size, subgrid_size, image_size, w_step_in_lambda, nr_channels,
                     nr_stations, uvw, wavenumbers, visibilities, spheroidal, aterms, metadata,
-                    subgrids, *, sincos: int = SINCOS_FAST, variant: int = 0) -> None:
+                    subgrids, *, sincos: int = SINCOS_FAST, variant: int = 0, flags: int = 0) -> None:
     """cuda::c_run_degridder (tests/degridder_common.cpp:21-30): host arrays in,
     ``visibilities`` [T][C][4] complex64 overwritten."""
     tt, slots, ptrs = _host_args(nr_subgrids, subgrid_size, nr_channels, nr_stations, uvw,
                                  wavenumbers, visibilities, spheroidal, aterms, metadata, subgrids,
                                  vis_out=True, sg_out=False)
     p = _params(nr_subgrids, grid_size, subgrid_size, image_size, w_step_in_lambda, nr_channels,
-                nr_stations, sincos, variant)
+                nr_stations, sincos, variant, flags)
     _check(lib.idgb200_c_run_degridder_ex(C.byref(p), tt, slots, *ptrs))
 
 
@@ -194,7 +219,7 @@ def _stream_ptr(stream) -> C.c_void_p:
 
 def _device_call(fn, nr_subgrids, grid_size, subgrid_size, image_size, w_step_in_lambda,
                  nr_channels, nr_stations, total_timesteps, uvw, wavenumbers, visibilities,
-                 spheroidal, aterms, metadata, subgrids, sincos, variant, stream):
+                 spheroidal, aterms, metadata, subgrids, sincos, variant, stream, flags=0):
     N, C_ = int(subgrid_size), int(nr_channels)
     tt = int(total_timesteps)
     ptrs = [
@@ -207,26 +232,28 @@ def _device_call(fn, nr_subgrids, grid_size, subgrid_size, image_size, w_step_in
         _dev_ptr(subgrids, "subgrids", int(nr_subgrids) * N * N * 32),
     ]
     p = _params(nr_subgrids, grid_size, subgrid_size, image_size, w_step_in_lambda, nr_channels,
-                nr_stations, sincos, variant)
+                nr_stations, sincos, variant, flags)
     _check(fn(C.byref(p), *ptrs, _stream_ptr(stream)))
 
 
 def gridder(nr_subgrids, grid_size, subgrid_size, image_size, w_step_in_lambda, nr_channels,
             nr_stations, total_timesteps, uvw, wavenumbers, visibilities, spheroidal, aterms,
-            metadata, subgrids, *, sincos: int = SINCOS_FAST, variant: int = 0, stream=None) -> None:
+            metadata, subgrids, *, sincos: int = SINCOS_FAST, variant: int = 0, stream=None,
+            flags: int = 0) -> None:
     """One asynchronous gridder launch on device-resident tensors (the kernel launch
-    of app/CUDA/util.cpp:163-170)."""
+    of app/CUDA/util.cpp:163-170).  ``flags=FLAG_FFT_SHIFT`` stores pixel (y, x) at the shifted index."""
     _device_call(lib.idgb200_gridder, nr_subgrids, grid_size, subgrid_size, image_size,
                  w_step_in_lambda, nr_channels, nr_stations, total_timesteps, uvw, wavenumbers,
-                 visibilities, spheroidal, aterms, metadata, subgrids, sincos, variant, stream)
+                 visibilities, spheroidal, aterms, metadata, subgrids, sincos, variant, stream, flags)
 
 
 def degridder(nr_subgrids, grid_size, subgrid_size, image_size, w_step_in_lambda, nr_channels,
               nr_stations, total_timesteps, uvw, wavenumbers, visibilities, spheroidal, aterms,
-              metadata, subgrids, *, sincos: int = SINCOS_FAST, variant: int = 0, stream=None) -> None:
+              metadata, subgrids, *, sincos: int = SINCOS_FAST, variant: int = 0, stream=None,
+              flags: int = 0) -> None:
     _device_call(lib.idgb200_degridder, nr_subgrids, grid_size, subgrid_size, image_size,
                  w_step_in_lambda, nr_channels, nr_stations, total_timesteps, uvw, wavenumbers,
-                 visibilities, spheroidal, aterms, metadata, subgrids, sincos, variant, stream)
+                 visibilities, spheroidal, aterms, metadata, subgrids, sincos, variant, stream, flags)
 
 
 # ------------------------------------------------------------- performance runs

@@ -55,6 +55,7 @@ int check_params(const idgb200_params *p) {
     return IDGB200_EINVAL;
   if (!(p->image_size > 0.0f)) return IDGB200_EINVAL;
   if (p->sincos_mode < 0 || p->sincos_mode > IDGB200_SINCOS_ACCURATE) return IDGB200_EINVAL;
+  if (p->flags & ~IDGB200_FLAG_FFT_SHIFT) return IDGB200_EINVAL;
   return IDGB200_OK;
 }
 
@@ -77,6 +78,7 @@ KernelArgs make_args(const idgb200_params *p, const idgb200_uvw *uvw, const floa
   a.subgrids = reinterpret_cast<const float2 *>(sg);
   a.nr_subgrids = p->nr_subgrids;
   a.subgrid_offset = 0;
+  a.flags = p->flags;
   return a;
 }
 
@@ -704,10 +706,48 @@ int idgb200_adder(const idgb200_params *p, const idgb200_metadata *d_meta, const
   for (int i = 0; i < nr_parts; i++)
     if (!grid_parts[i]) return IDGB200_EINVAL;
   if ((rc = have_device())) return rc;
-  cudaError_t e = launch_adder(p->nr_subgrids, 0, p->grid_size, p->subgrid_size, d_meta,
+  cudaError_t e = launch_adder(p->nr_subgrids, 0, p->grid_size, p->subgrid_size, p->flags, d_meta,
                                reinterpret_cast<const float2 *>(d_sg),
                                reinterpret_cast<float2 *const *>(grid_parts), nr_parts, rows_per_part,
                                static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return (int)e;
+  g_launches++;
+  return IDGB200_OK;
+}
+
+int idgb200_splitter(const idgb200_params *p, const idgb200_metadata *d_meta, idgb200_cfloat *d_sg,
+                     const idgb200_cfloat *const *grid_parts, int nr_parts, int rows_per_part, void *stream) {
+  int rc = check_params(p);
+  if (rc) return rc;
+  if (!d_meta || !d_sg || !grid_parts || nr_parts < 1 || nr_parts > 16 || rows_per_part < 1 ||
+      (long long)nr_parts * rows_per_part < p->grid_size)
+    return IDGB200_EINVAL;
+  for (int i = 0; i < nr_parts; i++)
+    if (!grid_parts[i]) return IDGB200_EINVAL;
+  if ((rc = have_device())) return rc;
+  cudaError_t e = launch_splitter(p->nr_subgrids, 0, p->grid_size, p->subgrid_size, p->flags, d_meta,
+                                  reinterpret_cast<float2 *>(d_sg),
+                                  reinterpret_cast<const float2 *const *>(grid_parts), nr_parts, rows_per_part,
+                                  static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return (int)e;
+  g_launches++;
+  return IDGB200_OK;
+}
+
+int idgb200_subgrid_fft(int64_t nr_subgrids, int subgrid_size, int direction, idgb200_cfloat *d_sg,
+                        void *stream) {
+  if (nr_subgrids < 0 || subgrid_size < 1 || (direction != 1 && direction != -1) ||
+      nr_subgrids * NR_POL > 0x7fffffffLL)
+    return IDGB200_EINVAL;
+  if (nr_subgrids > 0 && !d_sg) return IDGB200_EINVAL;
+  // shared memory of the direct-DFT kernel that serves the unusual sizes
+  if (((size_t)2 * subgrid_size * (subgrid_size + 1) + subgrid_size) * sizeof(float2) > 200 * 1024)
+    return IDGB200_EUNSUPPORTED;
+  int rc = have_device();
+  if (rc) return rc;
+  if (nr_subgrids == 0) return IDGB200_OK;
+  cudaError_t e = launch_subgrid_fft(nr_subgrids * NR_POL, subgrid_size, direction,
+                                     reinterpret_cast<float2 *>(d_sg), static_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) return (int)e;
   g_launches++;
   return IDGB200_OK;

@@ -82,10 +82,11 @@ degridder_kernel(const KernelArgs a) {
       const int q = tile0 + i;
       const int y = q / N, x = q - y * N;
       const float sph = __ldg(&a.spheroidal[q]);
+      const int src = subgrid_slot(q, N, a.flags);
       float2 px[NR_POL];
 #pragma unroll
       for (int p = 0; p < NR_POL; p++) {
-        const float2 v = __ldg(&sub[p * plane + q]);
+        const float2 v = __ldg(&sub[p * plane + src]);
         px[p] = make_float2(__fmul_rn(sph, v.x), __fmul_rn(sph, v.y));
       }
       float2 a1[4], a2[4];

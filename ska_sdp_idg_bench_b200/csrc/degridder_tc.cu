@@ -45,9 +45,10 @@ constexpr int D_TMEM_COLS = D_MAX_TILES * 16;   // 128 columns (power of two >= 
 __device__ __forceinline__ void pixel_after_aterms(const KernelArgs &a, const float2 *sub, size_t plane, size_t at1,
                                                    size_t at2, int q, float2 (&px)[NR_POL]) {
   const float sph = __ldg(&a.spheroidal[q]);
+  const int src = subgrid_slot(q, a.subgrid_size, a.flags);
 #pragma unroll
   for (int p = 0; p < NR_POL; p++) {
-    const float2 v = __ldg(&sub[p * plane + q]);
+    const float2 v = __ldg(&sub[p * plane + src]);
     px[p] = make_float2(__fmul_rn(sph, v.x), __fmul_rn(sph, v.y));
   }
   float2 a1[4], a2[4];

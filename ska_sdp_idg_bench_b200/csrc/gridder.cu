@@ -315,9 +315,10 @@ gridder_kernel(const KernelArgs a, const int slabs, const int vis_per_chunk) {
       load_jones(a.aterms, (at2 + pix[j]) * NR_POL, a2);
       apply_aterm_gridder(px, a1, a2);
       const float sph = __ldg(&a.spheroidal[pix[j]]);
+      const int slot = subgrid_slot(pix[j], a.subgrid_size, a.flags);
 #pragma unroll
       for (int p = 0; p < NR_POL; p++)
-        out[p * plane + pix[j]] = make_float2(__fmul_rn(px[p].x, sph), __fmul_rn(px[p].y, sph));
+        out[p * plane + slot] = make_float2(__fmul_rn(px[p].x, sph), __fmul_rn(px[p].y, sph));
     }
   }
 }

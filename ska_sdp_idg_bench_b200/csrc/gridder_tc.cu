@@ -382,9 +382,10 @@ gridder_tc_kernel(const KernelArgs a, const int slabs, const int tiles_per_cta, 
         load_jones(a.aterms, (at2 + pixel) * NR_POL, a2);
         apply_aterm_gridder(px, a1, a2);
         const float sph = __ldg(&a.spheroidal[pixel]);
+        const int dst = subgrid_slot(pixel, a.subgrid_size, a.flags);
 #pragma unroll
         for (int p = 0; p < NR_POL; p++)
-          out[p * plane + pixel] = make_float2(__fmul_rn(px[p].x, sph), __fmul_rn(px[p].y, sph));
+          out[p * plane + dst] = make_float2(__fmul_rn(px[p].x, sph), __fmul_rn(px[p].y, sph));
       }
     }
   }

@@ -11,9 +11,19 @@ cudaError_t launch_gridder(const KernelArgs &a, int sincos_mode, int variant, cu
 cudaError_t launch_degridder(const KernelArgs &a, int sincos_mode, int variant, cudaStream_t stream);
 
 // grid adder (adder.cu): parts[r] = base of the r-th block of rows_per_part grid rows (may be a peer address)
-cudaError_t launch_adder(int nr_subgrids, int subgrid_offset, int grid_size, int subgrid_size,
+// flags: IDGB200_FLAG_FFT_SHIFT
+cudaError_t launch_adder(int nr_subgrids, int subgrid_offset, int grid_size, int subgrid_size, int flags,
                          const idgb200_metadata *metadata, const float2 *subgrids, float2 *const *parts,
                          int nr_parts, int rows_per_part, cudaStream_t stream);
+// splitter (adder.cu): the adder's inverse, subgrids read out of the grid parts
+cudaError_t launch_splitter(int nr_subgrids, int subgrid_offset, int grid_size, int subgrid_size, int flags,
+                            const idgb200_metadata *metadata, float2 *subgrids, const float2 *const *parts,
+                            int nr_parts, int rows_per_part, cudaStream_t stream);
+
+// subgrid FFT (subgrid_fft.cu): in-place 2-D DFT of nr_planes N x N planes; direction >= 0 forward
+// (exp(-i)), < 0 backward (exp(+i), scaled by 1/N^2)
+cudaError_t launch_subgrid_fft(long long nr_planes, int subgrid_size, int direction, float2 *planes,
+                               cudaStream_t stream);
 
 // what variant 0 means for this shape / sincos mode (other values are returned unchanged)
 int resolve_gridder_variant(int subgrid_size, int nr_channels, int sincos_mode, int variant);

@@ -89,14 +89,32 @@ class _Lib:
         self._run("gridder", p, p.visibilities, out)
         return out
 
-    def adder(self, p: "Problem", subgrids=None) -> np.ndarray:
+    def adder(self, p: "Problem", subgrids=None, flags=0) -> np.ndarray:
         """Grid adder (oracle only; SURVEY 8f-1, parity unpinned): complex64 [4][G][G]."""
         assert not self.is_reference, "the reference has no adder"
         sg = np.ascontiguousarray(p.subgrids if subgrids is None else subgrids)
         grid = np.zeros((4, p.grid_size, p.grid_size), np.complex64)
         self._f("adder")(C.c_int(p.nr_subgrids), C.c_int(p.grid_size), C.c_int(p.subgrid_size),
-                         _ptr(p.metadata), _ptr(sg), _ptr(grid))
+                         C.c_int(flags), _ptr(p.metadata), _ptr(sg), _ptr(grid))
         return grid
+
+    def splitter(self, p: "Problem", grid: np.ndarray, flags=0) -> np.ndarray:
+        """Splitter (oracle only; SURVEY 8f-3, parity unpinned): complex64 [S][4][N][N]."""
+        assert not self.is_reference, "the reference has no splitter"
+        grid = np.ascontiguousarray(grid, np.complex64)
+        sg = np.full((p.nr_subgrids, 4, p.subgrid_size, p.subgrid_size), np.nan, np.complex64)
+        self._f("splitter")(C.c_int(p.nr_subgrids), C.c_int(p.grid_size), C.c_int(p.subgrid_size),
+                            C.c_int(flags), _ptr(p.metadata), _ptr(sg), _ptr(grid))
+        return sg
+
+    def subgrid_fft(self, subgrids: np.ndarray, direction=1) -> np.ndarray:
+        """Subgrid FFT (oracle only; SURVEY 8f-2, parity unpinned): a transformed copy."""
+        assert not self.is_reference, "the reference has no FFT"
+        out = np.array(subgrids, np.complex64, order="C", copy=True)
+        N = out.shape[-1]
+        assert out.shape[-2] == N
+        self._f("subgrid_fft")(C.c_long(out.size // (N * N)), C.c_int(N), C.c_int(direction), _ptr(out))
+        return out
 
     def degridder(self, p: "Problem") -> np.ndarray:
         out = np.full((p.total_timesteps, p.nr_channels, 4), np.nan, np.complex64)
