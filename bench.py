@@ -431,6 +431,32 @@ def run_ours(args) -> None:
                "pcie_h2d_gbs_measured": h2d_gbs, "h2d_floor_ms": h2d / (h2d_gbs * 1e9) * 1e3,
                "note": "copy-bound: the step cannot be faster than its host->device bytes over the measured link"}
 
+    # ---- the "next" rows around the two kernels: subgrid FFT, adder, splitter - byte movers,
+    # timed with the same protocol on a scratch copy; algorithmic bytes as in tools/next_rows_bench.py
+    next_rows = None
+    if world == 1:
+        G = prob["grid_size"]
+        work = sub_in.clone()
+        grid = torch.zeros((4, G, G), dtype=torch.complex64, device=dev)
+        sg_bytes = work.numel() * 8
+        grid_bytes = min(grid.numel() * 8, sg_bytes)
+        hbm = float(measured_peaks().get("hbm_gbs") or 0.0)
+
+        def nr(step, nbytes):
+            sec, _ = timed(step, args.steps, args.warmup)
+            gbs = nbytes * args.steps / sec * 1e-9
+            return {"ms": sec / args.steps * 1e3, "gb_per_s": gbs, "hbm_frac": gbs / hbm if hbm else None,
+                    "algorithmic_bytes": int(nbytes)}
+
+        next_rows = {
+            "subgrid_fft": nr(lambda: idg.subgrid_fft(S, N, work, 1), 2 * sg_bytes),
+            "adder": nr(lambda: idg.adder(S, G, N, prob["metadata"], work, grid), sg_bytes + grid_bytes),
+            "splitter": nr(lambda: idg.splitter(S, G, N, prob["metadata"], work, grid), sg_bytes + grid_bytes),
+            "note": "HBM-bound byte movers (hbm_frac against MEASURED_PEAKS.json hbm_gbs); the reference has none "
+                    "of them (parity unpinned, oracle/idg_next_oracle.c); together < 4 % of a gridder launch",
+        }
+        del work, grid
+
     # ---- CPU baseline + parity sample, rank 0 at N=1 only
     cpu_baseline, parity = None, None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -572,7 +598,7 @@ def run_ours(args) -> None:
                 "ms_per_step": sec_d32 / args.steps * 1e3,
                 "roofline": roof(sec_d32, args.steps, 128.329e6 / 1740, None)},
             "reference_gpu": ref_gpu,
-            "cpu_baseline": cpu_baseline, "parity": parity, "e2e": e2e,
+            "cpu_baseline": cpu_baseline, "parity": parity, "e2e": e2e, "next_rows": next_rows,
             "gpu_launches": int(launches_g), "degridder_gpu_launches": int(launches_d),
             "clocks": clocks, "device": idg.device_name(),
         }

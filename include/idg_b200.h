@@ -157,6 +157,15 @@ int idgb200_splitter(const idgb200_params *params, const idgb200_metadata *d_met
                      idgb200_cfloat *d_subgrids, const idgb200_cfloat *const *grid_parts,
                      int nr_parts, int rows_per_part, void *stream);
 
+/* Multi-GPU adder, second half: out[i] = sources[0][i] + ... + sources[nr_sources-1][i], summed in
+ * that order (bit-reproducible), count complex64 elements (even; every pointer 16-byte aligned).
+ * sources is a HOST array of device pointers that may be peer (NVLink) addresses: rank r calls it
+ * with every rank's local copy of grid part r and ends up owning the reduced part r - a
+ * reduce-scatter by direct peer loads (tools/adder_reduce_scatter.py compares it with
+ * ncclReduceScatter and with the adder's reductions into peer memory). nr_sources <= 16. */
+int idgb200_reduce_parts(int nr_sources, const idgb200_cfloat *const *sources, int64_t count,
+                         idgb200_cfloat *d_out, void *stream);
+
 /* Subgrid FFT: in-place 2-D DFT of each of the nr_subgrids * 4 planes of N x N pixels.
  *   direction = +1 (forward, after the gridder):  B[ky][kx] = sum A[y][x] exp(-2 pi i (ky y + kx x) / N)
  *   direction = -1 (backward, before the degridder): exp(+...), scaled by 1 / N^2

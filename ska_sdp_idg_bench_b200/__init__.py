@@ -12,7 +12,7 @@ built library raises, and calling it without a CUDA device raises IdgError.
 from .api import (FLAG_FFT_SHIFT, IdgError, SINCOS_ACCURATE, SINCOS_FAST, SINCOS_REDUCED, adder, bytes_gridder,
                   c_run_degridder, c_run_gridder, degridder, device_name, flops_gridder, gridder,
                   init_problem_device, launch_count, p_run_degridder, p_run_gridder,
-                  print_device_info, resolve_variant, sm_count, splitter, subgrid_fft)
+                  print_device_info, reduce_parts, resolve_variant, sm_count, splitter, subgrid_fft)
 from .layout import BASELINE_DTYPE, METADATA_DTYPE, NR_CORRELATIONS, IMAGE_SIZE, W_STEP
 from .shard import partition_subgrids, shard_metadata
 
@@ -20,6 +20,6 @@ __all__ = [
     "IdgError", "SINCOS_FAST", "SINCOS_REDUCED", "SINCOS_ACCURATE", "c_run_gridder",
     "c_run_degridder", "gridder", "degridder", "p_run_gridder", "p_run_degridder",
     "flops_gridder", "bytes_gridder", "print_device_info", "device_name", "sm_count",
-    "launch_count", "resolve_variant", "adder", "splitter", "subgrid_fft", "FLAG_FFT_SHIFT", "init_problem_device", "METADATA_DTYPE", "BASELINE_DTYPE",
+    "launch_count", "resolve_variant", "adder", "reduce_parts", "splitter", "subgrid_fft", "FLAG_FFT_SHIFT", "init_problem_device", "METADATA_DTYPE", "BASELINE_DTYPE",
     "NR_CORRELATIONS", "IMAGE_SIZE", "W_STEP", "partition_subgrids", "shard_metadata",
 ]

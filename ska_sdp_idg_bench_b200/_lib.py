@@ -37,6 +37,7 @@ SYMBOLS = {
     "idgb200_resolve_variant": (C.c_int, [C.POINTER(Params), C.c_int]),
     "idgb200_adder": (C.c_int, [C.POINTER(Params), _P, _P, C.POINTER(C.c_void_p), C.c_int, C.c_int, _P]),
     "idgb200_splitter": (C.c_int, [C.POINTER(Params), _P, _P, C.POINTER(C.c_void_p), C.c_int, C.c_int, _P]),
+    "idgb200_reduce_parts": (C.c_int, [C.c_int, C.POINTER(C.c_void_p), C.c_int64, _P, _P]),
     "idgb200_subgrid_fft": (C.c_int, [C.c_int64, C.c_int, C.c_int, _P, _P]),
     "idgb200_c_run_gridder": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int,
                                         C.c_int, C.c_int64, C.c_int] + [_P] * 7),

@@ -99,6 +99,14 @@ def splitter(nr_subgrids, grid_size, subgrid_size, metadata, subgrids, grid_part
                                 C.c_void_p(subgrids.data_ptr()), arr, n, rpp, _stream_ptr(stream)))
 
 
+def reduce_parts(sources, out, stream=None) -> None:
+    """out = sources[0] + sources[1] + ... (in that order).  ``sources``: complex64 CUDA tensors or
+    integer device addresses (peer memory allowed) of out.numel() elements each."""
+    arr = (C.c_void_p * len(sources))(*[int(q) if isinstance(q, int) else q.data_ptr() for q in sources])
+    _check(lib.idgb200_reduce_parts(len(sources), arr, int(out.numel()), C.c_void_p(out.data_ptr()),
+                                    _stream_ptr(stream)))
+
+
 def subgrid_fft(nr_subgrids, subgrid_size, subgrids, direction: int = 1, stream=None) -> None:
     """Subgrid FFT: in-place 2-D DFT of the nr_subgrids * 4 planes of ``subgrids``
     (complex64 CUDA tensor [S][4][N][N]); direction +1 forward (unscaled), -1 backward (1/N^2)."""

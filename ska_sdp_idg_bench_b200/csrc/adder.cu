@@ -167,7 +167,53 @@ splitter_kernel(const int grid_size, const int subgrid_size, const idgb200_metad
   }
 }
 
+// out[i] = sources[0][i] + sources[1][i] + ... in that order (deterministic, unlike the atomics above).
+// The sources may be peer addresses: rank r runs this over its own slice of every rank's local grid -
+// a one-shot "pull" reduce-scatter over NVLink with 16-byte loads, no staging and no second copy.
+struct ReduceSources {
+  const float4 *src[ADDER_MAX_PARTS];
+};
+__global__ void __launch_bounds__(256)
+reduce_parts_kernel(const __grid_constant__ ReduceSources srcs, const int nr_sources, const long long count4,
+                    float4 *__restrict__ out) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count4; i += stride) {
+    float4 acc;
+    asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(acc.x), "=f"(acc.y), "=f"(acc.z), "=f"(acc.w) : "l"(srcs.src[0] + i) : "memory");
+    for (int k = 1; k < nr_sources; k++) {
+      float4 v;
+      asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];"
+                   : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(srcs.src[k] + i) : "memory");
+      acc.x += v.x;
+      acc.y += v.y;
+      acc.z += v.z;
+      acc.w += v.w;
+    }
+    out[i] = acc;
+  }
+}
+
 }  // namespace
+
+cudaError_t launch_reduce_parts(int nr_sources, const float2 *const *sources, long long count, float2 *out,
+                                int sm_count, cudaStream_t stream) {
+  if (count == 0) return cudaSuccess;
+  if (nr_sources < 1 || nr_sources > ADDER_MAX_PARTS || count < 0 || (count & 1)) return cudaErrorInvalidValue;
+  ReduceSources s{};
+  for (int i = 0; i < nr_sources; i++) {
+    if ((uintptr_t)sources[i] & 15) return cudaErrorInvalidValue;
+    s.src[i] = reinterpret_cast<const float4 *>(sources[i]);
+  }
+  if ((uintptr_t)out & 15) return cudaErrorInvalidValue;
+  const long long count4 = count / 2;
+  long long ctas = (count4 + 255) / 256;
+  const long long cap = (long long)(sm_count > 0 ? sm_count : 148) * 8;   // a few waves, grid-stride beyond
+  if (ctas > cap) ctas = cap;
+  reduce_parts_kernel<<<dim3((unsigned)ctas), dim3(256), 0, stream>>>(s, nr_sources, count4,
+                                                                       reinterpret_cast<float4 *>(out));
+  return cudaGetLastError();
+}
 
 cudaError_t launch_splitter(int nr_subgrids, int subgrid_offset, int grid_size, int subgrid_size, int flags,
                             const idgb200_metadata *metadata, float2 *subgrids, const float2 *const *parts,

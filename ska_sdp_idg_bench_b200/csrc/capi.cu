@@ -734,6 +734,24 @@ int idgb200_splitter(const idgb200_params *p, const idgb200_metadata *d_meta, id
   return IDGB200_OK;
 }
 
+int idgb200_reduce_parts(int nr_sources, const idgb200_cfloat *const *sources, int64_t count,
+                         idgb200_cfloat *d_out, void *stream) {
+  if (nr_sources < 1 || nr_sources > 16 || !sources || count < 0 || (count & 1)) return IDGB200_EINVAL;
+  if (count > 0 && (!d_out || ((uintptr_t)d_out & 15))) return IDGB200_EINVAL;
+  for (int i = 0; i < nr_sources; i++)
+    if (!sources[i] || ((uintptr_t)sources[i] & 15)) return IDGB200_EINVAL;
+  int rc = have_device();
+  if (rc) return rc;
+  if (count == 0) return IDGB200_OK;
+  int sms = 0;
+  idgb200_sm_count(&sms);
+  cudaError_t e = launch_reduce_parts(nr_sources, reinterpret_cast<const float2 *const *>(sources), count,
+                                      reinterpret_cast<float2 *>(d_out), sms, static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return (int)e;
+  g_launches++;
+  return IDGB200_OK;
+}
+
 int idgb200_subgrid_fft(int64_t nr_subgrids, int subgrid_size, int direction, idgb200_cfloat *d_sg,
                         void *stream) {
   if (nr_subgrids < 0 || subgrid_size < 1 || (direction != 1 && direction != -1) ||

@@ -20,6 +20,11 @@ cudaError_t launch_splitter(int nr_subgrids, int subgrid_offset, int grid_size, 
                             const idgb200_metadata *metadata, float2 *subgrids, const float2 *const *parts,
                             int nr_parts, int rows_per_part, cudaStream_t stream);
 
+// out[i] = sum over the sources in order (adder.cu); count complex64 elements (even), pointers 16-byte
+// aligned, sources may be peer addresses
+cudaError_t launch_reduce_parts(int nr_sources, const float2 *const *sources, long long count, float2 *out,
+                                int sm_count, cudaStream_t stream);
+
 // subgrid FFT (subgrid_fft.cu): in-place 2-D DFT of nr_planes N x N planes; direction >= 0 forward
 // (exp(-i)), < 0 backward (exp(+i), scaled by 1/N^2)
 cudaError_t launch_subgrid_fft(long long nr_planes, int subgrid_size, int direction, float2 *planes,

@@ -91,9 +91,15 @@ __device__ __forceinline__ void pack_phasor(const float2 ph, unsigned &hi, unsig
   const __half2 hh = __floats2half2_rn(ph.x, ph.y);
   hi = *reinterpret_cast<const unsigned *>(&hh);
   if (SPLIT) {
-    const float2 hf = __half22float2(hh);
-    const float2 rs = __fadd2_rn(ph, make_float2(-hf.x, -hf.y));   // one packed FADD2 (exact: Sterbenz)
-    const __half2 ll = __floats2half2_rn(rs.x, rs.y);
+    // residual = ph - float(hh), exact (Sterbenz).  sm_100a's mixed-precision FMA reads the fp16 halves
+    // of the packed word directly (SASS: FHFMA Rd, Rh.H0|.H1, -1.0h, Rph): one instruction per
+    // component instead of two conversions and a packed FADD2 (= 4 dispatch cycles)
+    const unsigned short h0 = (unsigned short)(hi & 0xffffu), h1 = (unsigned short)(hi >> 16);
+    const unsigned short minus_one = 0xbc00u;
+    float r0, r1;
+    asm("fma.rn.f32.f16 %0, %1, %2, %3;" : "=f"(r0) : "h"(h0), "h"(minus_one), "f"(ph.x));
+    asm("fma.rn.f32.f16 %0, %1, %2, %3;" : "=f"(r1) : "h"(h1), "h"(minus_one), "f"(ph.y));
+    const __half2 ll = __floats2half2_rn(r0, r1);
     lo = *reinterpret_cast<const unsigned *>(&ll);
   }
 }

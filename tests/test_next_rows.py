@@ -308,3 +308,28 @@ def test_imaging_round_trip_pipeline():
     assert err < 1e-4, err
     # and the round trip through the grid reproduced the gridder's subgrids (disjoint tiles)
     assert np.abs(back - sg).max() <= 1e-5 * np.abs(sg).max()
+
+
+@pytest.mark.gpu
+def test_reduce_parts_is_the_ordered_sum():
+    """idgb200_reduce_parts: out = sources[0] + sources[1] + ... in that order, bit for bit (the
+    second half of the multi-GPU adder; here all sources live on one GPU)."""
+    import torch
+
+    import ska_sdp_idg_bench_b200 as idg
+    dev = torch.device("cuda", 0)
+    g = torch.Generator(dev).manual_seed(3)
+    n = 4 * 37 * 50                                     # even, not a multiple of the CTA size
+    src = [torch.view_as_complex(torch.randn((n, 2), device=dev, generator=g)) for _ in range(5)]
+    out = torch.full((n,), float("nan"), dtype=torch.complex64, device=dev)
+    idg.reduce_parts(src, out)
+    ref = src[0].clone()
+    for t in src[1:]:
+        ref = ref + t
+    assert torch.equal(out, ref)
+    idg.reduce_parts(src[:1], out)
+    assert torch.equal(out, src[0])
+    with pytest.raises(idg.IdgError):
+        idg.reduce_parts(src, out[:n - 1])              # odd element count
+    with pytest.raises(idg.IdgError):
+        idg.reduce_parts([t for t in src] * 4, out)     # more than 16 sources

@@ -5,9 +5,13 @@ grid rows [r * rows, (r + 1) * rows).
   baseline  each rank adds into a full local grid, then ncclReduceScatter (torch.distributed)
   fused     the owners' slices live in symmetric (peer-mapped) memory; every rank's adder kernel
             reduces its subgrids straight into the owners' slices with system-scope
-            red.global.add.v2.f32 over NVLink / NVSwitch: no partial grid, no second pass
+            red.global.add.v4.f32 over NVLink / NVSwitch: no partial grid, no second pass
+  pull      each rank adds into its own local grid, which lives in symmetric memory; after a barrier
+            every rank sums ITS slice out of all ranks' local grids with 16-byte peer loads over
+            NVLink (idgb200_reduce_parts): a one-shot reduce-scatter, rank-ordered sums
+            (bit-reproducible), no staging buffers, no NCCL
 
-Both give the same slices (checked here to fp32 summation order).  Times are CUDA events on the
+All give the same slices (checked here to fp32 summation order).  Times are CUDA events on the
 launching stream with a barrier on both sides, max over ranks.
 
   python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tools/adder_reduce_scatter.py
@@ -91,22 +95,46 @@ def main():
         hdl.barrier(channel=1)                       # every rank's reductions have landed
 
     ms_fused = timed(fused)
+
+    # ---- pull: local grid in symmetric memory, every rank reduces its slice out of all local grids
+    part_elems = 4 * rpp * G
+    sym_grid_f = symm_mem.empty((world, 4, rpp, G, 2), dtype=torch.float32, device=dev)
+    hdl2 = symm_mem.rendezvous(sym_grid_f, dist.group.WORLD)
+    sym_grid = torch.view_as_complex(sym_grid_f)
+    sym_parts = [sym_grid[r] for r in range(world)]
+    my_part_of = [int(p) + rank * part_elems * 8 for p in hdl2.buffer_ptrs]   # rank q's copy of MY part
+    out_pull = torch.zeros((4, rpp, G), dtype=torch.complex64, device=dev)
+
+    def pull():
+        sym_grid_f.zero_()
+        idg.adder(S, G, N, meta, sg, sym_parts, rows_per_part=rpp)
+        hdl2.barrier(channel=0)                      # every rank's local grid is complete
+        idg.reduce_parts(my_part_of, out_pull)
+        hdl2.barrier(channel=1)                      # nobody zeroes a grid that is still being read
+
+    ms_pull = timed(pull)
     fused()
     baseline()
+    pull()
     torch.cuda.synchronize()
     a, b = torch.view_as_complex(slice_f), out_nccl
     err = float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
-    errs = torch.tensor([err], dtype=torch.float64, device=dev)
+    err_pull = float((out_pull - b).abs().max() / b.abs().max().clamp_min(1e-30))
+    errs = torch.tensor([err, err_pull], dtype=torch.float64, device=dev)
     dist.all_reduce(errs, op=dist.ReduceOp.MAX)
     if rank == 0:
         grid_bytes = 4 * G * G * 8
         print(json.dumps({
             "what": "grid adder + reduce-scatter by grid rows (SURVEY 8f-1)", "n_gpus": world, "grid_size": G,
             "subgrid_size": N, "subgrids_per_gpu": S, "grid_mbytes": grid_bytes * 1e-6,
-            "nccl_ms": ms_base, "fused_peer_atomics_ms": ms_fused, "speedup": ms_base / ms_fused,
-            "max_rel_difference_fused_vs_nccl": float(errs),
-            "note": "nccl = local memset + adder into a full local grid + ncclReduceScatter; fused = memset of the "
-                    "own slice + barrier + adder with system-scope red.v2.f32 into the peers' slices + barrier"}))
+            "nccl_ms": ms_base, "fused_peer_atomics_ms": ms_fused, "pull_peer_loads_ms": ms_pull,
+            "speedup_push_vs_nccl": ms_base / ms_fused, "speedup_pull_vs_nccl": ms_base / ms_pull,
+            "max_rel_difference_fused_vs_nccl": float(errs[0]), "max_rel_difference_pull_vs_nccl": float(errs[1]),
+            "overlap_subgrid_pixels_per_grid_cell": world * S * N * N / (G * G),
+            "note": "nccl = memset + adder into a full local grid + ncclReduceScatter; fused (push) = memset of the "
+                    "own slice + barrier + adder with system-scope red.v4.f32 into the owners' slices + barrier; "
+                    "pull = memset + adder into a local grid in symmetric memory + barrier + idgb200_reduce_parts "
+                    "(16-byte peer loads of the own slice from every rank) + barrier"}))
     dist.barrier()
     dist.destroy_process_group()
 
