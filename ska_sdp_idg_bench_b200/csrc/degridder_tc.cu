@@ -94,7 +94,7 @@ __device__ __forceinline__ void dtc_produce(unsigned char *A, const float4 *geo,
 
 // The same stage when the thread's four channels are equally spaced (common.cuh: linear_channels):
 // per pixel one sincos for the first channel (the reference's angle, bit for bit), one for the
-// rotation e^{i idx dw}, and 3 complex multiplications.
+// rotation e^{i idx dw}, one complex multiplication and two steps of the three-term recurrence.
 template <bool SPLIT>
 __device__ __forceinline__ void dtc_produce_linear(unsigned char *A, const float4 *geo, const float u, const float v,
                                                    const float w, const float wn0, const float dw, const int lane) {
@@ -105,15 +105,21 @@ __device__ __forceinline__ void dtc_produce_linear(unsigned char *A, const float
     for (int i = 0; i < 4; i++) {
       const float4 g = geo[kc * 4 + i];
       const float idx = __fadd_rn(__fmaf_rn(u, g.x, __fmul_rn(v, g.y)), __fmul_rn(w, g.z));
-      float2 ph = phasor<IDGB200_SINCOS_FAST>(__fmaf_rn(idx, wn0, -g.w));
+      const float2 p0 = phasor<IDGB200_SINCOS_FAST>(__fmaf_rn(idx, wn0, -g.w));
       const float2 d = phasor<IDGB200_SINCOS_FAST>(__fmul_rn(idx, dw));
       const float2 dxx = make_float2(d.x, d.x), dny = make_float2(-d.y, d.y);
-#pragma unroll
-      for (int j = 0; j < 4; j++) {
-        pack_phasor<SPLIT>(ph, pk[j][i], pl[j][i]);
-        // (x, y) * d = (x, y) * (dx, dx) + (y, x) * (-dy, dy): FMUL2 + FFMA2 (gridder_tc.cu)
-        if (j < 3) ph = ffma2(make_float2(ph.y, ph.x), dny, __fmul2_rn(ph, dxx));
-      }
+      const float c2 = __fadd_rn(d.x, d.x);
+      const float2 cc = make_float2(c2, c2);
+      // channel 1 by rotation: (x, y) * d = (x, y) * (dx, dx) + (y, x) * (-dy, dy): FMUL2 + FFMA2;
+      // channels 2, 3 by the three-term recurrence ph[c+1] = 2 cos(delta) ph[c] - ph[c-1]: one FFMA2
+      // each (gridder_tc.cu: tc_produce_linear has the error argument)
+      const float2 p1 = ffma2(make_float2(p0.y, p0.x), dny, __fmul2_rn(p0, dxx));
+      const float2 p2 = ffma2(p1, cc, make_float2(-p0.x, -p0.y));
+      const float2 p3 = ffma2(p2, cc, make_float2(-p1.x, -p1.y));
+      pack_phasor<SPLIT>(p0, pk[0][i], pl[0][i]);
+      pack_phasor<SPLIT>(p1, pk[1][i], pl[1][i]);
+      pack_phasor<SPLIT>(p2, pk[2][i], pl[2][i]);
+      pack_phasor<SPLIT>(p3, pk[3][i], pl[3][i]);
     }
 #pragma unroll
     for (int j = 0; j < 4; j++) {

@@ -89,22 +89,34 @@ __device__ __forceinline__ void tc_produce(unsigned char *A, const float *wn8, c
 
 // The same stage for a block of equally spaced channels (common.cuh: linear_channels): one sincos
 // for the first channel (the same angle as above, bit for bit), the per-channel rotation
-// e^{-i idx dw} (rot), then 7 complex multiplications (FMUL2 + FFMA2 each) instead of 14 MUFU.
+// d = e^{-i idx dw} (rot) for the second, and from there the three-term recurrence of equally spaced
+// angles, ph[c+1] = 2 cos(delta) ph[c] - ph[c-1]: ONE packed FFMA2 per phasor (2 dispatch cycles)
+// where the complex multiplication ph[c] * d costs FMUL2 + FFMA2 (4).  A rounding error e made at one
+// step comes back as e sin(k delta) / sin(delta) <= k e after k steps, so over the 6 steps of a block
+// the phasor stays within ~2e-6 of the rotated one - 1 % of the fp16 rounding of the operand it
+// becomes (tools/hrot.cu has the dispatch costs, tests/test_gpu_parity.py the parity cases).
 template <bool SPLIT>
 __device__ __forceinline__ void tc_produce_linear(unsigned char *A, const float wn0, const float2 (&rot)[4],
                                                   const float (&idx)[4], const float (&off)[4], const int lane) {
 #pragma unroll
   for (int j = 0; j < 4; j++) {
-    float2 ph = phasor<IDGB200_SINCOS_FAST>(__fmaf_rn(-idx[j], wn0, off[j]));   // :69
+    float2 prev = phasor<IDGB200_SINCOS_FAST>(__fmaf_rn(-idx[j], wn0, off[j]));   // :69
     const float2 d = rot[j];
     const float2 dxx = make_float2(d.x, d.x), dny = make_float2(-d.y, d.y);
+    const float c2 = __fadd_rn(d.x, d.x);
+    const float2 cc = make_float2(c2, c2);
     unsigned pk[8], pl[8];
+    pack_phasor<SPLIT>(prev, pk[0], pl[0]);
+    // (x, y) * d = (x, y) * (dx, dx) + (y, x) * (-dy, dy): FMUL2 + FFMA2 with free operand modes
+    // (broadcast scalar, LO_HI swizzle)
+    float2 cur = ffma2(make_float2(prev.y, prev.x), dny, __fmul2_rn(prev, dxx));
+    pack_phasor<SPLIT>(cur, pk[1], pl[1]);
 #pragma unroll
-    for (int i = 0; i < 8; i++) {
-      pack_phasor<SPLIT>(ph, pk[i], pl[i]);
-      // (x, y) * d = (x, y) * (dx, dx) + (y, x) * (-dy, dy): FMUL2 + FFMA2 with free operand modes
-      // (broadcast scalar, LO_HI swizzle) - 2 issue slots instead of 4 in an issue-bound loop
-      if (i < 7) ph = ffma2(make_float2(ph.y, ph.x), dny, __fmul2_rn(ph, dxx));
+    for (int i = 2; i < 8; i++) {
+      const float2 nxt = ffma2(cur, cc, make_float2(-prev.x, -prev.y));
+      pack_phasor<SPLIT>(nxt, pk[i], pl[i]);
+      prev = cur;
+      cur = nxt;
     }
     *reinterpret_cast<uint4 *>(A + (lane + 32 * j) * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
     *reinterpret_cast<uint4 *>(A + A_CHUNK_BYTES + (lane + 32 * j) * 16) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
