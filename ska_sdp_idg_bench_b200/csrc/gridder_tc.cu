@@ -252,6 +252,53 @@ gridder_tc_kernel(const KernelArgs a, const int slabs, const int tiles_per_cta, 
       float un = 0.f, vn = 0.f, wnx = 0.f;   // uvw of the next timestep, fetched one timestep ahead
       if (nt > 0) { un = __ldg(&g_uvw[0]); vn = __ldg(&g_uvw[1]); wnx = __ldg(&g_uvw[2]); }
       unsigned k = 0, sk = 0;   // channel blocks (= B slots) and stages done; unsigned: masks and shifts
+      if (WIDE && !SPLIT && same_dw && !(ncb & 1)) {
+        // ---- the regular case (an even number of linear channel blocks, one spacing): every stage is
+        // two blocks, nothing about it depends on data.  The generic loop below spends as many issue
+        // slots per stage on block flags, slot / phase arithmetic and rematerialised shared-memory
+        // addresses (~170 instructions, ncu source page) as on 20 of the 64 phasors it makes; here the
+        // per-stage state is three counters and the addresses are opaque registers.
+        unsigned wn_u = smem_u32(s_wn);
+        const float dw0 = s_dw[0];
+        asm volatile("" : "+r"(wn_u));
+        unsigned slot2 = 0, ring_phase = 0;     // B slot pair of the stage (k % 16), lap parity of the ring
+        const unsigned last_k = (unsigned)nstages - 2u;
+        for (int t = 0; t < nt; t++) {
+          const float u = un, v = vn, w = wnx;
+          if (t + 1 < nt) { un = __ldg(&g_uvw[3 * t + 3]); vn = __ldg(&g_uvw[3 * t + 4]); wnx = __ldg(&g_uvw[3 * t + 5]); }
+          float idx[4];
+          float2 rot[4];
+#pragma unroll
+          for (int j = 0; j < 4; j++) {  // gridder_reference.cpp:61 as contracted by the CPU binary
+            idx[j] = __fmaf_rn(w, n[j], __fmaf_rn(u, l[j], __fmul_rn(v, m[j])));
+            rot[j] = phasor<IDGB200_SINCOS_FAST>(__fmul_rn(-idx[j], dw0));
+          }
+          for (int cb0 = 0; cb0 < ncb; cb0 += 2, sk++, k += 2) {
+            if (sk >= 1) mbar_wait_u(my_empty_u, (sk - 1) & 1);
+            float wn0a, wn0b;
+            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(wn0a) : "r"(wn_u + (unsigned)cb0 * (T2_CB * 4)));
+            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(wn0b) : "r"(wn_u + (unsigned)cb0 * (T2_CB * 4) + T2_CB * 4));
+            tc_produce_linear<false>(A_tile, wn0a, rot, idx, off, lane);
+            tc_produce_linear<false>(A_tile + T2_A_STAGE, wn0b, rot, idx, off, lane);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_wait_u(bfull_u + slot2 * 8, ring_phase);
+            mbar_wait_u(bfull_u + slot2 * 8 + 8, ring_phase);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (elect_one()) {
+              const unsigned long long db = db0 + (unsigned long long)(slot2 * (T2_B_SLOT >> 4));
+              umma_f16(tmem_d, da0, db, idesc, k > 0 ? 1u : 0u);
+              umma_f16(tmem_d, da0 + (unsigned long long)(T2_A_STAGE >> 4), db + (unsigned long long)(T2_B_SLOT >> 4), idesc, 1u);
+              umma_commit_u(my_empty_u);
+              if ((slot2 & 7u) == 6u) umma_commit_u(bempty_u + (slot2 >> 3) * 8);   // half ring consumed
+              if (k == last_k) umma_commit_u(done_u);
+            }
+            __syncwarp();
+            slot2 += 2;
+            if (slot2 == (unsigned)T2_NB) { slot2 = 0; ring_phase ^= 1u; }
+          }
+        }
+      } else
       for (int t = 0; t < nt; t++) {
         const float u = un, v = vn, w = wnx;
         if (t + 1 < nt) { un = __ldg(&g_uvw[3 * t + 3]); vn = __ldg(&g_uvw[3 * t + 4]); wnx = __ldg(&g_uvw[3 * t + 5]); }
