@@ -224,7 +224,8 @@ int resolve_degridder_variant(int subgrid_size, int nr_channels, int sincos_mode
   // the tensor kernel pads the channels to quads of 4 and the pixels to stages of 8
   const int npix = subgrid_size * subgrid_size, ncg = (nr_channels + 3) / 4;
   const bool tc = sincos_mode == IDGB200_SINCOS_FAST && 4 * nr_channels >= 3 * ncg * 4 && npix >= 256;
-  return tc ? 22 : 4;
+  // channel counts that fill groups of 8: the two-tiles-per-warp kernel (degridder_tc8.cu)
+  return tc ? ((nr_channels & 7) ? 22 : 24) : 4;
 }
 
 cudaError_t launch_degridder(const KernelArgs &a, int sincos_mode, int variant, cudaStream_t stream) {
@@ -244,6 +245,10 @@ cudaError_t launch_degridder(const KernelArgs &a, int sincos_mode, int variant, 
       return sincos_mode == IDGB200_SINCOS_FAST ? launch_degridder_tc(a, 10, true, stream) : cudaErrorInvalidValue;
     case 23:
       return sincos_mode == IDGB200_SINCOS_FAST ? launch_degridder_tc(a, 10, false, stream) : cudaErrorInvalidValue;
+    case 24:   // two M-tiles per warp, groups of 8 channels, fp16 hi + lo phasors (nr_channels % 8 == 0); 25: no recurrence
+    case 25:
+      return sincos_mode == IDGB200_SINCOS_FAST && !(a.nr_channels & 7) ? launch_degridder_tc8(a, variant == 24, stream)
+                                                                        : cudaErrorInvalidValue;
     default: return cudaErrorInvalidValue;
   }
 }

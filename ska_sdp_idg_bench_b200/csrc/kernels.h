@@ -37,6 +37,8 @@ int resolve_degridder_variant(int subgrid_size, int nr_channels, int sincos_mode
 // tcgen05 / TMEM gridder (gridder_tc.cu); FAST sincos only
 cudaError_t launch_gridder_tc(const KernelArgs &a, int poly, bool recur, cudaStream_t stream);
 cudaError_t launch_degridder_tc(const KernelArgs &a, int poly, bool recur, cudaStream_t stream);
+// two M-tiles per warp, groups of 8 channels (degridder_tc8.cu); nr_channels % 8 == 0
+cudaError_t launch_degridder_tc8(const KernelArgs &a, bool recur, cudaStream_t stream);
 // phasor operand written to TMEM from registers (gridder_tc3.cu)
 cudaError_t launch_gridder_tc3(const KernelArgs &a, int mode, cudaStream_t stream);
 
