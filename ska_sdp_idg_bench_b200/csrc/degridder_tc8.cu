@@ -71,31 +71,46 @@ __device__ __forceinline__ void store_chunk(unsigned char *A, int kc, int lane, 
 // ~1e-4 rad the FAST sincos itself is off at these phases)
 __device__ __forceinline__ void etc_produce_linear(unsigned char *A, const float4 *geo, const float u, const float v,
                                                    const float w, const float wn0, const float dw, const int lane) {
+  // phase A, all 8 pixels of the stage: geometry, phase index, the two sincos, the first rotation - 8
+  // independent chains cover the MUFU and LDS latencies with only ~4 warps per sub-partition resident
+  float2 prev[8], cur[8], cc[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    const float4 g = geo[i];   // broadcast: all lanes read the same 16 bytes
+    // degridder_reference.cpp:106 as the CPU binary evaluates it (w term unfused)
+    const float idx = __fadd_rn(__fmaf_rn(u, g.x, __fmul_rn(v, g.y)), __fmul_rn(w, g.z));
+    prev[i] = phasor<IDGB200_SINCOS_FAST>(__fmaf_rn(idx, wn0, -g.w));   // :112, (cos, sin)
+    const float2 d = phasor<IDGB200_SINCOS_FAST>(__fmul_rn(idx, dw));
+    const float2 dxx = make_float2(d.x, d.x), dny = make_float2(-d.y, d.y);
+    const float c2 = __fadd_rn(d.x, d.x);
+    cc[i] = make_float2(c2, c2);
+    cur[i] = ffma2(make_float2(prev[i].y, prev[i].x), dny, __fmul2_rn(prev[i], dxx));
+  }
+  // phase B, channel-major over each chunk of 4 pixels: every recurrence step is 4 independent FFMA2 and
+  // the 4 packed words of a row (one 16-byte store) are produced back to back
 #pragma unroll
   for (int kc = 0; kc < 2; kc++) {
-    unsigned pk[8][4], pl[8][4];   // [channel][pixel]
 #pragma unroll
-    for (int i = 0; i < 4; i++) {
-      const float4 g = geo[kc * 4 + i];   // broadcast: all lanes read the same 16 bytes
-      // degridder_reference.cpp:106 as the CPU binary evaluates it (w term unfused)
-      const float idx = __fadd_rn(__fmaf_rn(u, g.x, __fmul_rn(v, g.y)), __fmul_rn(w, g.z));
-      float2 prev = phasor<IDGB200_SINCOS_FAST>(__fmaf_rn(idx, wn0, -g.w));   // :112, (cos, sin)
-      const float2 d = phasor<IDGB200_SINCOS_FAST>(__fmul_rn(idx, dw));
-      const float2 dxx = make_float2(d.x, d.x), dny = make_float2(-d.y, d.y);
-      const float c2 = __fadd_rn(d.x, d.x);
-      const float2 cc = make_float2(c2, c2);
-      pack_phasor<true>(prev, pk[0][i], pl[0][i]);
-      float2 cur = ffma2(make_float2(prev.y, prev.x), dny, __fmul2_rn(prev, dxx));
-      pack_phasor<true>(cur, pk[1][i], pl[1][i]);
+    for (int c = 0; c < 8; c++) {
+      unsigned hi[4], lo[4];
 #pragma unroll
-      for (int c = 2; c < 8; c++) {
-        const float2 nxt = ffma2(cur, cc, make_float2(-prev.x, -prev.y));
-        pack_phasor<true>(nxt, pk[c][i], pl[c][i]);
-        prev = cur;
-        cur = nxt;
+      for (int i = 0; i < 4; i++) {
+        const int q = kc * 4 + i;
+        if (c == 0) {
+          pack_phasor<true>(prev[q], hi[i], lo[i]);
+        } else if (c == 1) {
+          pack_phasor<true>(cur[q], hi[i], lo[i]);
+        } else {
+          const float2 nxt = ffma2(cur[q], cc[q], make_float2(-prev[q].x, -prev[q].y));
+          pack_phasor<true>(nxt, hi[i], lo[i]);
+          prev[q] = cur[q];
+          cur[q] = nxt;
+        }
       }
+      unsigned char *row = A + (c >> 2) * (2 * E_A_BUF) + kc * A_CHUNK_BYTES + (lane + 32 * (c & 3)) * 16;
+      *reinterpret_cast<uint4 *>(row) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+      *reinterpret_cast<uint4 *>(row + E_A_BUF) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
     }
-    store_chunk(A, kc, lane, pk, pl);
   }
 }
 
