@@ -45,12 +45,15 @@ SM_XU_LANES = 16      # MUFU lanes per SM
 # what the formulation needs per item: gridder 24 = F2FP 1 + recurrence FFMA2 2 x 6/8 +
 # (first rotation 4 + first-channel sincos 4) / 8 + STS.128 1/4 + per-timestep (phase index 12 + rotation
 # sincos 16) / 64 = 4.19; degridder 22 per pixel and channel quad = phase index 4 + two sincos 8 + 2 cos 1 +
-# rotation 4 + 2 recurrence steps 4 + 4 x (F2FP + 2 FHFMA + F2FP) 16 + STS 2 + LDS 1 = 40 / 4 = 10.
+# rotation 4 + 2 recurrence steps 4 + 4 x (F2FP + 2 FHFMA + F2FP) 16 + STS 2 + LDS 1 = 40 / 4 = 10;
+# degridder 24 per pixel and group of 8 channels = LDS 1 + phase index 4 + two sincos 8 + 2 cos 1 + rotation 4
+# + 6 recurrence steps 12 + 8 x 4 = 32 + STS 4 = 66 / 8 = 8.25.
 TC_GRIDDER = {11: (2.0, 10.1, None), 12: (1.5, 12.6, None), 13: (1.375, 12.9, None), 14: (1.25, 13.3, None),
               15: (1.0, 14.2, None), 21: (0.375, 10.0, None), 22: (0.375, 15.2, None), 23: (2.0, 17.1, None),
-              24: (0.375, 6.85, 4.19)}
+              24: (0.382, 6.91, 4.19)}
 TC_DEGRIDDER = {11: (2.0, 11.5, None), 12: (1.5, 13.5, None), 13: (1.25, 13.2, None), 14: (1.0, 15.5, None),
-                21: (1.0, 10.5, None), 22: (1.0, 14.54, 10.0), 23: (2.0, 18.5, None)}
+                21: (1.0, 10.5, None), 22: (1.006, 14.63, 10.0), 23: (2.0, 18.5, None),
+                24: (0.505, 11.95, 8.25)}
 
 
 # ----------------------------------------------------------------- shared helpers
@@ -583,22 +586,26 @@ def run_ours(args) -> None:
             "config": dict(workload_config(shape, world), sincos=args.sincos,
                            gridder_variant=g_variant, degridder_variant=d_variant,
                            gridder_kernel=("tcgen05: fp16 phasor tile x fp16 hi+lo visibilities, f32 accumulate in "
-                                           "TMEM" + ("; phasors of equally spaced channels by rotation from the "
-                                                     "first channel of each 8-channel block (as the reference's "
-                                                     "gridder_v8)" if g_variant in (21, 24) else "")
+                                           "TMEM" + ("; phasors of equally spaced channels from the first channel of each "
+                                                     "8-channel block by one rotation and the three-term recurrence (the "
+                                                     "reference's gridder_v8 rotates every channel)"
+                                                     if g_variant in (21, 24) else "")
                                            if tc_g is not None else "FP32 FFMA2 + MUFU"),
                            degridder_kernel=(("tcgen05: fp16 hi+lo phasor tile x fp16 hi+lo pixels, f32 accumulate in "
                                               "TMEM; phasors of equally spaced channel quads by rotation"
-                                              if d_variant == 22 else "tcgen05, opt-in variant")
+                                              if d_variant == 22 else
+                                              "tcgen05, two M-tiles per warp: fp16 hi+lo phasor tile x fp16 hi+lo pixels, f32 "
+                                              "accumulate in TMEM; phasors of equally spaced groups of 8 channels by the "
+                                              "three-term recurrence" if d_variant == 24 else "tcgen05, opt-in variant")
                                              if tc_d is not None else "FP32 FFMA2 + MUFU")),
             "tflops": world * flops * args.steps / sec_g * 1e-12,
-            # ncu --set full, 3675-subgrid launches: 341.6 MB (tcgen05 gridder), FP32 kernels from the
+            # ncu --set full, 3675-subgrid launches: 343.1 MB (tcgen05 gridder), 314.7 MB (tcgen05 degridder), FP32 kernels from the
             # 1740-subgrid captures (profiles/)
-            "roofline": roof(sec_g, args.steps, 341.6e6 / 3675 if tc_g is not None else 145.165e6 / 1740, tc_g),
+            "roofline": roof(sec_g, args.steps, 343.1e6 / 3675 if tc_g is not None else 145.165e6 / 1740, tc_g),
             "degridder": {"value": total_mvis * args.steps / sec_d, "unit": "MVis/s",
                           "ms_per_step": sec_d / args.steps * 1e3,
                           "tflops": world * flops * args.steps / sec_d * 1e-12,
-                          "roofline": roof(sec_d, args.steps, 315.8e6 / 3675 if tc_d is not None
+                          "roofline": roof(sec_d, args.steps, 314.7e6 / 3675 if tc_d is not None
                                            else 128.329e6 / 1740, tc_d)},
             "gridder_fp32": None if sec_g32 is None else {
                 "value": total_mvis * args.steps / sec_g32, "unit": "MVis/s", "variant": 10,
