@@ -223,6 +223,48 @@ def test_shapes_vs_oracle(shape):
     for variant in (11, 12, 21, 22):   # random pixels: no cancellation, the fp16 phasors stay inside FAST
         got = run_degridder(p, idg.SINCOS_FAST, variant)
         assert_close(got[rows], ref_d[rows], 2, idg.SINCOS_FAST, f"degridder tcgen05 {shape} v{variant}")
+    for variant in (24, 25):           # two M-tiles per warp: groups of 8 channels only
+        if p.nr_channels % 8 == 0:
+            got = run_degridder(p, idg.SINCOS_FAST, variant)
+            assert_close(got[rows], ref_d[rows], 2, idg.SINCOS_FAST, f"degridder tc8 {shape} v{variant}")
+        else:
+            with pytest.raises(idg.IdgError):
+                run_degridder(p, idg.SINCOS_FAST, variant)
+
+
+@pytest.mark.parametrize("shape", [
+    dict(subgrid_size=32, nr_channels=16, max_timesteps=128, nr_subgrids=3),   # the bench shape: 2 full rounds
+    dict(subgrid_size=32, nr_channels=64, max_timesteps=60, nr_subgrids=2),    # 4 rounds, the last one short
+    dict(subgrid_size=24, nr_channels=8, max_timesteps=37, nr_subgrids=3),     # one partial tile pair
+    dict(subgrid_size=32, nr_channels=24, max_timesteps=50, nr_subgrids=2),    # odd number of 8-channel blocks
+    dict(subgrid_size=64, nr_channels=32, max_timesteps=33, nr_subgrids=2),
+])
+def test_equally_spaced_channels_take_the_recurrence_paths(shape):
+    """Equally spaced wavenumbers (what the reference's init.cpp generates): the default FAST kernels
+    take the regular-case stage loop with the three-term recurrence (gridder_tc.cu; even block counts)
+    and the two-tiles-per-warp degridder (degridder_tc8.cu) - rounds, idle warps in a short last round
+    and partial tiles included - and must agree with the oracle and with the per-channel variants."""
+    o = oracle()
+    p = random_problem(77, **shape)
+    C = p.nr_channels
+    p.wavenumbers[:] = (2.9 + 0.0147 * np.arange(C)).astype(np.float32)
+    ref_g, ref_d = o.gridder(p), o.degridder(p)
+    rows = covered_rows(p)
+    assert idg.resolve_variant(p.subgrid_size, C, idg.SINCOS_FAST, 0, gridder=False) == 24
+    a = run_gridder(p, idg.SINCOS_FAST)
+    assert_close(a, ref_g, 1, idg.SINCOS_FAST, f"gridder recurrence {shape}")
+    b = run_gridder(p, idg.SINCOS_FAST, 12)
+    assert_close(b, ref_g, 1, idg.SINCOS_FAST, f"gridder per-channel {shape}")
+    assert not np.array_equal(a, b)
+    d0 = run_degridder(p, idg.SINCOS_FAST)
+    assert_close(d0[rows], ref_d[rows], 2, idg.SINCOS_FAST, f"degridder tc8 recurrence {shape}")
+    assert not d0[~rows].any(), "rows no subgrid covers must come back as zeros"
+    d1 = run_degridder(p, idg.SINCOS_FAST, 25)
+    assert_close(d1[rows], ref_d[rows], 2, idg.SINCOS_FAST, f"degridder tc8 per-channel {shape}")
+    assert not np.array_equal(d0, d1)
+    # the recurrence costs accuracy of the order of the fp32 rounding, not of the tolerance
+    mx, _ = per_pol_errors(d0[rows], d1[rows], 2)
+    assert (mx < 5e-5).all(), mx
 
 
 def test_channel_rotation_is_checked_per_block():
