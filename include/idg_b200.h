@@ -241,7 +241,8 @@ int idgb200_host_free(void *ptr);
  * environment variables (GRID_SIZE, SUBGRID_SIZE, NR_STATIONS, NR_TIMESLOTS,
  * NR_TIMESTEPS_SUBGRID, NR_CHANNELS, NR_WARM_UP_RUNS, NR_ITERATIONS), the same
  * report line on stdout.  Unlike the reference all device buffers are
- * initialised (idgb200_init_* below) before timing. */
+ * initialised (idgb200_init_* below) before timing.  IDGB200_ENERGY_SECONDS (default 2,
+ * 0 = off): how long the kernel is relaunched for the energy columns. */
 typedef struct {
   double seconds;     /* mean kernel time over the timed iterations (CUDA events) */
   double gflops;      /* flops_gridder * 1e-9 (work per launch, not a rate)       */
@@ -249,6 +250,9 @@ typedef struct {
   double mvis;        /* 1e-6 * total_timesteps * nr_channels                     */
   int32_t nr_subgrids;
   int32_t iterations;
+  double joules;      /* energy per launch from the GPU's NVML counter (0 = not available); replaces the
+                         PowerSensor measurement of util.cpp:131-155: W = joules / seconds,
+                         GFLOP/s/W = gflops / joules, MVis/J = mvis / joules (common.cpp:47-54) */
 } idgb200_perf;
 
 int idgb200_p_run_gridder(idgb200_perf *result /* may be NULL */);

@@ -18,7 +18,8 @@ class Params(C.Structure):  # idgb200_params
 
 class Perf(C.Structure):  # idgb200_perf
     _fields_ = [("seconds", C.c_double), ("gflops", C.c_double), ("gbytes", C.c_double),
-                ("mvis", C.c_double), ("nr_subgrids", C.c_int32), ("iterations", C.c_int32)]
+                ("mvis", C.c_double), ("nr_subgrids", C.c_int32), ("iterations", C.c_int32),
+                ("joules", C.c_double)]
 
 
 # every symbol include/idg_b200.h declares: name -> (restype, argtypes)

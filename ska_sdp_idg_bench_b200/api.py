@@ -268,9 +268,12 @@ def degridder(nr_subgrids, grid_size, subgrid_size, image_size, w_step_in_lambda
 def _perf(fn) -> dict:
     r = Perf()
     _check(fn(C.byref(r)))
-    return dict(seconds=r.seconds, gflops=r.gflops, gbytes=r.gbytes, mvis=r.mvis,
-                nr_subgrids=r.nr_subgrids, iterations=r.iterations,
-                mvis_per_s=r.mvis / r.seconds, tflops_per_s=r.gflops / r.seconds * 1e-3)
+    out = dict(seconds=r.seconds, gflops=r.gflops, gbytes=r.gbytes, mvis=r.mvis,
+               nr_subgrids=r.nr_subgrids, iterations=r.iterations,
+               mvis_per_s=r.mvis / r.seconds, tflops_per_s=r.gflops / r.seconds * 1e-3, joules=r.joules)
+    if r.joules > 0:   # the reference's energy columns (app/common/common.cpp:47-54)
+        out.update(watts=r.joules / r.seconds, gflops_per_watt=r.gflops / r.joules, mvis_per_joule=r.mvis / r.joules)
+    return out
 
 
 def p_run_gridder() -> dict:

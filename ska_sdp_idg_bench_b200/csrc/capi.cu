@@ -4,6 +4,9 @@
 //
 // There is deliberately no CPU code path here: without a CUDA device every
 // compute entry point returns IDGB200_ENODEVICE.
+#include <dlfcn.h>
+
+#include <algorithm>
 #include <atomic>
 #include <cmath>
 #include <cstdio>
@@ -463,18 +466,20 @@ __global__ void k_init_subgrids(int64_t count, int N, float2 *sg) {  // init.cpp
 unsigned blocks_for(int64_t n, int bs = 256) { return (unsigned)((n + bs - 1) / bs); }
 
 // report line of the reference (app/common/common.cpp:27-56)
-void report(const char *name, double seconds, double gflops, double gbytes, double mvis) {
+void report(const char *name, double seconds, double gflops, double gbytes, double mvis, double joules) {
   std::printf("%20s: %7.2f ms", name, seconds * 1e3);
   if (gflops != 0) std::printf(", %7.2f GFLOP/s", gflops / seconds);
   if (gbytes != 0) std::printf(", %7.2f GB/s", gbytes / seconds);
   if (gflops != 0 && gbytes != 0) std::printf(", %7.2f FLOP/byte", gflops / gbytes);
   if (mvis != 0) std::printf(", %7.2f MVis/s", mvis / seconds);
+  if (joules != 0)   // common.cpp:47-54
+    std::printf(", %7.2f W, %7.2f GFLOP/s/W, %7.2f MVis/J", joules / seconds, gflops / joules, mvis / joules);
   std::printf("\n");
   std::fflush(stdout);
 }
 
 // key,value CSV of the reference (app/common/common.cpp:58-98)
-void report_csv(const char *name, double seconds, double gflops, double gbytes, double mvis) {
+void report_csv(const char *name, double seconds, double gflops, double gbytes, double mvis, double joules) {
   char dev[256] = "";
   idgb200_device_name(dev, sizeof dev);
   for (char *c = dev; *c; c++)
@@ -488,10 +493,55 @@ void report_csv(const char *name, double seconds, double gflops, double gbytes, 
     if (gbytes != 0) std::fprintf(f, "GB/s,%.2f\n", gbytes / seconds);
     if (gflops != 0 && gbytes != 0) std::fprintf(f, "FLOP/Byte,%.2f\n", gflops / gbytes);
     if (mvis != 0) std::fprintf(f, "MVis/s,%.2f\n", mvis / seconds);
+    if (joules != 0) {   // common.cpp:88-95
+      std::fprintf(f, "W,%.2f\n", joules / seconds);
+      std::fprintf(f, "GFLOP/s/W,%.2f\n", gflops / joules);
+      std::fprintf(f, "MVis/J,%.2f\n", mvis / joules);
+    }
     std::fclose(f);
     std::printf("Saving output in %s\n", path.c_str());
   }
 }
+
+// Energy per launch.  The reference measures it with PowerSensor, an external library
+// that is not vendored (app/CUDA/util.cpp:131-155: the kernel is relaunched for 10 s between two
+// sensor reads).  Here the same protocol reads the GPU's own energy counter through NVML
+// (nvmlDeviceGetTotalEnergyConsumption, millijoules since driver load), loaded at run time so that
+// the library has no link-time dependency; no NVML or no counter -> 0 and the columns are left out,
+// as in a reference build without PowerSensor.
+class EnergyMeter {
+ public:
+  EnergyMeter() {
+    lib_ = dlopen("libnvidia-ml.so.1", RTLD_NOW | RTLD_LOCAL);
+    if (!lib_) return;
+    auto init = reinterpret_cast<int (*)()>(dlsym(lib_, "nvmlInit_v2"));
+    by_bus_ = reinterpret_cast<int (*)(const char *, void **)>(dlsym(lib_, "nvmlDeviceGetHandleByPciBusId_v2"));
+    energy_ = reinterpret_cast<int (*)(void *, unsigned long long *)>(dlsym(lib_, "nvmlDeviceGetTotalEnergyConsumption"));
+    if (!init || !by_bus_ || !energy_ || init() != 0) return;
+    int dev = 0;
+    char bus[32] = "";
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetPCIBusId(bus, sizeof bus, dev) != cudaSuccess) return;
+    if (by_bus_(bus, &handle_) != 0) handle_ = nullptr;
+    unsigned long long mj = 0;
+    if (handle_ && energy_(handle_, &mj) != 0) handle_ = nullptr;
+  }
+  ~EnergyMeter() {
+    if (lib_) {
+      if (auto shutdown = reinterpret_cast<int (*)()>(dlsym(lib_, "nvmlShutdown"))) shutdown();
+      dlclose(lib_);
+    }
+  }
+  bool ok() const { return handle_ != nullptr; }
+  double joules() const {
+    unsigned long long mj = 0;
+    return (handle_ && energy_(handle_, &mj) == 0) ? 1e-3 * (double)mj : 0.0;
+  }
+
+ private:
+  void *lib_ = nullptr, *handle_ = nullptr;
+  int (*by_bus_)(const char *, void **) = nullptr;
+  int (*energy_)(void *, unsigned long long *) = nullptr;
+};
 
 int perf_run(bool gridding, idgb200_perf *result) {
   int rc = have_device();
@@ -567,10 +617,27 @@ int perf_run(bool gridding, idgb200_perf *result) {
   const double gflops = 1e-9 * idgb200_flops_gridder(C, tt, S, N, NR_POL);
   const double gbytes = 1e-9 * idgb200_bytes_gridder(C, tt, S, N, NR_POL);
   const double mvis = 1e-6 * tt * C;
+  // energy: relaunch for IDGB200_ENERGY_SECONDS (default 2; 0 = off) between two counter reads
+  double joules = 0;
+  const double energy_s = (double)env_long("IDGB200_ENERGY_SECONDS", 2);
+  if (energy_s > 0) {
+    EnergyMeter meter;
+    if (meter.ok()) {
+      const int launches = (int)std::max(1.0, energy_s / seconds);
+      CK(cudaDeviceSynchronize());
+      const double j0 = meter.joules();
+      for (int i = 0; i < launches && !rc; i++) rc = run();
+      if (rc) return rc;
+      CK(cudaDeviceSynchronize());
+      const double j1 = meter.joules();
+      if (j1 > j0) joules = (j1 - j0) / launches;
+    }
+  }
   const char *name = gridding ? "gridder_b200" : "degridder_b200";
-  report(name, seconds, gflops, gbytes, mvis);
-  report_csv(name, seconds, gflops, gbytes, mvis);
+  report(name, seconds, gflops, gbytes, mvis, joules);
+  report_csv(name, seconds, gflops, gbytes, mvis, joules);
   if (result) {
+    result->joules = joules;
     result->seconds = seconds;
     result->gflops = gflops;
     result->gbytes = gbytes;

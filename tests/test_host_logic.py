@@ -36,7 +36,7 @@ def test_header_symbols_all_exported():
 def test_abi_struct_sizes():
     assert C.sizeof(_lib.Params) == 64
     assert idg.METADATA_DTYPE.itemsize == 36
-    assert C.sizeof(_lib.Perf) == 40
+    assert C.sizeof(_lib.Perf) == 48
 
 
 @pytest.mark.parametrize("shape", [(16, 24500 * 128, 24500, 32), (64, 1000, 10, 32), (16, 77, 3, 64),
@@ -112,7 +112,8 @@ def test_default_variant_selection():
     assert idg.resolve_variant(32, 9, idg.SINCOS_FAST) == 10     # 9 of 16 channels
     assert idg.resolve_variant(32, 4096, idg.SINCOS_FAST) == 10  # wavenumber tables beyond the smem budget
     assert idg.resolve_variant(32, 16, idg.SINCOS_FAST, variant=3) == 3
-    assert idg.resolve_variant(32, 16, idg.SINCOS_FAST, gridder=False) == 22
+    assert idg.resolve_variant(32, 16, idg.SINCOS_FAST, gridder=False) == 24   # groups of 8 channels: two tiles per warp
+    assert idg.resolve_variant(32, 12, idg.SINCOS_FAST, gridder=False) == 22   # quads of 4 channels
     assert idg.resolve_variant(32, 16, idg.SINCOS_ACCURATE, gridder=False) == 4
     assert idg.resolve_variant(32, 1, idg.SINCOS_FAST, gridder=False) == 4     # 1 of 4 channels
     assert idg.resolve_variant(8, 16, idg.SINCOS_FAST, gridder=False) == 4     # 64 pixels
