@@ -32,14 +32,19 @@
 //     ring at a time by tcgen05.commit from every tile;
 //   epilogue: tcgen05.ld of the accumulators (a warp can only read its own 32-lane quadrant),
 //     A-terms, taper, coalesced stores - identical math to gridder.cu.
-// Every mbarrier wait is bounded (trap instead of hang).
+// Every mbarrier wait is bounded (trap instead of hang) and carries a suspend-time hint, so that a
+// waiting warp sleeps in the barrier unit instead of polling through the shared issue port.
 //
 // On top of that, selected by template / launch parameters:
 //   recur - blocks of 8 equally spaced channels (checked per block, common.cuh: linear_channels) get
-//           their phasors by complex rotation from the block's first channel, FMUL2 + FFMA2 per
-//           step, as the reference's gridder_v8 assumes unconditionally: the XU stops being the
-//           roof, the dispatch port takes over;
-//   WIDE  - both channel blocks of a timestep in the tile's two A buffers as one K = 32 stage;
+//           their phasors from the block's first channel: one complex rotation (FMUL2 + FFMA2) for
+//           the second, then the three-term recurrence ph[c+1] = 2 cos(delta) ph[c] - ph[c-1], one
+//           FFMA2 per phasor (the reference's gridder_v8 rotates every channel and assumes the
+//           spacing unconditionally): the XU stops being the roof;
+//   WIDE  - both channel blocks of a timestep in the tile's two A buffers as one K = 32 stage; when
+//           every block is linear with one spacing and their number is even (the benchmark, SKA-Low)
+//           the stage loop is a second, lean one: three counters of per-stage state instead of
+//           ~170 instructions of flags, slot / phase arithmetic and rematerialised addresses;
 //   SPLIT - fp16 hi + lo phasors (second A buffer, second MMA): FP32-class accuracy;
 //   MASK16 - where the recurrence does not apply, part of the channels' phasors from an FP32
 //           polynomial instead of MUFU.
