@@ -50,3 +50,41 @@ for case in range(n_cases):
     print(f"case {case}: N={N} C={C} T<={T} S={S} linear={linear} gridder v{idg.resolve_variant(N, C, 0)} "
           f"degridder v{idg.resolve_variant(N, C, 0, gridder=False)} ok, worst error / tolerance so far {worst:.3f}")
 print(f"{n_cases} cases passed; worst error / tolerance = {worst:.3f}")
+
+# ---- the next rows: subgrid FFT, adder, splitter on random shapes and positions
+import torch  # noqa: E402
+
+dev = torch.device("cuda", 0)
+worst_fft = worst_add = 0.0
+for case in range(n_cases):
+    N = int(rng.choice([8, 12, 16, 20, 24, 32, 40, 48, 64]))
+    G = int(rng.choice([64, 100, 256, 1000]))
+    S = int(rng.integers(1, 40))
+    flags = int(rng.integers(0, 2))
+    p = random_problem(int(rng.integers(1 << 30)), subgrid_size=N, nr_subgrids=S, grid_size=G, max_timesteps=1,
+                       nr_channels=1)
+    p.metadata["x"] = rng.integers(-N, G + N, S)        # overhang on every side, some fully outside
+    p.metadata["y"] = rng.integers(-N, G + N, S)
+    meta = torch.from_numpy(np.ascontiguousarray(p.metadata).view(np.int32).reshape(-1, 9)).to(dev)
+    sg = torch.from_numpy(p.subgrids).to(dev)
+    for direction in (1, -1):
+        t = sg.clone()
+        idg.subgrid_fft(S, N, t, direction)
+        ref = o.subgrid_fft(p.subgrids, direction)
+        err = float(np.abs(t.cpu().numpy() - ref).max() / np.abs(ref).max())
+        worst_fft = max(worst_fft, err / (2e-6 * max(1.0, np.log2(N * N))))
+    grid = torch.zeros((4, G, G), dtype=torch.complex64, device=dev)
+    idg.adder(S, G, N, meta, sg, grid, flags=flags)
+    ref = o.adder(p, flags=flags)
+    scale = max(float(np.abs(ref).max()), 1e-30)
+    worst_add = max(worst_add, float(np.abs(grid.cpu().numpy() - ref).max() / scale) / 1e-5)
+    out = torch.full_like(sg, float("nan"))
+    idg.splitter(S, G, N, meta, out, grid, flags=flags)
+    if not np.array_equal(out.cpu().numpy(), o.splitter(p, grid.cpu().numpy(), flags=flags)):
+        print("FAIL splitter", dict(N=N, G=G, S=S, flags=flags))
+        sys.exit(1)
+    if worst_fft > 1 or worst_add > 1:
+        print("FAIL fft/adder", dict(N=N, G=G, S=S, flags=flags), worst_fft, worst_add)
+        sys.exit(1)
+print(f"{n_cases} next-row cases passed (splitter bit-exact); worst error / tolerance: fft {worst_fft:.3f}, "
+      f"adder {worst_add:.3f}")
