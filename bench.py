@@ -50,7 +50,7 @@ SM_XU_LANES = 16      # MUFU lanes per SM
 # + 6 recurrence steps 12 + 8 x 4 = 32 + STS 4 = 66 / 8 = 8.25.
 TC_GRIDDER = {11: (2.0, 10.1, None), 12: (1.5, 12.6, None), 13: (1.375, 12.9, None), 14: (1.25, 13.3, None),
               15: (1.0, 14.2, None), 21: (0.375, 10.0, None), 22: (0.375, 15.2, None), 23: (2.0, 17.1, None),
-              24: (0.382, 6.91, 4.19)}
+              24: (0.382, 6.91, 4.19), 26: (0.382, 6.91, 4.19)}
 TC_DEGRIDDER = {11: (2.0, 11.5, None), 12: (1.5, 13.5, None), 13: (1.25, 13.2, None), 14: (1.0, 15.5, None),
                 21: (1.0, 10.5, None), 22: (1.006, 14.63, 10.0), 23: (2.0, 18.5, None),
                 24: (0.505, 11.95, 8.25)}
@@ -589,7 +589,7 @@ def run_ours(args) -> None:
                                            "TMEM" + ("; phasors of equally spaced channels from the first channel of each "
                                                      "8-channel block by one rotation and the three-term recurrence (the "
                                                      "reference's gridder_v8 rotates every channel)"
-                                                     if g_variant in (21, 24) else "")
+                                                     if g_variant in (21, 24, 26) else "")
                                            if tc_g is not None else "FP32 FFMA2 + MUFU"),
                            degridder_kernel=(("tcgen05: fp16 hi+lo phasor tile x fp16 hi+lo pixels, f32 accumulate in "
                                               "TMEM; phasors of equally spaced channel quads by rotation"

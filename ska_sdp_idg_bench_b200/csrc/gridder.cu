@@ -33,6 +33,9 @@
 //  * phase_offset is hoisted out of the time loop (it does not depend on t) and phase /
 //    phase_index are evaluated in the CPU binary's operation order, so the angle fed to
 //    sincos is bit-identical to the reference's.
+#include <atomic>
+#include <mutex>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -367,6 +370,23 @@ cudaError_t launch_t(const KernelArgs &a, int mode, cudaStream_t stream) {
 //          3 swizzled FFMA2, 256 threads x 8 pixels
 //          4 first design: FFMA2 on duplicated records, rotated sums, software pipelined (256 x 4)
 //          5 swizzled FFMA2, 128 threads x 8 pixels, 3 blocks/SM (more registers)
+// One int per launch for variant 26's device-side decision, from a ring that is allocated once per
+// device: the three kernels of a launch are stream-ordered, and 4096 launches would have to be in
+// flight at once for a slot to be reused too early.
+static int *regular_flag_slot() {
+  static std::mutex mu;
+  static int *ring[64] = {};
+  static std::atomic<unsigned> next{0};
+  constexpr unsigned kSlots = 4096;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  {
+    std::lock_guard<std::mutex> lock(mu);
+    if (!ring[dev] && cudaMalloc(&ring[dev], kSlots * sizeof(int)) != cudaSuccess) return nullptr;
+  }
+  return ring[dev] + (next.fetch_add(1) % kSlots);
+}
+
 int resolve_gridder_variant(int subgrid_size, int nr_channels, int sincos_mode, int variant) {
   if (variant != 0) return variant;
   // the tensor kernel pads the channels to blocks of 8 (K = 16) and the pixels to tiles of 128
@@ -376,7 +396,9 @@ int resolve_gridder_variant(int subgrid_size, int nr_channels, int sincos_mode, 
   const bool tc = sincos_mode == IDGB200_SINCOS_FAST && 4 * nr_channels >= 3 * ncb * 8 &&
                   4 * npix >= 3 * tiles * 128 && nr_channels <= 1024;
   if (!tc) return 10;
-  return ncb % 2 == 0 ? 24 : 21;   // K = 32 stages when the channel blocks pair up
+  // K = 32 stages when the channel blocks pair up.  (26, two tiles per warp for regular channel layouts,
+  // measured the same 12.86 ms as 24 plus two small launches: opt-in)
+  return ncb % 2 == 0 ? 24 : 21;
 }
 
 cudaError_t launch_gridder(const KernelArgs &a, int sincos_mode, int variant, cudaStream_t stream) {
@@ -396,6 +418,15 @@ cudaError_t launch_gridder(const KernelArgs &a, int sincos_mode, int variant, cu
       return sincos_mode == IDGB200_SINCOS_FAST ? launch_gridder_tc(a, 10, false, stream) : cudaErrorInvalidValue;
     case 24:   // as 21 with 16 channels (K = 32) per stage, single-buffered
       return sincos_mode == IDGB200_SINCOS_FAST ? launch_gridder_tc(a, 11, true, stream) : cudaErrorInvalidValue;
+    case 26: {   // gridder_tc8.cu where the channel layout is regular (decided on the device), else 24
+      if (sincos_mode != IDGB200_SINCOS_FAST) return cudaErrorInvalidValue;
+      int *flag = regular_flag_slot();
+      if (!flag) return cudaErrorMemoryAllocation;
+      cudaError_t e = launch_gridder_regular_check(a, flag, stream);
+      if (e == cudaSuccess) e = launch_gridder_tc8(a, flag, stream);
+      if (e == cudaSuccess) e = launch_gridder_tc(a, 11, true, stream, flag);
+      return e;
+    }
     case 21:   // tensor-core kernel, phasors of equally spaced channel blocks by rotation (else as 12)
       return sincos_mode == IDGB200_SINCOS_FAST ? launch_gridder_tc(a, 3, true, stream) : cudaErrorInvalidValue;
     case 16: case 17: case 18: case 19:   // phasor tile in TMEM; 18, 19: fp16 hi + lo phasors

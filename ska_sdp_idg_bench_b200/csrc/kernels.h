@@ -35,7 +35,13 @@ int resolve_gridder_variant(int subgrid_size, int nr_channels, int sincos_mode, 
 int resolve_degridder_variant(int subgrid_size, int nr_channels, int sincos_mode, int variant);
 
 // tcgen05 / TMEM gridder (gridder_tc.cu); FAST sincos only
-cudaError_t launch_gridder_tc(const KernelArgs &a, int poly, bool recur, cudaStream_t stream);
+// skip_flag (device, may be null): the kernel returns at once when *skip_flag != 0
+cudaError_t launch_gridder_tc(const KernelArgs &a, int poly, bool recur, cudaStream_t stream,
+                              const int *skip_flag = nullptr);
+// two M-tiles per warp, regular channel layouts only (gridder_tc8.cu): the check writes *d_flag = 1 when every
+// 8-channel block is equally spaced with one spacing and the blocks pair up; the kernel is a no-op unless it is set
+cudaError_t launch_gridder_regular_check(const KernelArgs &a, int *d_flag, cudaStream_t stream);
+cudaError_t launch_gridder_tc8(const KernelArgs &a, const int *d_regular_flag, cudaStream_t stream);
 cudaError_t launch_degridder_tc(const KernelArgs &a, int poly, bool recur, cudaStream_t stream);
 // two M-tiles per warp, groups of 8 channels (degridder_tc8.cu); nr_channels % 8 == 0
 cudaError_t launch_degridder_tc8(const KernelArgs &a, bool recur, cudaStream_t stream);
