@@ -56,6 +56,17 @@ TC_DEGRIDDER = {11: (2.0, 11.5, None), 12: (1.5, 13.5, None), 13: (1.25, 13.2, N
                 24: (0.505, 11.95, 8.25)}
 
 
+# tcgen05.mma instructions (M=128, N=16, K=16, both operands in shared memory) per (pixel, visibility) item:
+# one MMA covers 128 rows x 8 K-pairs = 1024 items; the hi + lo phasor kernels issue two per block.
+TC_MMA_PER_ITEM = {"gridder": {21: 1 / 1024, 24: 1 / 1024, 26: 1 / 1024, 22: 2 / 1024, 23: 2 / 1024},
+                   "degridder": {21: 1 / 1024, 22: 2 / 1024, 23: 2 / 1024, 24: 2 / 1024, 25: 2 / 1024}}
+# measured on the B200 (tools/smem_mix.cu, profiles/r01_smem_mix_microbench.log): tcgen05.mma of that shape take
+# 40.0 clocks each on an SM when the pipe stays fed (256 between two commits; 51-55 with a drain every 16) - the
+# 4 KB A tile is fetched from shared memory at ~100 B/clk, 5x the 8 clocks of its math - and concurrent STS.128
+# traffic of the LSU does not slow them (the two paths do not share one crossbar)
+MMA_SS_CLOCKS = 40.0
+
+
 # ----------------------------------------------------------------- shared helpers
 def shape_counts(shape: dict) -> dict:
     nbl = shape["nr_stations"] * (shape["nr_stations"] - 1) // 2
@@ -517,7 +528,7 @@ def run_ours(args) -> None:
         nbytes = idg.bytes_gridder(C_, tt, S, N)
         hbm_peak = float(peaks.get("hbm_gbs") or 6650.0)
 
-        def roof(sec, steps, traffic_per_subgrid, tc):
+        def roof(sec, steps, traffic_per_subgrid, tc, mma_per_item=None):
             """tc None: FP32 kernel (bound = the FP32 issue port); else (MUFU per item, dispatch
             cycles per warp-item) of a tensor-core kernel, whose MACs run on tcgen05 and whose roof
             is the XU (MUFU) pipe or the instruction dispatch port, whichever is busier."""
@@ -568,7 +579,24 @@ def run_ours(args) -> None:
                                                                                       inst_per_item),
                               "peak_source": f"{sms} SMs x 4 sub-partitions x {f_max:.0f} MHz; dispatch cycles per "
                                              "item from the ncu capture under profiles/"})
-                r.update({"bound_note": note, "sfu_frac": sfu_frac, "issue_frac": issue_frac}, **common)
+                if mma_per_item:
+                    # the busiest resource: the tensor core's shared-memory operand fetch (one small-N MMA per
+                    # 1024 items still reads its whole 4 KB A tile)
+                    p_mma = sms * f_max * 1e6 / MMA_SS_CLOCKS
+                    mma = mma_per_item * items / t
+                    if mma / p_mma >= max(sfu_frac, r["frac"]):
+                        r = {"bound": "tensor", "achieved": mma * 1e-9, "peak": p_mma * 1e-9,
+                             "unit": "G tcgen05.mma/s (M=128, N=16, K=16, operands in shared memory)",
+                             "frac": mma / p_mma, "useful_issue_frac": useful_frac,
+                             "peak_source": f"{sms} SMs x {f_max:.0f} MHz / {MMA_SS_CLOCKS} clocks per MMA, measured "
+                                            "back to back on this GPU type (tools/smem_mix.cu, "
+                                            "profiles/r01_smem_mix_microbench.log)",
+                             "frac_note": "share of the time the SM's tensor pipe needs for the launch's MMAs at the "
+                                          "measured rate: with N = 16 an MMA is bound by fetching its 4 KB A tile from "
+                                          "shared memory, not by its math (pipe_tensor_cycles_active 11-13 % in ncu)"}
+                r.update({"bound_note": note, "sfu_frac": sfu_frac, "issue_frac": issue_frac,
+                          "tensor_frac": (mma_per_item * items / t) / (sms * f_max * 1e6 / MMA_SS_CLOCKS)
+                          if mma_per_item else None}, **common)
             if clocks.get("sm_mhz"):
                 r["frac_at_measured_clock"] = r["frac"] * f_max / clocks["sm_mhz"]
             return r
@@ -601,12 +629,13 @@ def run_ours(args) -> None:
             "tflops": world * flops * args.steps / sec_g * 1e-12,
             # ncu --set full, 3675-subgrid launches: 343.1 MB (tcgen05 gridder), 314.7 MB (tcgen05 degridder), FP32 kernels from the
             # 1740-subgrid captures (profiles/)
-            "roofline": roof(sec_g, args.steps, 343.1e6 / 3675 if tc_g is not None else 145.165e6 / 1740, tc_g),
+            "roofline": roof(sec_g, args.steps, 343.1e6 / 3675 if tc_g is not None else 145.165e6 / 1740, tc_g,
+                             TC_MMA_PER_ITEM["gridder"].get(g_variant)),
             "degridder": {"value": total_mvis * args.steps / sec_d, "unit": "MVis/s",
                           "ms_per_step": sec_d / args.steps * 1e3,
                           "tflops": world * flops * args.steps / sec_d * 1e-12,
                           "roofline": roof(sec_d, args.steps, 314.7e6 / 3675 if tc_d is not None
-                                           else 128.329e6 / 1740, tc_d)},
+                                           else 128.329e6 / 1740, tc_d, TC_MMA_PER_ITEM["degridder"].get(d_variant))},
             "gridder_fp32": None if sec_g32 is None else {
                 "value": total_mvis * args.steps / sec_g32, "unit": "MVis/s", "variant": 10,
                 "ms_per_step": sec_g32 / args.steps * 1e3,
