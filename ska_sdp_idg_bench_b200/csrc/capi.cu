@@ -743,7 +743,7 @@ int idgb200_gridder(const idgb200_params *p, const idgb200_uvw *d_uvw, const flo
   cudaError_t e = launch_gridder(a, p->sincos_mode, p->variant, static_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) return (int)e;
   // variant 26 = channel-layout check + the two-tile kernel + the (gated) generic kernel
-  g_launches += resolve_gridder_variant(p->subgrid_size, p->nr_channels, p->sincos_mode, p->variant) == 26 ? 3 : 1;
+  g_launches += resolve_gridder_variant(p->subgrid_size, p->nr_channels, p->sincos_mode, p->variant) >= 26 ? 3 : 1;
   return IDGB200_OK;
 }
 

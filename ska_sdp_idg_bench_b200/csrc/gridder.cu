@@ -418,12 +418,13 @@ cudaError_t launch_gridder(const KernelArgs &a, int sincos_mode, int variant, cu
       return sincos_mode == IDGB200_SINCOS_FAST ? launch_gridder_tc(a, 10, false, stream) : cudaErrorInvalidValue;
     case 24:   // as 21 with 16 channels (K = 32) per stage, single-buffered
       return sincos_mode == IDGB200_SINCOS_FAST ? launch_gridder_tc(a, 11, true, stream) : cudaErrorInvalidValue;
-    case 26: {   // gridder_tc8.cu where the channel layout is regular (decided on the device), else 24
+    case 26:     // gridder_tc8.cu where the channel layout is regular (decided on the device), else 24
+    case 27: {   // gridder_tc4.cu (phasor operand in TMEM) likewise
       if (sincos_mode != IDGB200_SINCOS_FAST) return cudaErrorInvalidValue;
       int *flag = regular_flag_slot();
       if (!flag) return cudaErrorMemoryAllocation;
       cudaError_t e = launch_gridder_regular_check(a, flag, stream);
-      if (e == cudaSuccess) e = launch_gridder_tc8(a, flag, stream);
+      if (e == cudaSuccess) e = variant == 26 ? launch_gridder_tc8(a, flag, stream) : launch_gridder_tc4(a, flag, stream);
       if (e == cudaSuccess) e = launch_gridder_tc(a, 11, true, stream, flag);
       return e;
     }

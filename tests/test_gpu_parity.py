@@ -135,7 +135,7 @@ def test_gridder_tensor_core_variant(config1):
     """variant 11 = tcgen05 kernel (what variant 0 picks for FAST sincos), variant 10 = FP32
     kernel: both inside the FAST tolerance; the tensor kernel refuses the other sincos modes."""
     p, ref_g, _ = config1
-    for v in (11, 12, 13, 14, 15, 16, 17, 18, 19, 21, 22, 23, 24, 26):   # 12..15: part of the phasors from the FP32 polynomial; 16..19: phasor tile in TMEM
+    for v in (11, 12, 13, 14, 15, 16, 17, 18, 19, 21, 22, 23, 24, 26, 27):   # 12..15: part of the phasors from the FP32 polynomial; 16..19: phasor tile in TMEM
         mx, rms = assert_close(run_gridder(p, idg.SINCOS_FAST, v), ref_g, 1, idg.SINCOS_FAST, f"gridder tcgen05 v{v}")
         print(f"tcgen05 gridder v{v}: per-pol max rel {mx}, rel rms {rms}")
     mx, rms = assert_close(run_gridder(p, idg.SINCOS_FAST, 10), ref_g, 1, idg.SINCOS_FAST, "gridder fp32")
@@ -213,7 +213,7 @@ def test_shapes_vs_oracle(shape):
     for variant in (0, 2):
         assert_close(run_gridder(p, idg.SINCOS_ACCURATE, variant), ref_g, 1, idg.SINCOS_ACCURATE,
                      f"gridder {shape} v{variant}")
-    for variant in (11, 12, 17, 19, 21, 22, 24, 26):
+    for variant in (11, 12, 17, 19, 21, 22, 24, 26, 27):
         assert_close(run_gridder(p, idg.SINCOS_FAST, variant), ref_g, 1, idg.SINCOS_FAST,
                      f"gridder tcgen05 {shape} v{variant}")
     rows = covered_rows(p)
