@@ -200,13 +200,8 @@ gridder_tc4_kernel(const KernelArgs a, const int slabs, const int tiles_per_cta,
           for (int j = 0; j < 4; j++) tmem_st16(tmem_grp + j * G4_TCOLS + 16 + lane_base, pk[j]);
           asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
           asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-          // producer / consumer use of the group's named barrier: quadrants 1-3 only arrive and go on to
-          // the next stage's phasors (they meet the single-buffered A columns again at the empty barrier),
-          // the issuing warp waits for all four
-          if (q4 != 0) {
-            asm volatile("bar.arrive %0, 128;" ::"r"(1 + grp) : "memory");
-          } else {
-            asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+          asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+          if (q4 == 0) {
             mbar_wait_u(bfull_u + slot2 * 8, ring_phase);
             mbar_wait_u(bfull_u + slot2 * 8 + 8, ring_phase);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
