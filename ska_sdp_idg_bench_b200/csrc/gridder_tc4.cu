@@ -17,6 +17,8 @@
 // Regular channel layouts only, behind the same device-side check and gate as gridder_tc8.cu.
 #include <cuda_fp16.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.h"
 #include "tc_common.cuh"
@@ -68,7 +70,8 @@ __device__ __forceinline__ void g4_block(const float wn0, const float2 d, const 
 }
 
 __global__ void __launch_bounds__(G4_THREADS, 2)
-gridder_tc4_kernel(const KernelArgs a, const int slabs, const int tiles_per_cta, const int *__restrict__ regular_flag) {
+gridder_tc4_kernel(const KernelArgs a, const int slabs, const int tiles_per_cta, const int *__restrict__ regular_flag,
+                   const int arrive_split) {
   if (*regular_flag == 0) return;   // irregular channels: gridder_tc.cu runs instead
   extern __shared__ __align__(1024) unsigned char smem[];
   constexpr int TMEM_COLS = G4_TILES * G4_TCOLS;              // 256
@@ -200,7 +203,13 @@ gridder_tc4_kernel(const KernelArgs a, const int slabs, const int tiles_per_cta,
           for (int j = 0; j < 4; j++) tmem_st16(tmem_grp + j * G4_TCOLS + 16 + lane_base, pk[j]);
           asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
           asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-          asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+          // the group's named barrier.  arrive_split (IDGB200_TC4_SPLIT=1, experimental): quadrants 1-3 only
+          // arrive and go on to the next stage's phasors - they meet the single-buffered A columns again at
+          // the empty barrier - and only the issuing warp waits for all four
+          if (arrive_split && q4 != 0)
+            asm volatile("bar.arrive %0, 128;" ::"r"(1 + grp) : "memory");
+          else
+            asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
           if (q4 == 0) {
             mbar_wait_u(bfull_u + slot2 * 8, ring_phase);
             mbar_wait_u(bfull_u + slot2 * 8 + 8, ring_phase);
@@ -325,7 +334,9 @@ cudaError_t launch_gridder_tc4(const KernelArgs &a, const int *d_regular_flag, c
   auto k = gridder_tc4_kernel;
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  k<<<dim3((unsigned)a.nr_subgrids * nslabs), dim3(G4_THREADS), smem, stream>>>(a, nslabs, tiles_per_cta, d_regular_flag);
+  const char *split = std::getenv("IDGB200_TC4_SPLIT");
+  k<<<dim3((unsigned)a.nr_subgrids * nslabs), dim3(G4_THREADS), smem, stream>>>(a, nslabs, tiles_per_cta, d_regular_flag,
+                                                                                 split && split[0] == '1' ? 1 : 0);
   return cudaGetLastError();
 }
 
