@@ -532,3 +532,14 @@ def test_reference_harness_dropin(kind):
     env = dict(os.environ, NR_STATIONS="8", NR_TIMESLOTS="2", NR_ITERATIONS="2")
     out = subprocess.run([exe], capture_output=True, text=True, env=env, timeout=300)
     assert out.returncode == 0 and "MVis/s" in out.stdout, out.stdout + out.stderr
+
+
+def test_c_example_imaging_cycle():
+    """examples/imaging_cycle.c: gridder -> FFT -> adder -> splitter -> inverse FFT -> degridder through
+    the C ABI from plain C on device-resident data; the program checks itself."""
+    import subprocess
+
+    from test_host_logic import build_c_example
+    r = subprocess.run([build_c_example(), "6", "2"], capture_output=True, text=True, timeout=300)
+    print(r.stdout, r.stderr)
+    assert r.returncode == 0 and "imaging cycle OK" in r.stdout

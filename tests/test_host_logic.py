@@ -224,3 +224,21 @@ def test_bench_multi_rank_logic_gloo_world2():
     assert res[0][1] == res[1][1] == 15 * 5
     assert res[0][2] == res[1][2] == 2 * 75
     assert abs(res[0][3] - 0.020) < 1e-9 and abs(res[1][3] - 0.020) < 1e-9
+
+
+def build_c_example() -> str:
+    """examples/imaging_cycle.c: the C ABI used from plain C (gcc, no CUDA headers)."""
+    import subprocess
+    pkg = os.path.join(ROOT, "ska_sdp_idg_bench_b200")
+    exe = os.path.join(ROOT, "examples", "imaging_cycle")
+    subprocess.run(["gcc", "-O2", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "examples", "imaging_cycle.c"), "-L", pkg, "-lidgb200",
+                    f"-Wl,-rpath,{pkg}", "-L/usr/local/cuda/lib64", "-lcudart", "-lm", "-o", exe], check=True)
+    return exe
+
+
+@pytest.mark.skipif(_has_gpu(), reason="checks the no-device behaviour")
+def test_c_example_builds_and_refuses_without_a_device():
+    import subprocess
+    r = subprocess.run([build_c_example()], capture_output=True, text=True)
+    assert r.returncode != 0 and "imaging cycle OK" not in r.stdout
