@@ -441,12 +441,31 @@ def run_ours(args) -> None:
         torch.cuda.synchronize()
         h2d_gbs = (1 << 30) / (pe0.elapsed_time(pe1) * 1e-3) * 1e-9
         del probe_h, probe_d
+        # the degridder the same way: subgrids host -> device, visibilities device -> host
+        def e2e_step_d():
+            idg.c_run_degridder(*a, sincos=sincos, variant=args.degridder_variant)
+
+        for _ in range(2):
+            e2e_step_d()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e_steps):
+            e2e_step_d()
+        torch.cuda.synchronize()
+        sec_ed = reduce_max_time(time.perf_counter() - t0, dev)
+        e2e_degridder = {"value": world * shape["mvis"] * e_steps / sec_ed, "unit": "MVis/s",
+                         "ms_per_step": sec_ed / e_steps * 1e3,
+                         "h2d_bytes_per_step": int(sum(npy[k].nbytes for k in ("uvw", "wavenumbers", "spheroidal", "aterms",
+                                                                               "metadata", "subgrids"))),
+                         "d2h_bytes_per_step": int(npy["visibilities"].nbytes),
+                         "api": "idgb200_c_run_degridder_ex (host pointers, pinned)"}
         e2e = {"value": world * shape["mvis"] * e_steps / sec_e, "unit": "MVis/s",
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(npy["subgrids"].nbytes),
                "ms_per_step": sec_e / e_steps * 1e3, "steps": e_steps,
                "api": "idgb200_c_run_gridder_ex (host pointers, pinned; chunked H2D/kernel/D2H on 3 streams)",
                "pcie_h2d_gbs_measured": h2d_gbs, "h2d_floor_ms": h2d / (h2d_gbs * 1e9) * 1e3,
-               "note": "copy-bound: the step cannot be faster than its host->device bytes over the measured link"}
+               "note": "copy-bound: the step cannot be faster than its host->device bytes over the measured link",
+               "degridder": e2e_degridder}
 
     # ---- the "next" rows around the two kernels: subgrid FFT, adder, splitter - byte movers,
     # timed with the same protocol on a scratch copy; algorithmic bytes as in tools/next_rows_bench.py
