@@ -59,6 +59,9 @@ int check_params(const idgb200_params *p) {
   if (!(p->image_size > 0.0f)) return IDGB200_EINVAL;
   if (p->sincos_mode < 0 || p->sincos_mode > IDGB200_SINCOS_ACCURATE) return IDGB200_EINVAL;
   if (p->flags & ~IDGB200_FLAG_FFT_SHIFT) return IDGB200_EINVAL;
+  // the shifted slot and the adder / splitter rows are found with a float reciprocal that is exact for
+  // plane sizes below 2^22 pixels (common.cuh: subgrid_slot, adder.cu: div_small)
+  if ((p->flags & IDGB200_FLAG_FFT_SHIFT) && p->subgrid_size > 1024) return IDGB200_EUNSUPPORTED;
   return IDGB200_OK;
 }
 
@@ -773,6 +776,7 @@ int idgb200_adder(const idgb200_params *p, const idgb200_metadata *d_meta, const
     return IDGB200_EINVAL;
   for (int i = 0; i < nr_parts; i++)
     if (!grid_parts[i]) return IDGB200_EINVAL;
+  if (p->subgrid_size > 1024) return IDGB200_EUNSUPPORTED;   // adder.cu: div_small
   if ((rc = have_device())) return rc;
   cudaError_t e = launch_adder(p->nr_subgrids, 0, p->grid_size, p->subgrid_size, p->flags, d_meta,
                                reinterpret_cast<const float2 *>(d_sg),
@@ -792,6 +796,7 @@ int idgb200_splitter(const idgb200_params *p, const idgb200_metadata *d_meta, id
     return IDGB200_EINVAL;
   for (int i = 0; i < nr_parts; i++)
     if (!grid_parts[i]) return IDGB200_EINVAL;
+  if (p->subgrid_size > 1024) return IDGB200_EUNSUPPORTED;   // adder.cu: div_small
   if ((rc = have_device())) return rc;
   cudaError_t e = launch_splitter(p->nr_subgrids, 0, p->grid_size, p->subgrid_size, p->flags, d_meta,
                                   reinterpret_cast<float2 *>(d_sg),

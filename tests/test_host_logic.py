@@ -242,3 +242,15 @@ def test_c_example_builds_and_refuses_without_a_device():
     import subprocess
     r = subprocess.run([build_c_example()], capture_output=True, text=True)
     assert r.returncode != 0 and "imaging cycle OK" not in r.stdout
+
+
+def test_next_rows_reject_sizes_beyond_their_index_arithmetic():
+    """The shifted slot and the adder / splitter rows use a float reciprocal that is exact below 2^22
+    pixels per plane: larger subgrids are refused (before any device work), not mis-indexed."""
+    from ska_sdp_idg_bench_b200.api import _params
+    p = _params(1, 4096, 2048, 1.0, 0.0, 1, 1, 0, 0, flags=idg.FLAG_FFT_SHIFT)
+    dummy = (C.c_void_p * 1)(C.c_void_p(16))
+    assert _lib.lib.idgb200_adder(C.byref(p), C.c_void_p(16), C.c_void_p(16), dummy, 1, 4096, None) == -3
+    p.flags = 0
+    assert _lib.lib.idgb200_adder(C.byref(p), C.c_void_p(16), C.c_void_p(16), dummy, 1, 4096, None) == -3
+    assert _lib.lib.idgb200_splitter(C.byref(p), C.c_void_p(16), C.c_void_p(16), dummy, 1, 4096, None) == -3
