@@ -245,10 +245,12 @@ cudaError_t launch_degridder(const KernelArgs &a, int sincos_mode, int variant, 
       return sincos_mode == IDGB200_SINCOS_FAST ? launch_degridder_tc(a, 10, true, stream) : cudaErrorInvalidValue;
     case 23:
       return sincos_mode == IDGB200_SINCOS_FAST ? launch_degridder_tc(a, 10, false, stream) : cudaErrorInvalidValue;
-    case 24:   // two M-tiles per warp, groups of 8 channels, fp16 hi + lo phasors (nr_channels % 8 == 0); 25: no recurrence
-    case 25:
-      return sincos_mode == IDGB200_SINCOS_FAST && !(a.nr_channels & 7) ? launch_degridder_tc8(a, variant == 24, stream)
-                                                                        : cudaErrorInvalidValue;
+    case 24:   // two M-tiles per warp, groups of 8 channels, fp16 hi + lo phasors (nr_channels % 8 == 0), planar
+    case 25:   // subgrids (w = 0) folded onto half the pixels; 25: no recurrence, 28: no folding (24 before it)
+    case 28:
+      return sincos_mode == IDGB200_SINCOS_FAST && !(a.nr_channels & 7)
+                 ? launch_degridder_tc8(a, variant != 25, variant == 24, stream)
+                 : cudaErrorInvalidValue;
     default: return cudaErrorInvalidValue;
   }
 }

@@ -107,6 +107,7 @@ __device__ __forceinline__ void etc_produce_linear(unsigned char *A, const float
           cur[q] = nxt;
         }
       }
+      if ((IDGB200_ABLATE & 2) && !ablate_never()) continue;
       unsigned char *row = A + (c >> 2) * (2 * E_A_BUF) + kc * A_CHUNK_BYTES + (lane + 32 * (c & 3)) * 16;
       *reinterpret_cast<uint4 *>(row) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
       *reinterpret_cast<uint4 *>(row + E_A_BUF) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
@@ -133,7 +134,7 @@ __device__ __forceinline__ void etc_produce(unsigned char *A, const float4 *geo,
 }
 
 __global__ void __launch_bounds__(E_THREADS, 3)
-degridder_tc8_kernel(const KernelArgs a, const int recur) {
+degridder_tc8_kernel(const KernelArgs a, const int recur, const int fold_ok) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const int N = a.subgrid_size, C = a.nr_channels, npix = N * N;
   const int s = a.subgrid_offset + blockIdx.x;
@@ -150,14 +151,12 @@ degridder_tc8_kernel(const KernelArgs a, const int recur) {
   const int pairs_sub = (octs + 31) >> 5;
   const int rounds = (pairs_sub + E_PAIRS - 1) / E_PAIRS;
   const int ppr = (pairs_sub + rounds - 1) / rounds;
-  const int nstages = (npix + E_PB - 1) / E_PB;
-  const int ngroups = (nstages + E_GROUP - 1) / E_GROUP;
 
   unsigned char *sA = smem;                                                      // [warp][half][hi|lo][4 KB]
   unsigned char *sB = sA + E_PAIRS * E_A_WARP;                                   // [NG * GROUP][512 B]
   float4 *sG = reinterpret_cast<float4 *>(sB + E_NG * E_GROUP * E_B_SLOT);       // [NG * GROUP][8] (l, m, n, off)
-  float *scratch = reinterpret_cast<float *>(sG + E_NG * E_GROUP * E_PB);        // [32][8] builder scratch
-  unsigned long long *aempty = reinterpret_cast<unsigned long long *>(scratch + 32 * 8);  // [warp]
+  float *scratch = reinterpret_cast<float *>(sG + E_NG * E_GROUP * E_PB);        // [2][32][8] builder scratch
+  unsigned long long *aempty = reinterpret_cast<unsigned long long *>(scratch + 2 * 32 * 8);  // [warp]
   unsigned long long *bfull = aempty + E_PAIRS;                                  // [NG]
   unsigned long long *bempty = bfull + E_NG;                                     // [NG]
   unsigned long long *done = bempty + E_NG;
@@ -188,15 +187,41 @@ degridder_tc8_kernel(const KernelArgs a, const int recur) {
   const float2 *sub = a.subgrids + (size_t)s * NR_POL * plane;
   const float *g_uvw = reinterpret_cast<const float *>(a.uvw) + (size_t)ctx.time_offset * 3;
 
-  // fp16 has 5 exponent bits: scale P' by a power of two so that its largest component lands in
-  // [2^13, 2^14) (exact; undone in the epilogue), as in degridder_tc.cu
+  // Planar subgrids (w = 0 for every timestep and no w offset - the reference's own synthetic
+  // observation, init.cpp:4-25, and any snapshot of a coplanar array): pixel q and its mirror image
+  // q' = npix - 1 - q have l, m negated, so their phases are exact negatives of each other in the
+  // reference's own fp32 arithmetic (every operation of degridder_reference.cpp:96-112 is odd in
+  // (l, m) once the w terms are +-0) and the phasor of q' is the conjugate of q's, bit for bit.  Then
+  //   P[q] ph + P[q'] conj(ph) = (P[q] + P[q']) cos + i (P[q] - P[q']) sin,
+  // i.e. the same GEMM over HALF the pixels with B built from the sum and the difference of the
+  // pair: half the phasors, half the operand stores, half the MMAs.  Checked per subgrid; anything
+  // else (w != 0, odd subgrid size) takes the full sum.
+  int planar = fold_ok && ctx.w_offset == 0.f && !(N & 1);
+  for (int t = tid; t < nt; t += E_THREADS) planar &= __ldg(&g_uvw[3 * t + 2]) == 0.f;
+  const bool fold = __syncthreads_and(planar) != 0;
+  const int npix_k = fold ? npix / 2 : npix;                  // pixels (pairs) along K
+  const int nstages = (npix_k + E_PB - 1) / E_PB;
+  const int ngroups = (nstages + E_GROUP - 1) / E_GROUP;
+
+  // fp16 has 5 exponent bits: scale P' (or the pair's sum and difference) by a power of two so that
+  // the largest component lands in [2^13, 2^14) (exact; undone in the epilogue), as in degridder_tc.cu
   {
     float amax = 0.f;
-    for (int q = tid; q < npix; q += E_THREADS) {
+    for (int q = tid; q < npix_k; q += E_THREADS) {
       float2 px[NR_POL];
       pixel_after_aterms8(a, sub, plane, at1, at2, q, px);
+      if (fold) {
+        float2 py[NR_POL];
+        pixel_after_aterms8(a, sub, plane, at1, at2, npix - 1 - q, py);
 #pragma unroll
-      for (int p = 0; p < NR_POL; p++) amax = fmaxf(amax, fmaxf(fabsf(px[p].x), fabsf(px[p].y)));
+        for (int p = 0; p < NR_POL; p++) {
+          amax = fmaxf(amax, fmaxf(fabsf(px[p].x + py[p].x), fabsf(px[p].y + py[p].y)));
+          amax = fmaxf(amax, fmaxf(fabsf(px[p].x - py[p].x), fabsf(px[p].y - py[p].y)));
+        }
+      } else {
+#pragma unroll
+        for (int p = 0; p < NR_POL; p++) amax = fmaxf(amax, fmaxf(fabsf(px[p].x), fabsf(px[p].y)));
+      }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
@@ -261,10 +286,12 @@ degridder_tc8_kernel(const KernelArgs a, const int recur) {
             if (elect_one()) {
               const unsigned long long db = db0 + (unsigned long long)(slot * (E_B_SLOT >> 4));
               const unsigned acc = (g > 0 || st > 0) ? 1u : 0u;
+              if (!(IDGB200_ABLATE & 1)) {
               umma_f16(tmem_d, da0, db, idesc, acc);                                              // tile 0, hi
               umma_f16(tmem_d, da0 + (unsigned long long)(E_A_BUF >> 4), db, idesc, 1u);          // tile 0, lo
               umma_f16(tmem_d + 16, da0 + (unsigned long long)(2 * E_A_BUF >> 4), db, idesc, acc);   // tile 1, hi
               umma_f16(tmem_d + 16, da0 + (unsigned long long)(3 * E_A_BUF >> 4), db, idesc, 1u);    // tile 1, lo
+              }
               umma_commit_u(my_empty_u);
               if (st == nst - 1) umma_commit_u(bempty_u + grp * 8);
               if (st == nst - 1 && g == ngroups - 1) umma_commit_u(done_u);
@@ -330,8 +357,18 @@ degridder_tc8_kernel(const KernelArgs a, const int recur) {
         const int q = g * (E_GROUP * E_PB) + lane;
         float2 px[NR_POL];
         float4 geo = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (q < npix) {
+        float2 pd[NR_POL] = {};   // the pair's difference (multiplies sin) when the subgrid is folded
+        if (q < npix_k) {
           pixel_after_aterms8(a, sub, plane, at1, at2, q, px);
+          if (fold) {
+            float2 py[NR_POL];
+            pixel_after_aterms8(a, sub, plane, at1, at2, npix - 1 - q, py);
+#pragma unroll
+            for (int pp = 0; pp < NR_POL; pp++) {
+              pd[pp] = make_float2(__fsub_rn(px[pp].x, py[pp].x), __fsub_rn(px[pp].y, py[pp].y));
+              px[pp] = make_float2(__fadd_rn(px[pp].x, py[pp].x), __fadd_rn(px[pp].y, py[pp].y));
+            }
+          }
           const int y = q / N, x = q - y * N;
           const float l = compute_l(x, N, a.image_size);
           const float m = compute_l(y, N, a.image_size);
@@ -348,6 +385,10 @@ degridder_tc8_kernel(const KernelArgs a, const int recur) {
         for (int pp = 0; pp < NR_POL; pp++) {
           scratch[lane * 8 + 2 * pp] = px[pp].x * pix_scale;
           scratch[lane * 8 + 2 * pp + 1] = px[pp].y * pix_scale;
+          if (fold) {
+            scratch[256 + lane * 8 + 2 * pp] = pd[pp].x * pix_scale;
+            scratch[256 + lane * 8 + 2 * pp + 1] = pd[pp].y * pix_scale;
+          }
         }
         __syncwarp();
 #pragma unroll
@@ -356,8 +397,9 @@ degridder_tc8_kernel(const KernelArgs a, const int recur) {
 #pragma unroll
           for (int i = 0; i < 4; i++) {
             const float2 vv = *reinterpret_cast<const float2 *>(&scratch[(st * E_PB + kc * 4 + i) * 8 + 2 * p]);
+            const float2 vd = fold ? *reinterpret_cast<const float2 *>(&scratch[256 + (st * E_PB + kc * 4 + i) * 8 + 2 * p]) : vv;
             const float x0 = im ? vv.y : vv.x;    // multiplies cos
-            const float x1 = im ? vv.x : -vv.y;   // multiplies sin
+            const float x1 = im ? vd.x : -vd.y;   // multiplies sin
             __half h0 = __float2half_rn(x0), h1 = __float2half_rn(x1);
             if (lo) {
               h0 = __float2half_rn(x0 - __half2float(h0));
@@ -383,15 +425,16 @@ degridder_tc8_kernel(const KernelArgs a, const int recur) {
 }  // namespace
 
 // nr_channels must be a multiple of 8; recur: octs of equally spaced channels get their phasors by recurrence
-cudaError_t launch_degridder_tc8(const KernelArgs &a, bool recur, cudaStream_t stream) {
+// fold: planar subgrids (checked per subgrid on the device) sum over half the pixels, see the kernel
+cudaError_t launch_degridder_tc8(const KernelArgs &a, bool recur, bool fold, cudaStream_t stream) {
   if (a.nr_subgrids == 0) return cudaSuccess;
   if (a.nr_channels & 7) return cudaErrorInvalidValue;
-  const size_t smem = (size_t)E_PAIRS * E_A_WARP + E_NG * E_GROUP * (E_B_SLOT + E_G_SLOT) + 32 * 8 * 4 +
+  const size_t smem = (size_t)E_PAIRS * E_A_WARP + E_NG * E_GROUP * (E_B_SLOT + E_G_SLOT) + 2 * 32 * 8 * 4 +
                       (E_PAIRS + 2 * E_NG + 1) * 8 + 8 + 48;
   auto k = degridder_tc8_kernel;
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  k<<<dim3((unsigned)a.nr_subgrids), dim3(E_THREADS), smem, stream>>>(a, recur ? 1 : 0);
+  k<<<dim3((unsigned)a.nr_subgrids), dim3(E_THREADS), smem, stream>>>(a, recur ? 1 : 0, fold ? 1 : 0);
   return cudaGetLastError();
 }
 

@@ -123,6 +123,7 @@ __device__ __forceinline__ void tc_produce_linear(unsigned char *A, const float 
       prev = cur;
       cur = nxt;
     }
+    if ((IDGB200_ABLATE & 2) && !ablate_never()) continue;
     *reinterpret_cast<uint4 *>(A + (lane + 32 * j) * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
     *reinterpret_cast<uint4 *>(A + A_CHUNK_BYTES + (lane + 32 * j) * 16) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
     if (SPLIT) {
@@ -294,8 +295,10 @@ gridder_tc_kernel(const KernelArgs a, const int slabs, const int tiles_per_cta, 
             __syncwarp();
             if (elect_one()) {
               const unsigned long long db = db0 + (unsigned long long)(slot2 * (T2_B_SLOT >> 4));
+              if (!(IDGB200_ABLATE & 1)) {
               umma_f16(tmem_d, da0, db, idesc, k > 0 ? 1u : 0u);
               umma_f16(tmem_d, da0 + (unsigned long long)(T2_A_STAGE >> 4), db + (unsigned long long)(T2_B_SLOT >> 4), idesc, 1u);
+              }
               umma_commit_u(my_empty_u);
               if ((slot2 & 7u) == 6u) umma_commit_u(bempty_u + (slot2 >> 3) * 8);   // half ring consumed
               if (k == last_k) umma_commit_u(done_u);

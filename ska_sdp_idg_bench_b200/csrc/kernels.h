@@ -46,7 +46,7 @@ cudaError_t launch_gridder_tc8(const KernelArgs &a, const int *d_regular_flag, c
 cudaError_t launch_gridder_tc4(const KernelArgs &a, const int *d_regular_flag, cudaStream_t stream);
 cudaError_t launch_degridder_tc(const KernelArgs &a, int poly, bool recur, cudaStream_t stream);
 // two M-tiles per warp, groups of 8 channels (degridder_tc8.cu); nr_channels % 8 == 0
-cudaError_t launch_degridder_tc8(const KernelArgs &a, bool recur, cudaStream_t stream);
+cudaError_t launch_degridder_tc8(const KernelArgs &a, bool recur, bool fold, cudaStream_t stream);
 // phasor operand written to TMEM from registers (gridder_tc3.cu)
 cudaError_t launch_gridder_tc3(const KernelArgs &a, int mode, cudaStream_t stream);
 

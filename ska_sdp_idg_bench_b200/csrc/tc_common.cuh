@@ -13,6 +13,18 @@ constexpr int B_CHUNK_BYTES = 16 * 16;
 
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 
+// Ablation builds (tools/ablate.py, never the shipped library): bit 0 = do not issue the stage's MMAs,
+// bit 1 = the phasor operand's stores are predicated off at run time (ablate_never() is false, but only
+// the hardware knows: the instructions still issue, nothing reaches the shared-memory pipe).
+#ifndef IDGB200_ABLATE
+#define IDGB200_ABLATE 0
+#endif
+__device__ __forceinline__ bool ablate_never() {
+  unsigned n;
+  asm volatile("mov.u32 %0, %%nctaid.z;" : "=r"(n));
+  return n == 12345u;
+}
+
 constexpr unsigned MBAR_SUSPEND_HINT = 0x989680u;   // upper bound of one try_wait's sleep (what CUTLASS passes)
 
 __device__ __forceinline__ void mbar_init(unsigned long long *bar, int count) {

@@ -267,6 +267,46 @@ def test_equally_spaced_channels_take_the_recurrence_paths(shape):
     assert (mx < 5e-5).all(), mx
 
 
+@pytest.mark.parametrize("shape", [
+    dict(subgrid_size=32, nr_channels=16, max_timesteps=128, nr_subgrids=4),   # the bench shape
+    dict(subgrid_size=24, nr_channels=8, max_timesteps=37, nr_subgrids=5),     # 288 pixel pairs: 9 ring groups
+    dict(subgrid_size=64, nr_channels=16, max_timesteps=20, nr_subgrids=2, nr_stations=6, nr_slots=3),
+    dict(subgrid_size=18, nr_channels=8, max_timesteps=9, nr_subgrids=3),      # 162 pairs: a partial last stage
+])
+@pytest.mark.parametrize("linear", [True, False])
+def test_planar_subgrids_fold_onto_half_the_pixels(shape, linear):
+    """degridder_tc8.cu: a subgrid whose timesteps all have w = 0 (and no w offset) - what the reference's
+    init.cpp generates - is summed over pixel PAIRS (q, npix - 1 - q), whose phasors are conjugates bit for
+    bit: same result as the full sum (variant 28) up to the rounding of the pair's sum and difference,
+    same parity with the oracle; a single timestep with w != 0 sends its subgrid back to the full sum."""
+    o = oracle()
+    p = random_problem(78, with_w=False, **shape)
+    assert not p.uvw[:, 2].any() and p.w_step == 0.0
+    if linear:
+        p.wavenumbers[:] = (2.9 + 0.0147 * np.arange(p.nr_channels)).astype(np.float32)
+    ref = o.degridder(p)
+    rows = covered_rows(p)
+    folded, full = run_degridder(p, idg.SINCOS_FAST, 24), run_degridder(p, idg.SINCOS_FAST, 28)
+    assert_close(folded[rows], ref[rows], 2, idg.SINCOS_FAST, f"degridder folded {shape}")
+    assert_close(full[rows], ref[rows], 2, idg.SINCOS_FAST, f"degridder full sum {shape}")
+    assert not folded[~rows].any()
+    assert not np.array_equal(folded, full), "variant 24 did not take the folded path"
+    mx, _ = per_pol_errors(folded[rows], full[rows], 2)
+    assert (mx < 2e-5).all(), mx
+    # one timestep off the plane: that subgrid (and only that one) must take the full sum
+    s = int(np.argmax(p.metadata["nr_timesteps"]))
+    t0 = int(p.metadata[s]["time_offset"])
+    nt = int(p.metadata[s]["nr_timesteps"])
+    p.uvw[t0 + nt // 2, 2] = 3.5
+    ref2 = o.degridder(p)
+    folded2, full2 = run_degridder(p, idg.SINCOS_FAST, 24), run_degridder(p, idg.SINCOS_FAST, 28)
+    assert_close(folded2[rows], ref2[rows], 2, idg.SINCOS_FAST, f"degridder mixed {shape}")
+    assert np.array_equal(folded2[t0:t0 + nt], full2[t0:t0 + nt])
+    others = rows.copy()
+    others[t0:t0 + nt] = False
+    assert np.array_equal(folded2[others], folded[others])
+
+
 def test_channel_rotation_is_checked_per_block():
     """The default FAST kernels step through equally spaced channels by complex rotation
     (DESIGN.md 4.5); the spacing is tested per block of 8 (gridder) / quad of 4 (degridder)
