@@ -398,7 +398,10 @@ int resolve_gridder_variant(int subgrid_size, int nr_channels, int sincos_mode, 
   if (!tc) return 10;
   // K = 32 stages when the channel blocks pair up.  (26, two tiles per warp for regular channel layouts,
   // measured the same 12.86 ms as 24 plus two small launches: opt-in)
-  return ncb % 2 == 0 ? 24 : 21;
+  // 29: planar subgrids (w = 0) folded onto pixel pairs where the launch qualifies (decided on the device),
+  // else 24 behind it (gridder_fold.cu)
+  if (ncb % 2 == 0) return (nr_channels % 16 == 0 && subgrid_size % 2 == 0) ? 29 : 24;
+  return 21;
 }
 
 cudaError_t launch_gridder(const KernelArgs &a, int sincos_mode, int variant, cudaStream_t stream) {
@@ -425,6 +428,17 @@ cudaError_t launch_gridder(const KernelArgs &a, int sincos_mode, int variant, cu
       if (!flag) return cudaErrorMemoryAllocation;
       cudaError_t e = launch_gridder_regular_check(a, flag, stream);
       if (e == cudaSuccess) e = variant == 26 ? launch_gridder_tc8(a, flag, stream) : launch_gridder_tc4(a, flag, stream);
+      if (e == cudaSuccess) e = launch_gridder_tc(a, 11, true, stream, flag);
+      return e;
+    }
+    case 29: {   // gridder_fold.cu where the channel layout is regular and every subgrid planar, else 24
+      if (sincos_mode != IDGB200_SINCOS_FAST) return cudaErrorInvalidValue;
+      if ((a.nr_channels & 15) || (a.subgrid_size & 1) || a.nr_channels > 1024) return launch_gridder_tc(a, 11, true, stream);
+      int *flag = regular_flag_slot();
+      if (!flag) return cudaErrorMemoryAllocation;
+      cudaError_t e = launch_gridder_regular_check(a, flag, stream);
+      if (e == cudaSuccess) e = launch_gridder_planar_check(a, flag, stream);
+      if (e == cudaSuccess) e = launch_gridder_fold(a, flag, stream);
       if (e == cudaSuccess) e = launch_gridder_tc(a, 11, true, stream, flag);
       return e;
     }

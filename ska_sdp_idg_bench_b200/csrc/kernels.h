@@ -44,6 +44,10 @@ cudaError_t launch_gridder_regular_check(const KernelArgs &a, int *d_flag, cudaS
 cudaError_t launch_gridder_tc8(const KernelArgs &a, const int *d_regular_flag, cudaStream_t stream);
 // phasor operand in TMEM, four tiles per group of four warps (gridder_tc4.cu); regular layouts only, same gate
 cudaError_t launch_gridder_tc4(const KernelArgs &a, const int *d_regular_flag, cudaStream_t stream);
+// planar subgrids folded onto mirror-image pixel pairs (gridder_fold.cu): the planar check clears *d_flag (which
+// holds the regular-channel verdict) when a subgrid of the launch is off the plane; the kernel is a no-op unless set
+cudaError_t launch_gridder_planar_check(const KernelArgs &a, int *d_flag, cudaStream_t stream);
+cudaError_t launch_gridder_fold(const KernelArgs &a, const int *d_fold_flag, cudaStream_t stream);
 cudaError_t launch_degridder_tc(const KernelArgs &a, int poly, bool recur, cudaStream_t stream);
 // two M-tiles per warp, groups of 8 channels (degridder_tc8.cu); nr_channels % 8 == 0
 cudaError_t launch_degridder_tc8(const KernelArgs &a, bool recur, bool fold, cudaStream_t stream);

@@ -307,6 +307,50 @@ def test_planar_subgrids_fold_onto_half_the_pixels(shape, linear):
     assert np.array_equal(folded2[others], folded[others])
 
 
+@pytest.mark.parametrize("shape", [
+    dict(subgrid_size=32, nr_channels=16, max_timesteps=128, nr_subgrids=4),   # the bench shape: 4 tiles of pairs
+    dict(subgrid_size=24, nr_channels=16, max_timesteps=37, nr_subgrids=5),    # 288 pairs: a partial third tile
+    dict(subgrid_size=64, nr_channels=32, max_timesteps=20, nr_subgrids=2, nr_stations=6, nr_slots=3),  # 4 slabs
+    dict(subgrid_size=18, nr_channels=16, max_timesteps=9, nr_subgrids=3),     # 162 pairs, two tiles
+])
+def test_planar_launches_grid_pixel_pairs(shape):
+    """gridder_fold.cu: when every subgrid of a launch is planar (w = 0, no w offset) and the channels are
+    regular, the default FAST gridder makes one phasor row per pixel PAIR (q, npix - 1 - q) and recombines
+    E +- i F in the epilogue: same parity with the oracle as the full kernel (variant 24) and the same
+    result up to accumulation order; one timestep off the plane, or irregular channels, and the launch
+    takes variant 24 bit for bit."""
+    o = oracle()
+    p = random_problem(79, with_w=False, **shape)
+    # one spacing for every 8-channel block, bit for bit (exact in fp32), as the regular-case gate asks
+    p.wavenumbers[:] = (2.5 + 0.015625 * np.arange(p.nr_channels)).astype(np.float32)
+    assert idg.resolve_variant(p.subgrid_size, p.nr_channels, idg.SINCOS_FAST, 0, gridder=True) == 29
+    ref = o.gridder(p)
+    folded, full = run_gridder(p, idg.SINCOS_FAST), run_gridder(p, idg.SINCOS_FAST, 24)
+    assert_close(folded, ref, 1, idg.SINCOS_FAST, f"gridder folded {shape}")
+    assert_close(full, ref, 1, idg.SINCOS_FAST, f"gridder full {shape}")
+    assert not np.array_equal(folded, full), "the default did not take the folded path"
+    mx, _ = per_pol_errors(folded, full, 1)
+    assert (mx < 2e-5).all(), mx
+    # FFT-shifted store through the folded epilogue
+    out = np.full_like(p.subgrids, np.nan)
+    idg.c_run_gridder(p.nr_subgrids, p.grid_size, p.subgrid_size, p.image_size, p.w_step, p.nr_channels,
+                      p.nr_stations, p.uvw, p.wavenumbers, p.visibilities, p.spheroidal, p.aterms, p.metadata,
+                      out, sincos=idg.SINCOS_FAST, flags=idg.FLAG_FFT_SHIFT)
+    h = p.subgrid_size // 2
+    assert np.array_equal(np.roll(out, (-h, -h), axis=(2, 3)), folded)
+    # one timestep off the plane: the whole launch takes the full kernel
+    s = int(np.argmax(p.metadata["nr_timesteps"]))
+    t = int(p.metadata[s]["time_offset"]) + int(p.metadata[s]["nr_timesteps"]) // 2
+    w_saved = p.uvw[t, 2]
+    p.uvw[t, 2] = 3.5
+    assert np.array_equal(run_gridder(p, idg.SINCOS_FAST), run_gridder(p, idg.SINCOS_FAST, 24))
+    assert_close(run_gridder(p, idg.SINCOS_FAST), o.gridder(p), 1, idg.SINCOS_FAST, f"gridder off-plane {shape}")
+    p.uvw[t, 2] = w_saved
+    # irregular channels likewise
+    p.wavenumbers[3] += 1e-3
+    assert np.array_equal(run_gridder(p, idg.SINCOS_FAST), run_gridder(p, idg.SINCOS_FAST, 24))
+
+
 def test_channel_rotation_is_checked_per_block():
     """The default FAST kernels step through equally spaced channels by complex rotation
     (DESIGN.md 4.5); the spacing is tested per block of 8 (gridder) / quad of 4 (degridder)

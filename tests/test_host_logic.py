@@ -103,8 +103,9 @@ def test_argument_validation():
 def test_default_variant_selection():
     """variant 0: tcgen05 gridder only for FAST sincos and shapes that fill its 8-channel /
     128-pixel tiles; tcgen05 degridder (fp16 hi + lo phasors) likewise."""
-    assert idg.resolve_variant(32, 16, idg.SINCOS_FAST) == 24
-    assert idg.resolve_variant(24, 16, idg.SINCOS_FAST) == 24
+    assert idg.resolve_variant(32, 16, idg.SINCOS_FAST) == 29    # folded kernel behind its device-side gate, else 24
+    assert idg.resolve_variant(24, 16, idg.SINCOS_FAST) == 29
+    assert idg.resolve_variant(32, 12, idg.SINCOS_FAST) == 24    # two blocks, the second one partial: no folding
     assert idg.resolve_variant(32, 24, idg.SINCOS_FAST) == 21    # 3 blocks of 8 channels
     assert idg.resolve_variant(32, 16, idg.SINCOS_ACCURATE) == 10
     assert idg.resolve_variant(32, 16, idg.SINCOS_REDUCED) == 10
