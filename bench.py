@@ -53,13 +53,18 @@ TC_GRIDDER = {11: (2.0, 10.1, None), 12: (1.5, 12.6, None), 13: (1.375, 12.9, No
               24: (0.382, 6.91, 4.19), 26: (0.382, 6.91, 4.19)}
 TC_DEGRIDDER = {11: (2.0, 11.5, None), 12: (1.5, 13.5, None), 13: (1.25, 13.2, None), 14: (1.0, 15.5, None),
                 21: (1.0, 10.5, None), 22: (1.006, 14.63, 10.0), 23: (2.0, 18.5, None),
-                24: (0.505, 11.95, 8.25)}
+                24: (0.505, 11.95, 8.25), 28: (0.505, 11.95, 8.25)}
+# planar launches (pixel-pair folding): per NOMINAL (pixel, visibility) item, i.e. half the general path's
+# figures plus the epilogue / builder share; executed counts from profiles/r01_fold_ncu_full.txt
+# (2.79 / 5.02 warp instructions per nominal warp-item; the packed share taken from the general path's captures)
+TC_GRIDDER[29] = (0.191, 3.30, 2.10)
+TC_DEGRIDDER_FOLDED = (0.253, 5.52, 4.13)
 
 
 # tcgen05.mma instructions (M=128, N=16, K=16, both operands in shared memory) per (pixel, visibility) item:
 # one MMA covers 128 rows x 8 K-pairs = 1024 items; the hi + lo phasor kernels issue two per block.
-TC_MMA_PER_ITEM = {"gridder": {21: 1 / 1024, 24: 1 / 1024, 26: 1 / 1024, 22: 2 / 1024, 23: 2 / 1024},
-                   "degridder": {21: 1 / 1024, 22: 2 / 1024, 23: 2 / 1024, 24: 2 / 1024, 25: 2 / 1024}}
+TC_MMA_PER_ITEM = {"gridder": {21: 1 / 1024, 24: 1 / 1024, 26: 1 / 1024, 22: 2 / 1024, 23: 2 / 1024, 29: 0.5 / 1024},
+                   "degridder": {21: 1 / 1024, 22: 2 / 1024, 23: 2 / 1024, 24: 2 / 1024, 25: 2 / 1024, 28: 2 / 1024}}
 # measured on the B200 (tools/smem_mix.cu, profiles/r01_smem_mix_microbench.log): tcgen05.mma of that shape take
 # 40.0 clocks each on an SM when the pipe stays fed (256 between two commits; 51-55 with a drain every 16) - the
 # 4 KB A tile is fetched from shared memory at ~100 B/clk, 5x the 8 clocks of its math - and concurrent STS.128
@@ -393,6 +398,17 @@ def run_ours(args) -> None:
     sec_g, launches_g = timed(step_gridder, args.steps, args.warmup)
     sec_d, launches_d = timed(step_degridder, args.steps, args.warmup)
     # the FP32/SFU gridder next to the tensor-core one (north_star: tensor cores only if they win)
+    # The synthetic observation is the reference's own (init.cpp:4-25): every w is 0, so the default kernels
+    # take their planar paths (mirror-image pixel pairs share one phasor row: gridder_fold.cu, degridder_tc8.cu).
+    # The same kernels' general path (any w) is timed beside them on the same data: variants 24 / 28.
+    planar = not bool(prob["uvw"][:, 2].any().item())
+    sec_gw = sec_dw = None
+    if planar and g_variant == 29:
+        sec_gw = timed(lambda: idg.gridder(*scal, *tens, sincos=sincos, variant=24), args.steps, args.warmup)[0]
+    if planar and d_variant == 24:
+        sec_dw = timed(lambda: idg.degridder(*scal, prob["uvw"], prob["wavenumbers"], vis_out, prob["spheroidal"],
+                                             prob["aterms"], prob["metadata"], sub_in, sincos=sincos, variant=28),
+                       args.steps, args.warmup)[0]
     sec_g32 = timed(step_gridder_fp32, args.steps, args.warmup)[0] if g_variant in TC_GRIDDER else None
     sec_d32 = timed(step_degridder_fp32, args.steps, args.warmup)[0] if d_variant in TC_DEGRIDDER else None
     step_gridder()   # leave the default kernels' results in prob["subgrids"] / vis_out for the parity sample
@@ -621,7 +637,21 @@ def run_ours(args) -> None:
             return r
 
         tc_g, tc_d = TC_GRIDDER.get(g_variant), TC_DEGRIDDER.get(d_variant)
+        mma_g, mma_d = TC_MMA_PER_ITEM["gridder"].get(g_variant), TC_MMA_PER_ITEM["degridder"].get(d_variant)
+        if planar and d_variant == 24:
+            tc_d, mma_d = TC_DEGRIDDER_FOLDED, mma_d / 2
+        if g_variant == 29 and not planar:
+            tc_g, mma_g = TC_GRIDDER[24], TC_MMA_PER_ITEM["gridder"][24]
         total_mvis = world * shape["mvis"]
+
+        def general_w(sec, variant, tc, mma, traffic):
+            if sec is None:
+                return None
+            return {"value": total_mvis * args.steps / sec, "unit": "MVis/s", "variant": variant,
+                    "ms_per_step": sec / args.steps * 1e3, "tflops": world * flops * args.steps / sec * 1e-12,
+                    "what": "the same launch through the kernel's general path (any w: no pixel-pair folding), "
+                            "which is what a subgrid with a single w != 0 takes",
+                    "roofline": roof(sec, args.steps, traffic, tc, mma)}
         out = {
             "metric": "gridder_mvis_per_s", "value": total_mvis * args.steps / sec_g,
             "unit": "MVis/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -636,25 +666,34 @@ def run_ours(args) -> None:
                                            "TMEM" + ("; phasors of equally spaced channels from the first channel of each "
                                                      "8-channel block by one rotation and the three-term recurrence (the "
                                                      "reference's gridder_v8 rotates every channel)"
-                                                     if g_variant in (21, 24, 26) else "")
+                                                     if g_variant in (21, 24, 26, 29) else "")
+                                           + ("; planar launch (every w = 0, checked on the device): one phasor row per "
+                                              "mirror-image pixel pair, N = 32 MMAs, E +- i F recombined in the epilogue "
+                                              "(gridder_fold.cu)" if g_variant == 29 and planar else "")
                                            if tc_g is not None else "FP32 FFMA2 + MUFU"),
                            degridder_kernel=(("tcgen05: fp16 hi+lo phasor tile x fp16 hi+lo pixels, f32 accumulate in "
                                               "TMEM; phasors of equally spaced channel quads by rotation"
                                               if d_variant == 22 else
                                               "tcgen05, two M-tiles per warp: fp16 hi+lo phasor tile x fp16 hi+lo pixels, f32 "
                                               "accumulate in TMEM; phasors of equally spaced groups of 8 channels by the "
-                                              "three-term recurrence" if d_variant == 24 else "tcgen05, opt-in variant")
+                                              "three-term recurrence" + ("; planar subgrids (every w = 0, checked per "
+                                              "subgrid): summed over mirror-image pixel pairs, half the K dimension"
+                                              if planar else "") if d_variant == 24 else "tcgen05, opt-in variant")
                                              if tc_d is not None else "FP32 FFMA2 + MUFU")),
             "tflops": world * flops * args.steps / sec_g * 1e-12,
             # ncu --set full, 3675-subgrid launches: 343.1 MB (tcgen05 gridder), 314.7 MB (tcgen05 degridder), FP32 kernels from the
             # 1740-subgrid captures (profiles/)
-            "roofline": roof(sec_g, args.steps, 343.1e6 / 3675 if tc_g is not None else 145.165e6 / 1740, tc_g,
-                             TC_MMA_PER_ITEM["gridder"].get(g_variant)),
+            "roofline": roof(sec_g, args.steps, (339.1e6 if g_variant == 29 and planar else 343.1e6) / 3675 if tc_g is not None else 145.165e6 / 1740,
+                             tc_g, mma_g),
+            "planar": planar,
+            "gridder_general_w": general_w(sec_gw, 24, TC_GRIDDER[24], TC_MMA_PER_ITEM["gridder"][24], 343.1e6 / 3675),
             "degridder": {"value": total_mvis * args.steps / sec_d, "unit": "MVis/s",
                           "ms_per_step": sec_d / args.steps * 1e3,
                           "tflops": world * flops * args.steps / sec_d * 1e-12,
                           "roofline": roof(sec_d, args.steps, 314.7e6 / 3675 if tc_d is not None
-                                           else 128.329e6 / 1740, tc_d, TC_MMA_PER_ITEM["degridder"].get(d_variant))},
+                                           else 128.329e6 / 1740, tc_d, mma_d)},
+            "degridder_general_w": general_w(sec_dw, 28, TC_DEGRIDDER[24], TC_MMA_PER_ITEM["degridder"][24],
+                                             314.7e6 / 3675),
             "gridder_fp32": None if sec_g32 is None else {
                 "value": total_mvis * args.steps / sec_g32, "unit": "MVis/s", "variant": 10,
                 "ms_per_step": sec_g32 / args.steps * 1e3,

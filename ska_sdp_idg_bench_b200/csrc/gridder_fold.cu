@@ -43,14 +43,15 @@ constexpr int F_B_SLOT = 2 * F_B_CHUNK;          // 1 KB per channel block
 constexpr int F_NB = 16;                         // B ring slots
 constexpr int F_THREADS = (F_TILES + 1) * 32;
 
-// every subgrid of the launch planar?  (one thread per subgrid clears the flag otherwise)
+// every subgrid of the launch planar?  (one warp per subgrid, its lanes stride over the timesteps, so the
+// check is a handful of independent loads deep; a subgrid off the plane clears the flag)
 __global__ void gridder_planar_check_kernel(const KernelArgs a, int *flag) {
-  const int s_local = blockIdx.x * blockDim.x + threadIdx.x;
+  const int s_local = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (s_local >= a.nr_subgrids) return;
   const SubgridCtx ctx = load_ctx(a, a.subgrid_offset + s_local);
   bool planar = ctx.w_offset == 0.f && !(a.subgrid_size & 1);
   const float *g_uvw = reinterpret_cast<const float *>(a.uvw) + (size_t)ctx.time_offset * 3;
-  for (int t = 0; t < ctx.nr_timesteps && planar; t++) planar = __ldg(&g_uvw[3 * t + 2]) == 0.f;
+  for (int t = lane; t < ctx.nr_timesteps; t += 32) planar = planar && __ldg(&g_uvw[3 * t + 2]) == 0.f;
   if (!planar) *flag = 0;
 }
 
@@ -329,7 +330,7 @@ gridder_fold_kernel(const KernelArgs a, const int slabs, const int *__restrict__
 // a subgrid of the launch is off the plane or the subgrid size is odd
 cudaError_t launch_gridder_planar_check(const KernelArgs &a, int *d_flag, cudaStream_t stream) {
   if (a.nr_subgrids == 0) return cudaSuccess;
-  gridder_planar_check_kernel<<<(a.nr_subgrids + 127) / 128, 128, 0, stream>>>(a, d_flag);
+  gridder_planar_check_kernel<<<(a.nr_subgrids + 3) / 4, 128, 0, stream>>>(a, d_flag);
   return cudaGetLastError();
 }
 
