@@ -25,10 +25,17 @@ for case in range(n_cases):
     T = int(rng.integers(1, 70))
     S = int(rng.integers(1, 6))
     linear = bool(rng.integers(0, 2))
+    planar = bool(rng.integers(0, 2))     # w = 0 everywhere: the pixel-pair folded paths
     p = random_problem(int(rng.integers(1 << 30)), subgrid_size=N, nr_channels=C, max_timesteps=T, nr_subgrids=S,
-                       nr_stations=int(rng.integers(2, 7)), nr_slots=int(rng.integers(1, 4)))
+                       nr_stations=int(rng.integers(2, 7)), nr_slots=int(rng.integers(1, 4)), with_w=not planar)
     if linear:
-        p.wavenumbers[:] = (2.5 + rng.uniform(0.001, 0.02) * np.arange(C)).astype(np.float32)
+        # every other case with a spacing that is exact in fp32 (one spacing for all blocks bit for bit: the
+        # regular-case gridder loops, folded or not)
+        dw = float(rng.choice([2.0 ** -6, 2.0 ** -7])) if rng.integers(0, 2) else float(rng.uniform(0.001, 0.02))
+        p.wavenumbers[:] = (2.5 + dw * np.arange(C)).astype(np.float32)
+    if planar and S > 1 and rng.integers(0, 3) == 0:   # one subgrid off the plane in an otherwise planar launch
+        s = int(np.argmax(p.metadata["nr_timesteps"]))
+        p.uvw[int(p.metadata[s]["time_offset"]), 2] = 2.5
     ref_g, ref_d = o.gridder(p), o.degridder(p)
     rows = covered_rows(p)
     for gv in (0, 22):
@@ -36,7 +43,7 @@ for case in range(n_cases):
         ok = (mx <= tmx).all() and (rms <= trms).all()
         worst = max(worst, rms.max() / trms, mx.max() / tmx)
         if not ok:
-            print("FAIL gridder", gv, dict(N=N, C=C, T=T, S=S, linear=linear), mx, rms)
+            print("FAIL gridder", gv, dict(N=N, C=C, T=T, S=S, linear=linear, planar=planar), mx, rms)
             sys.exit(1)
     if rows.any():
         for dv in (0, 23):
@@ -45,9 +52,9 @@ for case in range(n_cases):
             ok = (mx <= tmx).all() and (rms <= trms).all() and not got[~rows].any()
             worst = max(worst, rms.max() / trms, mx.max() / tmx)
             if not ok:
-                print("FAIL degridder", dv, dict(N=N, C=C, T=T, S=S, linear=linear), mx, rms)
+                print("FAIL degridder", dv, dict(N=N, C=C, T=T, S=S, linear=linear, planar=planar), mx, rms)
                 sys.exit(1)
-    print(f"case {case}: N={N} C={C} T<={T} S={S} linear={linear} gridder v{idg.resolve_variant(N, C, 0)} "
+    print(f"case {case}: N={N} C={C} T<={T} S={S} linear={linear} planar={planar} gridder v{idg.resolve_variant(N, C, 0)} "
           f"degridder v{idg.resolve_variant(N, C, 0, gridder=False)} ok, worst error / tolerance so far {worst:.3f}")
 print(f"{n_cases} cases passed; worst error / tolerance = {worst:.3f}")
 
