@@ -176,9 +176,11 @@ int idgb200_subgrid_fft(int64_t nr_subgrids, int subgrid_size, int direction,
 
 /* The kernel variant params->variant == 0 resolves to for this shape and sincos
  * mode (gridder != 0: the gridder, else the degridder); a non-zero variant is
- * returned unchanged.  Gridder: 24 / 21 = tcgen05 kernel (FAST sincos, shapes that fill
- * its tiles), 10 = FP32 kernel.  Degridder: 22 = tcgen05 kernel with fp16 hi + lo
- * phasors (FAST sincos), 4 = FP32 kernel.  IDGB200_EINVAL on bad params. */
+ * returned unchanged.  Gridder: 29 / 24 / 21 = tcgen05 kernel (FAST sincos, shapes that fill
+ * its tiles; 29 = 24 with planar launches - every w = 0, checked on the device - gridded
+ * per mirror-image pixel pair), 10 = FP32 kernel.  Degridder: 24 / 22 = tcgen05 kernel with
+ * fp16 hi + lo phasors (FAST sincos; 24 sums planar subgrids over pixel pairs, 28 = 24
+ * without that), 4 = FP32 kernel.  IDGB200_EINVAL on bad params. */
 int idgb200_resolve_variant(const idgb200_params *params, int gridder);
 
 /* ---- host-pointer API --------------------------------------------------------

@@ -99,6 +99,37 @@ def test_argument_validation():
     assert e.value.code == -1
 
 
+def test_mirror_pixels_have_exactly_negated_direction_cosines():
+    """What the planar paths of gridder_fold.cu / degridder_tc8.cu rest on: with the
+    reference's formula l = float((x + 0.5 - N/2) * image_size / N) (math.hpp:9-12, double intermediate,
+    integer N/2) pixel x and its mirror image N-1-x have exactly negated l for EVEN N - and not for odd N,
+    which is why odd subgrid sizes never fold - and the fp32 phase chain of gridder_reference.cpp:61-69
+    with w = 0 is odd in (l, m), so the mirrored pixel's phase is the exact negative."""
+    def compute_l(x, N, image_size):
+        return np.float32((x + 0.5 - (N // 2)) * float(np.float32(image_size)) / N)
+
+    rng = np.random.default_rng(5)
+    for N in (8, 18, 24, 32, 48, 64):
+        l = np.array([compute_l(x, N, 0.01) for x in range(N)], np.float32)
+        assert np.array_equal(l, -l[::-1])
+        # phase_index = fma(u, l, v * m), phase = fma(-phase_index, k, offset) in fp32 with one rounding per
+        # operation (emulated through float64, which holds a product of two floats exactly)
+        u, v, uo, vo, k = (np.float32(t) for t in rng.uniform(-900, 900, 5))
+
+        def phase(lx, my):
+            vm = np.float32(np.float64(v) * np.float64(my))
+            idx = np.float32(np.float64(u) * np.float64(lx) + np.float64(vm))
+            vom = np.float32(np.float64(vo) * np.float64(my))
+            off = np.float32(np.float64(uo) * np.float64(lx) + np.float64(vom))
+            return np.float32(-np.float64(idx) * np.float64(k) + np.float64(off))
+
+        for x in range(N):
+            for y in (0, N // 3, N - 1):
+                assert phase(l[x], l[y]) == -phase(l[N - 1 - x], l[N - 1 - y])
+    l = np.array([compute_l(x, 31, 0.01) for x in range(31)], np.float32)
+    assert not np.array_equal(l, -l[::-1])
+
+
 # ------------------------------------------------------------------------ sharding
 def test_default_variant_selection():
     """variant 0: tcgen05 gridder only for FAST sincos and shapes that fill its 8-channel /
