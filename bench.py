@@ -679,7 +679,7 @@ def run_ours(args) -> None:
                                                      "8-channel block by one rotation and the three-term recurrence (the "
                                                      "reference's gridder_v8 rotates every channel)"
                                                      if g_variant in (21, 24, 26, 29) else "")
-                                           + ("; planar launch (every w = 0, checked on the device): one phasor row per "
+                                           + ("; planar subgrids (every w = 0, checked per subgrid on the device): one phasor row per "
                                               "mirror-image pixel pair, N = 32 MMAs, E +- i F recombined in the epilogue "
                                               "(gridder_fold.cu)" if g_variant == 29 and planar else "")
                                            if tc_g is not None else "FP32 FFMA2 + MUFU"),

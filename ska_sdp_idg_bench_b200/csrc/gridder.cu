@@ -431,16 +431,21 @@ cudaError_t launch_gridder(const KernelArgs &a, int sincos_mode, int variant, cu
       if (e == cudaSuccess) e = launch_gridder_tc(a, 11, true, stream, flag);
       return e;
     }
-    case 29: {   // gridder_fold.cu where the channel layout is regular and every subgrid planar, else 24
+    case 29: {   // gridder_fold.cu for the planar subgrids of a regular channel layout, 24 for the others
       if (sincos_mode != IDGB200_SINCOS_FAST) return cudaErrorInvalidValue;
       if ((a.nr_channels & 15) || (a.subgrid_size & 1) || a.nr_channels > 1024) return launch_gridder_tc(a, 11, true, stream);
       int *flag = regular_flag_slot();
       if (!flag) return cudaErrorMemoryAllocation;
-      cudaError_t e = launch_gridder_regular_check(a, flag, stream);
-      if (e == cudaSuccess) e = launch_gridder_planar_check(a, flag, stream);
-      if (e == cudaSuccess) e = launch_gridder_fold(a, flag, stream);
-      if (e == cudaSuccess) e = launch_gridder_tc(a, 11, true, stream, flag);
-      return e;
+      int *lists = nullptr;   // { n_fold, n_general, fold[], general[] }, stream-ordered like the launches that use it
+      cudaError_t e = cudaMallocAsync(reinterpret_cast<void **>(&lists), sizeof(int) * (2 + 2 * (size_t)a.nr_subgrids), stream);
+      if (e != cudaSuccess) return e;
+      e = cudaMemsetAsync(lists, 0, 2 * sizeof(int), stream);
+      if (e == cudaSuccess) e = launch_gridder_regular_check(a, flag, stream);
+      if (e == cudaSuccess) e = launch_gridder_planar_check(a, flag, lists, stream);
+      if (e == cudaSuccess) e = launch_gridder_fold(a, lists, stream);
+      if (e == cudaSuccess) e = launch_gridder_tc(a, 11, true, stream, nullptr, lists);
+      const cudaError_t ef = cudaFreeAsync(lists, stream);
+      return e != cudaSuccess ? e : ef;
     }
     case 21:   // tensor-core kernel, phasors of equally spaced channel blocks by rotation (else as 12)
       return sincos_mode == IDGB200_SINCOS_FAST ? launch_gridder_tc(a, 3, true, stream) : cudaErrorInvalidValue;

@@ -21,10 +21,11 @@
 // CTA = up to 4 tiles (one producer warp each, rows lane + 32 j) + the B builder warp = 160 threads,
 // 49 KB of shared memory, 128 TMEM columns: 4 CTAs per SM.  The stage loop is gridder_tc.cu's regular
 // case (every 8-channel block equally spaced with one spacing, an even number of blocks: one stage =
-// one timestep x 16 channels, single-buffered, three-term recurrence).  The gate (one flag per launch,
-// written by two small check kernels on the same stream) is: regular channel layout AND every subgrid of
-// the launch planar AND an even subgrid size; otherwise this kernel returns at once and gridder_tc.cu
-// (variant 24) runs behind it.
+// one timestep x 16 channels, single-buffered, three-term recurrence).  The gate is per subgrid: two small
+// check kernels on the same stream sort the launch's subgrids into a fold list (regular channel layout
+// AND planar subgrid AND even subgrid size) and a general list; this kernel serves the first,
+// gridder_tc.cu (variant 24), launched behind it, the second, and the CTAs either kernel has no
+// subgrid for return after one read.
 #include <cuda_fp16.h>
 
 #include "common.cuh"
@@ -43,16 +44,25 @@ constexpr int F_B_SLOT = 2 * F_B_CHUNK;          // 1 KB per channel block
 constexpr int F_NB = 16;                         // B ring slots
 constexpr int F_THREADS = (F_TILES + 1) * 32;
 
-// every subgrid of the launch planar?  (one warp per subgrid, its lanes stride over the timesteps, so the
-// check is a handful of independent loads deep; a subgrid off the plane clears the flag)
-__global__ void gridder_planar_check_kernel(const KernelArgs a, int *flag) {
+// which subgrids of the launch fold: regular channel layout (*regular_flag, written by
+// gridder_regular_check_kernel on the same stream) and a planar subgrid.  One warp per subgrid, its lanes
+// stride over the timesteps, so the check is a handful of independent loads deep.  The verdicts are
+// compacted into two lists, lists = { n_fold, n_general, fold[nr_subgrids], general[nr_subgrids] } (counts
+// zeroed on the stream before), so that in the two kernels behind it CTA i either finds its subgrid in
+// its list or returns after one read of a count every CTA shares.
+__global__ void gridder_planar_check_kernel(const KernelArgs a, const int *__restrict__ regular_flag,
+                                            int *__restrict__ lists) {
   const int s_local = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (s_local >= a.nr_subgrids) return;
   const SubgridCtx ctx = load_ctx(a, a.subgrid_offset + s_local);
-  bool planar = ctx.w_offset == 0.f && !(a.subgrid_size & 1);
+  bool planar = *regular_flag != 0 && ctx.w_offset == 0.f && !(a.subgrid_size & 1);
   const float *g_uvw = reinterpret_cast<const float *>(a.uvw) + (size_t)ctx.time_offset * 3;
   for (int t = lane; t < ctx.nr_timesteps; t += 32) planar = planar && __ldg(&g_uvw[3 * t + 2]) == 0.f;
-  if (!planar) *flag = 0;
+  planar = __all_sync(0xffffffffu, planar);
+  if (lane == 0) {
+    const int i = atomicAdd(&lists[planar ? 0 : 1], 1);
+    lists[2 + (planar ? 0 : a.nr_subgrids) + i] = s_local;
+  }
 }
 
 // one block of 8 equally spaced channels for the 4 pixel pairs of a thread: gridder_tc.cu's
@@ -84,12 +94,13 @@ __device__ __forceinline__ void fold_produce_linear(unsigned char *A, const floa
 }
 
 __global__ void __launch_bounds__(F_THREADS, 4)
-gridder_fold_kernel(const KernelArgs a, const int slabs, const int *__restrict__ fold_flag) {
-  if (*fold_flag == 0) return;   // irregular channels or a subgrid off the plane: gridder_tc.cu runs instead
+gridder_fold_kernel(const KernelArgs a, const int slabs, const int *__restrict__ lists) {
+  const int i_cta = blockIdx.x / slabs;
+  if (i_cta >= lists[0]) return;          // the other subgrids (irregular channels, off the plane): gridder_tc.cu
+  const int s_local = lists[2 + i_cta];
   extern __shared__ __align__(1024) unsigned char smem[];
   const int N = a.subgrid_size, C = a.nr_channels, npix = N * N, npairs = npix >> 1;
-  const int s_local = blockIdx.x / slabs;
-  const int slab = blockIdx.x - s_local * slabs;
+  const int slab = blockIdx.x - i_cta * slabs;
   const int s = a.subgrid_offset + s_local;
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);     // warp-uniform for the compiler too
@@ -326,16 +337,18 @@ gridder_fold_kernel(const KernelArgs a, const int slabs, const int *__restrict__
 
 }  // namespace
 
-// *d_flag must hold the regular-channel verdict (launch_gridder_regular_check) already: this clears it when
-// a subgrid of the launch is off the plane or the subgrid size is odd
-cudaError_t launch_gridder_planar_check(const KernelArgs &a, int *d_flag, cudaStream_t stream) {
+// d_lists[2 + 2 nr_subgrids] = { n_fold, n_general, fold[], general[] }: the subgrids that fold (regular channel
+// layout, *d_regular_flag from launch_gridder_regular_check on the same stream, and a planar subgrid of even
+// size) and the others; the two counts must be zero when this runs
+cudaError_t launch_gridder_planar_check(const KernelArgs &a, const int *d_regular_flag, int *d_lists,
+                                        cudaStream_t stream) {
   if (a.nr_subgrids == 0) return cudaSuccess;
-  gridder_planar_check_kernel<<<(a.nr_subgrids + 3) / 4, 128, 0, stream>>>(a, d_flag);
+  gridder_planar_check_kernel<<<(a.nr_subgrids + 3) / 4, 128, 0, stream>>>(a, d_regular_flag, d_lists);
   return cudaGetLastError();
 }
 
-// fold_flag: see above; the kernel is a no-op when 0
-cudaError_t launch_gridder_fold(const KernelArgs &a, const int *d_fold_flag, cudaStream_t stream) {
+// serves the subgrids of the fold list; the other CTAs return at once
+cudaError_t launch_gridder_fold(const KernelArgs &a, const int *d_lists, cudaStream_t stream) {
   if (a.nr_subgrids == 0) return cudaSuccess;
   if (a.nr_channels > 1024 || (a.nr_channels & 15) || (a.subgrid_size & 1)) return cudaErrorInvalidValue;
   const int npairs = a.subgrid_size * a.subgrid_size / 2;
@@ -345,7 +358,7 @@ cudaError_t launch_gridder_fold(const KernelArgs &a, const int *d_fold_flag, cud
                       (size_t)a.nr_channels * 4;
   cudaError_t e = cudaFuncSetAttribute(gridder_fold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  gridder_fold_kernel<<<dim3((unsigned)a.nr_subgrids * slabs), dim3(F_THREADS), smem, stream>>>(a, slabs, d_fold_flag);
+  gridder_fold_kernel<<<dim3((unsigned)a.nr_subgrids * slabs), dim3(F_THREADS), smem, stream>>>(a, slabs, d_lists);
   return cudaGetLastError();
 }
 

@@ -35,19 +35,23 @@ int resolve_gridder_variant(int subgrid_size, int nr_channels, int sincos_mode, 
 int resolve_degridder_variant(int subgrid_size, int nr_channels, int sincos_mode, int variant);
 
 // tcgen05 / TMEM gridder (gridder_tc.cu); FAST sincos only
-// skip_flag (device, may be null): the kernel returns at once when *skip_flag != 0
+// skip_flag (device, may be null): the kernel returns at once when *skip_flag != 0;
+// lists (device, may be null): gridder_fold.cu's { n_fold, n_general, fold[], general[] }: the launch then
+// serves the subgrids of the general list only
 cudaError_t launch_gridder_tc(const KernelArgs &a, int poly, bool recur, cudaStream_t stream,
-                              const int *skip_flag = nullptr);
+                              const int *skip_flag = nullptr, const int *lists = nullptr);
 // two M-tiles per warp, regular channel layouts only (gridder_tc8.cu): the check writes *d_flag = 1 when every
 // 8-channel block is equally spaced with one spacing and the blocks pair up; the kernel is a no-op unless it is set
 cudaError_t launch_gridder_regular_check(const KernelArgs &a, int *d_flag, cudaStream_t stream);
 cudaError_t launch_gridder_tc8(const KernelArgs &a, const int *d_regular_flag, cudaStream_t stream);
 // phasor operand in TMEM, four tiles per group of four warps (gridder_tc4.cu); regular layouts only, same gate
 cudaError_t launch_gridder_tc4(const KernelArgs &a, const int *d_regular_flag, cudaStream_t stream);
-// planar subgrids folded onto mirror-image pixel pairs (gridder_fold.cu): the planar check clears *d_flag (which
-// holds the regular-channel verdict) when a subgrid of the launch is off the plane; the kernel is a no-op unless set
-cudaError_t launch_gridder_planar_check(const KernelArgs &a, int *d_flag, cudaStream_t stream);
-cudaError_t launch_gridder_fold(const KernelArgs &a, const int *d_fold_flag, cudaStream_t stream);
+// planar subgrids folded onto mirror-image pixel pairs (gridder_fold.cu): the planar check sorts the launch's
+// subgrids into d_lists[2 + 2 nr_subgrids] = { n_fold, n_general, fold[], general[] } (counts zeroed before; fold =
+// regular channel layout per *d_regular_flag and a planar subgrid); the kernel serves the fold list
+cudaError_t launch_gridder_planar_check(const KernelArgs &a, const int *d_regular_flag, int *d_lists,
+                                        cudaStream_t stream);
+cudaError_t launch_gridder_fold(const KernelArgs &a, const int *d_lists, cudaStream_t stream);
 cudaError_t launch_degridder_tc(const KernelArgs &a, int poly, bool recur, cudaStream_t stream);
 // two M-tiles per warp, groups of 8 channels (degridder_tc8.cu); nr_channels % 8 == 0
 cudaError_t launch_degridder_tc8(const KernelArgs &a, bool recur, bool fold, cudaStream_t stream);

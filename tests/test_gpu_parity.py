@@ -314,11 +314,11 @@ def test_planar_subgrids_fold_onto_half_the_pixels(shape, linear):
     dict(subgrid_size=18, nr_channels=16, max_timesteps=9, nr_subgrids=3),     # 162 pairs, two tiles
 ])
 def test_planar_launches_grid_pixel_pairs(shape):
-    """gridder_fold.cu: when every subgrid of a launch is planar (w = 0, no w offset) and the channels are
-    regular, the default FAST gridder makes one phasor row per pixel PAIR (q, npix - 1 - q) and recombines
+    """gridder_fold.cu: for the planar subgrids (w = 0, no w offset) of a launch with regular channels
+    the default FAST gridder makes one phasor row per pixel PAIR (q, npix - 1 - q) and recombines
     E +- i F in the epilogue: same parity with the oracle as the full kernel (variant 24) and the same
-    result up to accumulation order; one timestep off the plane, or irregular channels, and the launch
-    takes variant 24 bit for bit."""
+    result up to accumulation order; a subgrid with one timestep off the plane is served by variant 24 bit
+    for bit while the others still fold; irregular channels send the whole launch to variant 24."""
     o = oracle()
     p = random_problem(79, with_w=False, **shape)
     # one spacing for every 8-channel block, bit for bit (exact in fp32), as the regular-case gate asks
@@ -338,13 +338,16 @@ def test_planar_launches_grid_pixel_pairs(shape):
                       out, sincos=idg.SINCOS_FAST, flags=idg.FLAG_FFT_SHIFT)
     h = p.subgrid_size // 2
     assert np.array_equal(np.roll(out, (-h, -h), axis=(2, 3)), folded)
-    # one timestep off the plane: the whole launch takes the full kernel
+    # one timestep off the plane: that subgrid (and only that one) is served by the full kernel
     s = int(np.argmax(p.metadata["nr_timesteps"]))
     t = int(p.metadata[s]["time_offset"]) + int(p.metadata[s]["nr_timesteps"]) // 2
     w_saved = p.uvw[t, 2]
     p.uvw[t, 2] = 3.5
-    assert np.array_equal(run_gridder(p, idg.SINCOS_FAST), run_gridder(p, idg.SINCOS_FAST, 24))
-    assert_close(run_gridder(p, idg.SINCOS_FAST), o.gridder(p), 1, idg.SINCOS_FAST, f"gridder off-plane {shape}")
+    mixed, full2 = run_gridder(p, idg.SINCOS_FAST), run_gridder(p, idg.SINCOS_FAST, 24)
+    assert_close(mixed, o.gridder(p), 1, idg.SINCOS_FAST, f"gridder off-plane {shape}")
+    assert np.array_equal(mixed[s], full2[s])
+    others = np.arange(p.nr_subgrids) != s
+    assert np.array_equal(mixed[others], folded[others])
     p.uvw[t, 2] = w_saved
     # irregular channels likewise
     p.wavenumbers[3] += 1e-3
