@@ -387,6 +387,30 @@ static int *regular_flag_slot() {
   return ring[dev] + (next.fetch_add(1) % kSlots);
 }
 
+// The fold / general subgrid lists of a variant-29 launch (gridder_fold.cu): 2 + 2 nr_subgrids ints out of a
+// per-device ring of 32 buffers that grow on demand (cudaFree waits for the device, so a buffer is never
+// pulled from under a running kernel).  Launches on one stream are ordered, so a buffer can only be
+// reused too early if 32 such launches were in flight at once on different streams.
+static int *subgrid_lists_slot(size_t count_ints) {
+  static std::mutex mu;
+  struct Buf { int *p; size_t cap; };
+  static Buf ring[64][32] = {};
+  static unsigned next[64] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  std::lock_guard<std::mutex> lock(mu);
+  Buf &b = ring[dev][next[dev]++ % 32];
+  if (b.cap < count_ints) {
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr;
+    b.cap = 0;
+    const size_t cap = count_ints < (1u << 16) ? (1u << 16) : count_ints + count_ints / 2;
+    if (cudaMalloc(&b.p, cap * sizeof(int)) != cudaSuccess) return nullptr;
+    b.cap = cap;
+  }
+  return b.p;
+}
+
 int resolve_gridder_variant(int subgrid_size, int nr_channels, int sincos_mode, int variant) {
   if (variant != 0) return variant;
   // the tensor kernel pads the channels to blocks of 8 (K = 16) and the pixels to tiles of 128
@@ -436,16 +460,13 @@ cudaError_t launch_gridder(const KernelArgs &a, int sincos_mode, int variant, cu
       if ((a.nr_channels & 15) || (a.subgrid_size & 1) || a.nr_channels > 1024) return launch_gridder_tc(a, 11, true, stream);
       int *flag = regular_flag_slot();
       if (!flag) return cudaErrorMemoryAllocation;
-      int *lists = nullptr;   // { n_fold, n_general, fold[], general[] }, stream-ordered like the launches that use it
-      cudaError_t e = cudaMallocAsync(reinterpret_cast<void **>(&lists), sizeof(int) * (2 + 2 * (size_t)a.nr_subgrids), stream);
-      if (e != cudaSuccess) return e;
-      e = cudaMemsetAsync(lists, 0, 2 * sizeof(int), stream);
-      if (e == cudaSuccess) e = launch_gridder_regular_check(a, flag, stream);
+      int *lists = subgrid_lists_slot(2 + 2 * (size_t)a.nr_subgrids);   // { n_fold, n_general, fold[], general[] }
+      if (!lists) return cudaErrorMemoryAllocation;
+      cudaError_t e = launch_gridder_regular_check(a, flag, stream, lists);   // also zeroes the two counts
       if (e == cudaSuccess) e = launch_gridder_planar_check(a, flag, lists, stream);
       if (e == cudaSuccess) e = launch_gridder_fold(a, lists, stream);
       if (e == cudaSuccess) e = launch_gridder_tc(a, 11, true, stream, nullptr, lists);
-      const cudaError_t ef = cudaFreeAsync(lists, stream);
-      return e != cudaSuccess ? e : ef;
+      return e;
     }
     case 21:   // tensor-core kernel, phasors of equally spaced channel blocks by rotation (else as 12)
       return sincos_mode == IDGB200_SINCOS_FAST ? launch_gridder_tc(a, 3, true, stream) : cudaErrorInvalidValue;

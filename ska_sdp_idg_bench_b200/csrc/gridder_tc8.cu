@@ -39,7 +39,9 @@ constexpr int G8_NB = 16;                        // B ring slots
 constexpr int G8_THREADS = (G8_PAIRS + 1) * 32;
 
 // regular = the recurrence applies to every block with one spacing and the blocks pair up
-__global__ void gridder_regular_check_kernel(const float *__restrict__ wavenumbers, const int C, int *flag) {
+__global__ void gridder_regular_check_kernel(const float *__restrict__ wavenumbers, const int C, int *flag,
+                                             int *zero2) {
+  if (zero2 && threadIdx.x < 2) zero2[threadIdx.x] = 0;   // the list counts of gridder_fold.cu's planar check
   const int ncb = (C + G8_CB - 1) / G8_CB;
   bool ok = !(ncb & 1);
   float dw0 = 0.f;
@@ -329,8 +331,8 @@ gridder_tc8_kernel(const KernelArgs a, const int slabs, const int tiles_per_cta,
 
 }  // namespace
 
-cudaError_t launch_gridder_regular_check(const KernelArgs &a, int *d_flag, cudaStream_t stream) {
-  gridder_regular_check_kernel<<<1, 32, 0, stream>>>(a.wavenumbers, a.nr_channels, d_flag);
+cudaError_t launch_gridder_regular_check(const KernelArgs &a, int *d_flag, cudaStream_t stream, int *d_zero2) {
+  gridder_regular_check_kernel<<<1, 32, 0, stream>>>(a.wavenumbers, a.nr_channels, d_flag, d_zero2);
   return cudaGetLastError();
 }
 

@@ -42,7 +42,8 @@ cudaError_t launch_gridder_tc(const KernelArgs &a, int poly, bool recur, cudaStr
                               const int *skip_flag = nullptr, const int *lists = nullptr);
 // two M-tiles per warp, regular channel layouts only (gridder_tc8.cu): the check writes *d_flag = 1 when every
 // 8-channel block is equally spaced with one spacing and the blocks pair up; the kernel is a no-op unless it is set
-cudaError_t launch_gridder_regular_check(const KernelArgs &a, int *d_flag, cudaStream_t stream);
+// d_zero2 (may be null): two ints the same kernel zeroes (gridder_fold.cu's list counts)
+cudaError_t launch_gridder_regular_check(const KernelArgs &a, int *d_flag, cudaStream_t stream, int *d_zero2 = nullptr);
 cudaError_t launch_gridder_tc8(const KernelArgs &a, const int *d_regular_flag, cudaStream_t stream);
 // phasor operand in TMEM, four tiles per group of four warps (gridder_tc4.cu); regular layouts only, same gate
 cudaError_t launch_gridder_tc4(const KernelArgs &a, const int *d_regular_flag, cudaStream_t stream);
