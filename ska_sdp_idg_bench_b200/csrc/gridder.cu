@@ -422,7 +422,7 @@ int resolve_gridder_variant(int subgrid_size, int nr_channels, int sincos_mode, 
   if (!tc) return 10;
   // K = 32 stages when the channel blocks pair up.  (26, two tiles per warp for regular channel layouts,
   // measured the same 12.86 ms as 24 plus two small launches: opt-in)
-  // 29: planar subgrids (w = 0) folded onto pixel pairs where the launch qualifies (decided on the device),
+  // 29: planar subgrids (w = 0) folded onto pixel pairs (decided per subgrid on the device),
   // else 24 behind it (gridder_fold.cu)
   if (ncb % 2 == 0) return (nr_channels % 16 == 0 && subgrid_size % 2 == 0) ? 29 : 24;
   return 21;
