@@ -131,8 +131,10 @@ int idgb200_degridder(const idgb200_params *params, const idgb200_uvw *d_uvw,
                       const idgb200_metadata *d_metadata,
                       const idgb200_cfloat *d_subgrids, void *stream);
 
-/* Number of kernel launches the two calls above have made in this process
- * (bench.py reports it as gpu_launches). */
+/* Number of KERNELS this library has put on a stream in this process, whatever the entry point
+ * (gridder, degridder, adder, splitter, reduce_parts, subgrid FFT, the host-pointer and performance
+ * runs): a call that enqueues two kernels counts two.  The idgb200_init_* generators are not counted.
+ * bench.py reports the difference over its timed region as gpu_launches. */
 uint64_t idgb200_launch_count(void);
 
 /* ---- "next" rows: grid adder, subgrid FFT, splitter ------------

@@ -45,15 +45,6 @@ int have_device() {
   return IDGB200_OK;
 }
 
-// kernels one launch_gridder call puts on the stream: variants 26 / 27 = channel-layout check + their kernel + the
-// (gated) generic kernel; 29 = the two checks + gridder_fold.cu + the generic kernel for the subgrids it left
-// (one generic kernel where the shape rules the fold out: gridder.cu)
-int gridder_kernels_per_launch(const idgb200_params *p) {
-  const int v = resolve_gridder_variant(p->subgrid_size, p->nr_channels, p->sincos_mode, p->variant);
-  if (v == 29) return ((p->nr_channels & 15) || (p->subgrid_size & 1) || p->nr_channels > 1024) ? 1 : 4;
-  return v >= 26 ? 3 : 1;
-}
-
 long env_long(const char *name, long dflt) {
   // same semantics as get_env_var (app/common/common.cpp:10-17): atoi of the value
   const char *v = std::getenv(name);
@@ -304,10 +295,11 @@ int host_run(bool gridding, const idgb200_params *p, int64_t total_timesteps, in
 
     a.nr_subgrids = s1 - s0;
     a.subgrid_offset = s0;
-    cudaError_t e = gridding ? launch_gridder(a, p->sincos_mode, p->variant, s_k)
-                             : launch_degridder(a, p->sincos_mode, p->variant, s_k);
+    int nk = 0;
+    cudaError_t e = gridding ? launch_gridder(a, p->sincos_mode, p->variant, s_k, &nk)
+                             : launch_degridder(a, p->sincos_mode, p->variant, s_k, &nk);
     if (e != cudaSuccess) { status = (int)e; break; }
-    g_launches += gridding ? gridder_kernels_per_launch(p) : 1;
+    g_launches += nk;
     cudaEventRecord(ev_k[i], s_k);
     cudaStreamWaitEvent(s_out, ev_k[i], 0);
 
@@ -752,9 +744,10 @@ int idgb200_gridder(const idgb200_params *p, const idgb200_uvw *d_uvw, const flo
   if (!aligned16(d_vis) || !aligned16(d_at) || !aligned16(d_sg)) return IDGB200_EINVAL;
   if ((rc = have_device())) return rc;
   KernelArgs a = make_args(p, d_uvw, d_wn, d_vis, d_sph, d_at, d_meta, d_sg);
-  cudaError_t e = launch_gridder(a, p->sincos_mode, p->variant, static_cast<cudaStream_t>(stream));
+  int nk = 0;
+  cudaError_t e = launch_gridder(a, p->sincos_mode, p->variant, static_cast<cudaStream_t>(stream), &nk);
   if (e != cudaSuccess) return (int)e;
-  g_launches += gridder_kernels_per_launch(p);
+  g_launches += nk;
   return IDGB200_OK;
 }
 
@@ -767,9 +760,10 @@ int idgb200_degridder(const idgb200_params *p, const idgb200_uvw *d_uvw, const f
   if (!aligned16(d_vis) || !aligned16(d_at) || !aligned16(d_sg)) return IDGB200_EINVAL;
   if ((rc = have_device())) return rc;
   KernelArgs a = make_args(p, d_uvw, d_wn, d_vis, d_sph, d_at, d_meta, d_sg);
-  cudaError_t e = launch_degridder(a, p->sincos_mode, p->variant, static_cast<cudaStream_t>(stream));
+  int nk = 0;
+  cudaError_t e = launch_degridder(a, p->sincos_mode, p->variant, static_cast<cudaStream_t>(stream), &nk);
   if (e != cudaSuccess) return (int)e;
-  g_launches++;
+  g_launches += nk;
   return IDGB200_OK;
 }
 

@@ -228,7 +228,8 @@ int resolve_degridder_variant(int subgrid_size, int nr_channels, int sincos_mode
   return tc ? ((nr_channels & 7) ? 22 : 24) : 4;
 }
 
-cudaError_t launch_degridder(const KernelArgs &a, int sincos_mode, int variant, cudaStream_t stream) {
+cudaError_t launch_degridder(const KernelArgs &a, int sincos_mode, int variant, cudaStream_t stream, int *kernels) {
+  if (kernels) *kernels = a.nr_subgrids == 0 ? 0 : 1;   // every variant is one kernel
   if (a.nr_subgrids == 0) return cudaSuccess;
   variant = resolve_degridder_variant(a.subgrid_size, a.nr_channels, sincos_mode, variant);
   switch (variant) {

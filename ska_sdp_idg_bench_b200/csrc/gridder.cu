@@ -59,7 +59,7 @@ struct Layout<1> { static constexpr int F4_PER_VIS = 2; static constexpr int ACC
 
 template <int NT, int P, int SCHEME, int MODE, int MINB>
 __global__ void __launch_bounds__(NT, MINB)
-gridder_kernel(const KernelArgs a, const int slabs, const int vis_per_chunk) {
+gridder_kernel(const KernelArgs a, const int slabs, const int vis_per_chunk, const int *__restrict__ todo) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int F4 = Layout<SCHEME>::F4_PER_VIS;
   constexpr int NACC = Layout<SCHEME>::ACC;
@@ -70,6 +70,7 @@ gridder_kernel(const KernelArgs a, const int slabs, const int vis_per_chunk) {
   const int C = a.nr_channels;
   const int npix = N * N;
   const int s_local = blockIdx.x / slabs;
+  if (todo && !todo[s_local]) return;   // gridder_sep.cu has gridded this subgrid
   const int slab = blockIdx.x - s_local * slabs;
   const int s = a.subgrid_offset + s_local;
   const int tid = threadIdx.x;
@@ -327,7 +328,7 @@ gridder_kernel(const KernelArgs a, const int slabs, const int vis_per_chunk) {
 }
 
 template <int NT, int P, int SCHEME, int MINB>
-cudaError_t launch_t(const KernelArgs &a, int mode, cudaStream_t stream) {
+cudaError_t launch_t(const KernelArgs &a, int mode, cudaStream_t stream, const int *todo = nullptr) {
   const int npix = a.subgrid_size * a.subgrid_size;
   const int slabs = (npix + NT * P - 1) / (NT * P);
   const int C = a.nr_channels;
@@ -338,7 +339,7 @@ cudaError_t launch_t(const KernelArgs &a, int mode, cudaStream_t stream) {
                       (P % 4 == 0 ? (size_t)3 * (P / 4) * NT * 16 : 0) + (size_t)2 * TB * 3 * 4 +
                       (size_t)(C + 1) * 4;
   if (smem > 200 * 1024) return cudaErrorInvalidValue;
-  void (*k)(const KernelArgs, int, int) = nullptr;
+  void (*k)(const KernelArgs, int, int, const int *) = nullptr;
   switch (mode) {
     case IDGB200_SINCOS_FAST: k = gridder_kernel<NT, P, SCHEME, IDGB200_SINCOS_FAST, MINB>; break;
     case IDGB200_SINCOS_REDUCED: k = gridder_kernel<NT, P, SCHEME, IDGB200_SINCOS_REDUCED, MINB>; break;
@@ -347,7 +348,7 @@ cudaError_t launch_t(const KernelArgs &a, int mode, cudaStream_t stream) {
   }
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  k<<<dim3((unsigned)a.nr_subgrids * slabs), dim3(NT), smem, stream>>>(a, slabs, vis_per_chunk);
+  k<<<dim3((unsigned)a.nr_subgrids * slabs), dim3(NT), smem, stream>>>(a, slabs, vis_per_chunk, todo);
   return cudaGetLastError();
 }
 
@@ -411,77 +412,99 @@ static int *subgrid_lists_slot(size_t count_ints) {
   return b.p;
 }
 
-int resolve_gridder_variant(int subgrid_size, int nr_channels, int sincos_mode, int variant) {
-  if (variant != 0) return variant;
-  // the tensor kernel pads the channels to blocks of 8 (K = 16) and the pixels to tiles of 128
+// the per-pixel kernel of a FAST launch: 24 / 21 (gridder_tc.cu) where the shape fills its tiles, else the FP32 kernel
+static int fallback_gridder_variant(int subgrid_size, int nr_channels) {
   const int npix = subgrid_size * subgrid_size;
   const int ncb = (nr_channels + 7) / 8, tiles = (npix + 127) / 128;
-  // (and keeps 10 floats per channel block in shared memory: beyond 1024 channels the FP32 kernel)
-  const bool tc = sincos_mode == IDGB200_SINCOS_FAST && 4 * nr_channels >= 3 * ncb * 8 &&
-                  4 * npix >= 3 * tiles * 128 && nr_channels <= 1024;
-  if (!tc) return 10;
-  // K = 32 stages when the channel blocks pair up.  (26, two tiles per warp for regular channel layouts,
-  // measured the same 12.86 ms as 24 plus two small launches: opt-in)
-  // 29: planar subgrids (w = 0) folded onto pixel pairs (decided per subgrid on the device),
-  // else 24 behind it (gridder_fold.cu)
-  if (ncb % 2 == 0) return (nr_channels % 16 == 0 && subgrid_size % 2 == 0) ? 29 : 24;
-  return 21;
+  const bool tc = 4 * nr_channels >= 3 * ncb * 8 && 4 * npix >= 3 * tiles * 128 && nr_channels <= 1024;
+  return !tc ? 10 : (ncb % 2 == 0 ? 24 : 21);
 }
 
-cudaError_t launch_gridder(const KernelArgs &a, int sincos_mode, int variant, cudaStream_t stream) {
+int resolve_gridder_variant(int subgrid_size, int nr_channels, int sincos_mode, int variant) {
+  if (variant != 0) return variant;
+  if (sincos_mode != IDGB200_SINCOS_FAST) return 10;
+  // 30: the row-column kernel (gridder_sep.cu), with the per-pixel kernel of this shape behind it
+  if (gridder_sep_supports(subgrid_size, nr_channels)) return 30;
+  return fallback_gridder_variant(subgrid_size, nr_channels);
+}
+
+cudaError_t launch_gridder_fp32(const KernelArgs &a, int sincos_mode, cudaStream_t stream, const int *todo) {
   if (a.nr_subgrids == 0) return cudaSuccess;
-  const int npix = a.subgrid_size * a.subgrid_size;
+  return a.subgrid_size * a.subgrid_size >= 1024 ? launch_t<128, 8, 3, 4>(a, sincos_mode, stream, todo)
+                                                 : launch_t<128, 4, 3, 4>(a, sincos_mode, stream, todo);
+}
+
+cudaError_t launch_gridder(const KernelArgs &a, int sincos_mode, int variant, cudaStream_t stream, int *kernels) {
+  int nk_local = 0;
+  int &nk = kernels ? *kernels : nk_local;
+  nk = 0;
+  if (a.nr_subgrids == 0) return cudaSuccess;
   variant = resolve_gridder_variant(a.subgrid_size, a.nr_channels, sincos_mode, variant);
+  const bool fast = sincos_mode == IDGB200_SINCOS_FAST;
+  cudaError_t e = cudaErrorInvalidValue;
   switch (variant) {
     case 10:
-      return npix >= 1024 ? launch_t<128, 8, 3, 4>(a, sincos_mode, stream)
-                          : launch_t<128, 4, 3, 4>(a, sincos_mode, stream);
+      nk = 1;
+      return launch_gridder_fp32(a, sincos_mode, stream);
     case 11: case 12: case 13: case 14: case 15:   // 12..15: 4, 5, 6, 8 of 16 phasors by FP32 polynomial
-      return sincos_mode == IDGB200_SINCOS_FAST ? launch_gridder_tc(a, variant - 11, false, stream)
-                                                : cudaErrorInvalidValue;
+      nk = 1;
+      return fast ? launch_gridder_tc(a, variant - 11, false, stream) : cudaErrorInvalidValue;
     case 22:   // as 21 with fp16 hi + lo phasors (FP32-class accuracy); 23: the same without the rotation
-      return sincos_mode == IDGB200_SINCOS_FAST ? launch_gridder_tc(a, 10, true, stream) : cudaErrorInvalidValue;
+      nk = 1;
+      return fast ? launch_gridder_tc(a, 10, true, stream) : cudaErrorInvalidValue;
     case 23:
-      return sincos_mode == IDGB200_SINCOS_FAST ? launch_gridder_tc(a, 10, false, stream) : cudaErrorInvalidValue;
+      nk = 1;
+      return fast ? launch_gridder_tc(a, 10, false, stream) : cudaErrorInvalidValue;
     case 24:   // as 21 with 16 channels (K = 32) per stage, single-buffered
-      return sincos_mode == IDGB200_SINCOS_FAST ? launch_gridder_tc(a, 11, true, stream) : cudaErrorInvalidValue;
+      nk = 1;
+      return fast ? launch_gridder_tc(a, 11, true, stream) : cudaErrorInvalidValue;
+    case 21:   // tensor-core kernel, phasors of equally spaced channel blocks by rotation (else as 12)
+      nk = 1;
+      return fast ? launch_gridder_tc(a, 3, true, stream) : cudaErrorInvalidValue;
     case 26:     // gridder_tc8.cu where the channel layout is regular (decided on the device), else 24
     case 27: {   // gridder_tc4.cu (phasor operand in TMEM) likewise
-      if (sincos_mode != IDGB200_SINCOS_FAST) return cudaErrorInvalidValue;
+      if (!fast) return cudaErrorInvalidValue;
       int *flag = regular_flag_slot();
       if (!flag) return cudaErrorMemoryAllocation;
-      cudaError_t e = launch_gridder_regular_check(a, flag, stream);
+      nk = 3;
+      e = launch_gridder_regular_check(a, flag, stream);
       if (e == cudaSuccess) e = variant == 26 ? launch_gridder_tc8(a, flag, stream) : launch_gridder_tc4(a, flag, stream);
       if (e == cudaSuccess) e = launch_gridder_tc(a, 11, true, stream, flag);
       return e;
     }
     case 29: {   // gridder_fold.cu for the planar subgrids of a regular channel layout, 24 for the others
-      if (sincos_mode != IDGB200_SINCOS_FAST) return cudaErrorInvalidValue;
+      if (!fast) return cudaErrorInvalidValue;
+      nk = 1;
       if ((a.nr_channels & 15) || (a.subgrid_size & 1) || a.nr_channels > 1024) return launch_gridder_tc(a, 11, true, stream);
       int *flag = regular_flag_slot();
       if (!flag) return cudaErrorMemoryAllocation;
       int *lists = subgrid_lists_slot(2 + 2 * (size_t)a.nr_subgrids);   // { n_fold, n_general, fold[], general[] }
       if (!lists) return cudaErrorMemoryAllocation;
-      cudaError_t e = launch_gridder_regular_check(a, flag, stream, lists);   // also zeroes the two counts
+      nk = 4;
+      e = launch_gridder_regular_check(a, flag, stream, lists);   // also zeroes the two counts
       if (e == cudaSuccess) e = launch_gridder_planar_check(a, flag, lists, stream);
       if (e == cudaSuccess) e = launch_gridder_fold(a, lists, stream);
       if (e == cudaSuccess) e = launch_gridder_tc(a, 11, true, stream, nullptr, lists);
       return e;
     }
-    case 21:   // tensor-core kernel, phasors of equally spaced channel blocks by rotation (else as 12)
-      return sincos_mode == IDGB200_SINCOS_FAST ? launch_gridder_tc(a, 3, true, stream) : cudaErrorInvalidValue;
+    case 30: {   // gridder_sep.cu (row-column form); subgrids it declines go to the per-pixel kernel behind it
+      if (!fast || !gridder_sep_supports(a.subgrid_size, a.nr_channels)) return cudaErrorInvalidValue;
+      ScratchLease lease;
+      e = scratch_acquire((size_t)a.nr_subgrids, stream, &lease);
+      if (e != cudaSuccess) return e;
+      nk = 2;
+      e = launch_gridder_sep(a, lease.ptr, stream);
+      if (e == cudaSuccess) {
+        const int fb = fallback_gridder_variant(a.subgrid_size, a.nr_channels);
+        e = fb == 10 ? launch_gridder_fp32(a, sincos_mode, stream, lease.ptr)
+                     : launch_gridder_tc(a, fb == 24 ? 11 : 3, true, stream, nullptr, nullptr, lease.ptr);
+      }
+      const cudaError_t e2 = scratch_release(lease, stream);
+      return e != cudaSuccess ? e : e2;
+    }
     case 16: case 17: case 18: case 19:   // phasor tile in TMEM; 18, 19: fp16 hi + lo phasors
-      return sincos_mode == IDGB200_SINCOS_FAST ? launch_gridder_tc3(a, variant - 16, stream)
-                                                : cudaErrorInvalidValue;
-    case 1: return launch_t<256, 4, 1, 2>(a, sincos_mode, stream);
-    case 2: return launch_t<256, 4, 3, 2>(a, sincos_mode, stream);
-    case 3: return launch_t<256, 8, 3, 1>(a, sincos_mode, stream);
-    case 4: return launch_t<256, 4, 0, 2>(a, sincos_mode, stream);
-    case 5: return launch_t<128, 8, 3, 3>(a, sincos_mode, stream);
-    case 6: return launch_t<128, 8, 3, 5>(a, sincos_mode, stream);   // experiments: occupancy vs registers
-    case 7: return launch_t<64, 8, 3, 8>(a, sincos_mode, stream);
-    case 8: return launch_t<256, 4, 3, 3>(a, sincos_mode, stream);
-    case 9: return launch_t<128, 4, 3, 6>(a, sincos_mode, stream);
+      nk = 1;
+      return fast ? launch_gridder_tc3(a, variant - 16, stream) : cudaErrorInvalidValue;
     default: return cudaErrorInvalidValue;
   }
 }

@@ -143,9 +143,10 @@ __device__ __forceinline__ void tc_produce_linear(unsigned char *A, const float 
 template <unsigned MASK16, bool SPLIT, bool WIDE = false>
 __global__ void __launch_bounds__(T2_THREADS, 3)
 gridder_tc_kernel(const KernelArgs a, const int slabs, const int tiles_per_cta, const int tmem_cols, const int recur,
-                  const int *__restrict__ skip_flag, const int *__restrict__ lists) {
+                  const int *__restrict__ skip_flag, const int *__restrict__ lists, const int *__restrict__ todo) {
   if (skip_flag && *skip_flag) return;   // gridder_tc8.cu has served this (regular) channel layout
   int s_local = blockIdx.x / slabs;
+  if (todo && !todo[s_local]) return;    // gridder_sep.cu has gridded this subgrid
   const int slab = blockIdx.x - s_local * slabs;
   if (lists) {   // gridder_fold.cu has served the fold list: this launch takes the general list (gridder_fold.cu)
     if (s_local >= lists[1]) return;
@@ -476,7 +477,7 @@ gridder_tc_kernel(const KernelArgs a, const int slabs, const int tiles_per_cta, 
 //       11 = as 3 with 16 channels (K = 32) per stage
 // recur: blocks of 8 equally spaced channels get their phasors by rotation from the first one
 cudaError_t launch_gridder_tc(const KernelArgs &a, int poly, bool recur, cudaStream_t stream, const int *skip_flag,
-                              const int *lists) {
+                              const int *lists, const int *todo) {
   if (a.nr_subgrids == 0) return cudaSuccess;
   const int npix = a.subgrid_size * a.subgrid_size;
   const int tiles_total = (npix + 127) / 128;
@@ -490,7 +491,7 @@ cudaError_t launch_gridder_tc(const KernelArgs &a, int poly, bool recur, cudaStr
   const size_t smem = (size_t)tiles_per_cta * T2_STAGES * T2_A_STAGE + T2_NB * T2_B_SLOT +
                       (T2_MAX_TILES * T2_STAGES + T2_NB + 3) * 8 + 8 + 48 + (size_t)ncb * (T2_CB + 2) * 4;
   if (smem > 200 * 1024) return cudaErrorInvalidValue;
-  void (*k)(const KernelArgs, int, int, int, int, const int *, const int *) = nullptr;
+  void (*k)(const KernelArgs, int, int, int, int, const int *, const int *, const int *) = nullptr;
   switch (poly) {
     case 0: k = gridder_tc_kernel<0x0000u, false>; break;
     case 1: k = gridder_tc_kernel<0x4444u, false>; break;   // 4 of 16: channels 2,6,10,14
@@ -503,7 +504,7 @@ cudaError_t launch_gridder_tc(const KernelArgs &a, int poly, bool recur, cudaStr
   }
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  k<<<dim3((unsigned)a.nr_subgrids * nslabs), dim3((producer_warps + 1) * 32), smem, stream>>>(a, nslabs, tiles_per_cta, tmem_cols, recur ? 1 : 0, skip_flag, lists);
+  k<<<dim3((unsigned)a.nr_subgrids * nslabs), dim3((producer_warps + 1) * 32), smem, stream>>>(a, nslabs, tiles_per_cta, tmem_cols, recur ? 1 : 0, skip_flag, lists, todo);
   return cudaGetLastError();
 }
 

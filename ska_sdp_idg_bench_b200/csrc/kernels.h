@@ -7,8 +7,9 @@
 namespace idgb200 {
 
 // sincos_mode: IDGB200_SINCOS_*; variant: see the launcher definitions.
-cudaError_t launch_gridder(const KernelArgs &a, int sincos_mode, int variant, cudaStream_t stream);
-cudaError_t launch_degridder(const KernelArgs &a, int sincos_mode, int variant, cudaStream_t stream);
+// *kernels (may be null) receives the number of kernels the call put on the stream
+cudaError_t launch_gridder(const KernelArgs &a, int sincos_mode, int variant, cudaStream_t stream, int *kernels = nullptr);
+cudaError_t launch_degridder(const KernelArgs &a, int sincos_mode, int variant, cudaStream_t stream, int *kernels = nullptr);
 
 // grid adder (adder.cu): parts[r] = base of the r-th block of rows_per_part grid rows (may be a peer address)
 // flags: IDGB200_FLAG_FFT_SHIFT
@@ -38,8 +39,16 @@ int resolve_degridder_variant(int subgrid_size, int nr_channels, int sincos_mode
 // skip_flag (device, may be null): the kernel returns at once when *skip_flag != 0;
 // lists (device, may be null): gridder_fold.cu's { n_fold, n_general, fold[], general[] }: the launch then
 // serves the subgrids of the general list only
+// todo (device, may be null): per-subgrid flags of this launch; subgrids whose flag is 0 are skipped
 cudaError_t launch_gridder_tc(const KernelArgs &a, int poly, bool recur, cudaStream_t stream,
-                              const int *skip_flag = nullptr, const int *lists = nullptr);
+                              const int *skip_flag = nullptr, const int *lists = nullptr, const int *todo = nullptr);
+// FP32 gridder (gridder.cu) with the same per-subgrid gate
+cudaError_t launch_gridder_fp32(const KernelArgs &a, int sincos_mode, cudaStream_t stream, const int *todo = nullptr);
+// row-column gridder (gridder_sep.cu): one GEMM per subgrid with the visibilities as K.  Writes
+// d_todo[nr_subgrids]: 0 = gridded, 1 = left to the per-pixel kernel launched behind it (the subgrid's
+// non-separable phase term is too large)
+bool gridder_sep_supports(int subgrid_size, int nr_channels);
+cudaError_t launch_gridder_sep(const KernelArgs &a, int *d_todo, cudaStream_t stream);
 // two M-tiles per warp, regular channel layouts only (gridder_tc8.cu): the check writes *d_flag = 1 when every
 // 8-channel block is equally spaced with one spacing and the blocks pair up; the kernel is a no-op unless it is set
 // d_zero2 (may be null): two ints the same kernel zeroes (gridder_fold.cu's list counts)
@@ -58,5 +67,14 @@ cudaError_t launch_degridder_tc(const KernelArgs &a, int poly, bool recur, cudaS
 cudaError_t launch_degridder_tc8(const KernelArgs &a, bool recur, bool fold, cudaStream_t stream);
 // phasor operand written to TMEM from registers (gridder_tc3.cu)
 cudaError_t launch_gridder_tc3(const KernelArgs &a, int mode, cudaStream_t stream);
+
+// per-launch device scratch (scratch.cu): acquire .. release brackets the enqueue of the kernels that use it
+struct ScratchLease {
+  int *ptr = nullptr;
+  void *pool = nullptr;
+  int slot = 0;
+};
+cudaError_t scratch_acquire(size_t ints, cudaStream_t stream, ScratchLease *lease);
+cudaError_t scratch_release(const ScratchLease &lease, cudaStream_t stream);
 
 }  // namespace idgb200

@@ -1,0 +1,155 @@
+"""GPU parity of the row-column kernels (csrc/gridder_sep.cu, degridder_sep.cu; variant 30 = what
+variant 0 resolves to for FAST sincos) against the oracle, through the C ABI.  Same stated
+tolerance as tests/test_gpu_parity.py (FAST: per-pol max|d|/max|ref| <= 1e-3, rel-RMS <= 3e-4)."""
+import numpy as np
+import pytest
+
+import ska_sdp_idg_bench_b200 as idg
+from oracle_lib import oracle, random_problem
+from test_gpu_parity import assert_close, covered_rows, per_pol_errors, run_degridder, run_gridder
+
+pytestmark = pytest.mark.gpu
+
+SEP = 30
+FAST = idg.SINCOS_FAST
+
+SHAPES = [
+    dict(subgrid_size=32, nr_channels=16, max_timesteps=128, nr_subgrids=3),   # the bench shape
+    dict(subgrid_size=32, nr_channels=64, max_timesteps=24, nr_subgrids=3, nr_stations=8),   # config 4 in miniature
+    dict(subgrid_size=64, nr_channels=16, max_timesteps=20, nr_subgrids=2, nr_stations=6, nr_slots=3),   # config 5
+    dict(subgrid_size=8, nr_channels=1, max_timesteps=3),
+    dict(subgrid_size=16, nr_channels=70, max_timesteps=5, nr_subgrids=4),
+    dict(subgrid_size=24, nr_channels=7, max_timesteps=40, nr_subgrids=6),
+    dict(subgrid_size=48, nr_channels=5, max_timesteps=20, nr_subgrids=3),
+    dict(subgrid_size=72, nr_channels=9, max_timesteps=11, nr_subgrids=2),     # 3 x 2 tiles, the last column tile 8 wide
+    dict(subgrid_size=20, nr_channels=300, max_timesteps=2, nr_subgrids=2),
+    dict(subgrid_size=32, nr_channels=24, max_timesteps=50, nr_subgrids=2),    # odd number of channel blocks
+    dict(subgrid_size=128, nr_channels=8, max_timesteps=6, nr_subgrids=1),     # 4 x 2 tiles
+]
+
+
+def with_linear_channels(p):
+    p.wavenumbers[:] = (2.9 + 0.0147 * np.arange(p.nr_channels)).astype(np.float32)
+    return p
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+@pytest.mark.parametrize("linear", [False, True])
+def test_gridder_sep_vs_oracle(shape, linear):
+    """w != 0, w_step != 0, image_size 0.02 (oracle_lib.random_problem): every subgrid passes the
+    separability check (|gamma| r ~ 1e-5 rad) and is gridded by the row-column kernel."""
+    o = oracle()
+    p = random_problem(201, **shape)
+    if linear:
+        with_linear_channels(p)
+    ref = o.gridder(p)
+    got = run_gridder(p, FAST, SEP)
+    mx, rms = assert_close(got, ref, 1, FAST, f"gridder sep {shape}")
+    print(f"gridder sep {shape} linear={linear}: max rel {mx.max():.2e}, rel rms {rms.max():.2e}")
+    # not the per-pixel kernel's result (the row-column kernel did the work) ...
+    fb = run_gridder(p, FAST, 10)
+    if np.abs(ref).max() > 0:
+        assert not np.array_equal(got, fb)
+    # ... and the default for this shape
+    assert idg.resolve_variant(p.subgrid_size, p.nr_channels, FAST, 0, gridder=True) == SEP
+    assert np.array_equal(run_gridder(p, FAST, 0), got)
+
+
+def test_gridder_sep_planar_config1():
+    o = oracle()
+    p = o.make_problem()
+    ref, ref64 = o.gridder(p), o.gridder_f64(p)
+    got = run_gridder(p, FAST, SEP)
+    mx, rms = assert_close(got, ref, 1, FAST, "gridder sep config 1")
+    e_gpu = np.abs(got - ref64).max() / np.abs(ref64).max()
+    e_cpu = np.abs(ref - ref64).max() / np.abs(ref64).max()
+    print(f"gridder sep config 1: max rel {mx}, rel rms {rms}; vs f64 {e_gpu:.2e} (cpu {e_cpu:.2e})")
+    assert e_gpu <= 2 * e_cpu + 2e-5
+
+
+def test_gridder_sep_declines_wide_fields():
+    """image_size 0.2 with w ~ N(0, 256): the dropped phase term gamma r reaches ~0.05 rad, so every subgrid
+    with timesteps fails the check and is gridded by the per-pixel kernel launched behind the row-column one,
+    bit for bit; a subgrid on the plane (w = 0, z such that w_offset = 0 is impossible with w_step != 0, so
+    w_step = 0 here) still takes the row-column kernel."""
+    o = oracle()
+    p = random_problem(202, subgrid_size=32, nr_channels=16, max_timesteps=30, nr_subgrids=5, image_size=0.2, w_step=0.0)
+    s = int(np.argmax(p.metadata["nr_timesteps"]))
+    t0, nt = int(p.metadata[s]["time_offset"]), int(p.metadata[s]["nr_timesteps"])
+    p.uvw[t0:t0 + nt, 2] = 0.0                      # one planar subgrid
+    ref = o.gridder(p)
+    got = run_gridder(p, FAST, SEP)
+    assert_close(got, ref, 1, FAST, "gridder sep wide field")
+    per_pixel = run_gridder(p, FAST, 24)
+    others = np.arange(p.nr_subgrids) != s
+    assert np.array_equal(got[others], per_pixel[others])
+    assert not np.array_equal(got[s], per_pixel[s])
+
+
+def test_gridder_sep_fft_shift_and_empty():
+    p = with_linear_channels(random_problem(203, subgrid_size=32, nr_channels=16, max_timesteps=20, nr_subgrids=4))
+    plain = run_gridder(p, FAST, SEP)
+    out = np.full_like(p.subgrids, np.nan)
+    idg.c_run_gridder(p.nr_subgrids, p.grid_size, p.subgrid_size, p.image_size, p.w_step, p.nr_channels,
+                      p.nr_stations, p.uvw, p.wavenumbers, p.visibilities, p.spheroidal, p.aterms, p.metadata,
+                      out, sincos=FAST, variant=SEP, flags=idg.FLAG_FFT_SHIFT)
+    h = p.subgrid_size // 2
+    assert np.array_equal(np.roll(out, (-h, -h), axis=(2, 3)), plain)
+    p.metadata["nr_timesteps"] = 0
+    assert not run_gridder(p, FAST, SEP).any()
+
+
+def test_gridder_sep_cancelling_sums():
+    """Cancellation-adversarial input: visibilities of a point source far outside the
+    subgrid's field, so that every pixel sum cancels to a small fraction of sum |v|.  The error of an fp16
+    operand is relative to sqrt(sum |v|^2), not to the result: report both, require the FAST tolerance
+    against the result for the default and FP32-class error for the precise variant."""
+    o = oracle()
+    p = with_linear_channels(random_problem(204, subgrid_size=32, nr_channels=16, max_timesteps=128, nr_subgrids=3,
+                                            with_w=False))
+    k = p.wavenumbers.astype(np.float64)
+    l0, m0 = 0.05, -0.04                               # 5 / 4 field widths away from the centre (image_size 0.02)
+    ph = (p.uvw[:, 0:1].astype(np.float64) * l0 + p.uvw[:, 1:2].astype(np.float64) * m0) * k[None, :]
+    p.visibilities[:] = (np.exp(-1j * ph)[:, :, None] * np.array([1.0, 0.5, -0.5, 1.0])).astype(np.complex64)
+    ref, ref64 = o.gridder(p), o.gridder_f64(p)
+    got = run_gridder(p, FAST, SEP)
+    nvis = np.maximum(p.metadata["nr_timesteps"], 1) * p.nr_channels
+    cancel = np.abs(ref64).reshape(p.nr_subgrids, -1).max(axis=1) / nvis
+    err = np.abs(got - ref64).reshape(p.nr_subgrids, -1).max(axis=1)
+    err_cpu = np.abs(ref - ref64).reshape(p.nr_subgrids, -1).max(axis=1)
+    print(f"cancelling sums: max|result| / sum|v| = {cancel}, error / max|result| = {err / np.abs(ref64).reshape(p.nr_subgrids, -1).max(axis=1)}, "
+          f"error / sqrt(sum|v|^2) = {err / np.sqrt(nvis)}, cpu-f32 error / max|result| = {err_cpu / np.abs(ref64).reshape(p.nr_subgrids, -1).max(axis=1)}")
+    assert_close(got, ref, 1, FAST, "gridder sep, cancelling sums")
+
+
+# ------------------------------------------------------------------------------------- degridder
+@pytest.mark.parametrize("shape", SHAPES)
+@pytest.mark.parametrize("linear", [False, True])
+def test_degridder_sep_vs_oracle(shape, linear):
+    if idg.resolve_variant(32, 16, FAST, 0, gridder=False) != SEP:
+        pytest.skip("row-column degridder not built yet")
+    o = oracle()
+    p = random_problem(211, **shape)
+    if linear:
+        with_linear_channels(p)
+    ref = o.degridder(p)
+    rows = covered_rows(p)
+    got = run_degridder(p, FAST, SEP)
+    mx, rms = assert_close(got[rows], ref[rows], 2, FAST, f"degridder sep {shape}")
+    print(f"degridder sep {shape} linear={linear}: max rel {mx.max():.2e}, rel rms {rms.max():.2e}")
+    assert not got[~rows].any(), "rows no subgrid covers must come back as zeros"
+    assert np.array_equal(run_degridder(p, FAST, 0), got)
+
+
+def test_degridder_sep_config1():
+    if idg.resolve_variant(32, 16, FAST, 0, gridder=False) != SEP:
+        pytest.skip("row-column degridder not built yet")
+    o = oracle()
+    p = o.make_problem()
+    ref, ref64 = o.degridder(p), o.degridder_f64(p)
+    got = run_degridder(p, FAST, SEP)
+    mx, rms = assert_close(got, ref, 2, FAST, "degridder sep config 1")
+    e_gpu = np.abs(got - ref64).max() / np.abs(ref64).max()
+    e_cpu = np.abs(ref - ref64).max() / np.abs(ref64).max()
+    print(f"degridder sep config 1: max rel {mx}, rel rms {rms}; vs f64 {e_gpu:.2e} (cpu {e_cpu:.2e})")
+    assert e_gpu <= 2 * e_cpu + 2e-5
