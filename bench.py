@@ -36,40 +36,7 @@ DEFAULT_SHAPE = dict(nr_stations=50, nr_timeslots=20, nr_timesteps=128, nr_chann
                      subgrid_size=32, grid_size=1024, image_size=0.01)
 SM_FP32_LANES = 128   # FP32 FMA lanes per SM (B200)
 SM_XU_LANES = 16      # MUFU lanes per SM
-# tensor-core kernel variants -> (MUFU per (pixel, visibility) item, dispatch cycles per warp-item executed,
-# dispatch cycles per warp-item of the formulation's minimal instruction mix).
-# Dispatch cycles = warp instructions + 1 per packed fp32x2 instruction (FFMA2 / FMUL2 / FADD2 hold the
-# sub-partition's dispatch port for two cycles: DESIGN.md 3).  "Executed" is counted by ncu on the committed
-# captures under profiles/ (gridder 24; degridder 22; the other variants' figures are older captures or
-# estimates) and includes loop control, barrier polls, MMA issue and the builder warp.  "Minimal" counts only
-# what the formulation needs per item: gridder 24 = F2FP 1 + recurrence FFMA2 2 x 6/8 +
-# (first rotation 4 + first-channel sincos 4) / 8 + STS.128 1/4 + per-timestep (phase index 12 + rotation
-# sincos 16) / 64 = 4.19; degridder 22 per pixel and channel quad = phase index 4 + two sincos 8 + 2 cos 1 +
-# rotation 4 + 2 recurrence steps 4 + 4 x (F2FP + 2 FHFMA + F2FP) 16 + STS 2 + LDS 1 = 40 / 4 = 10;
-# degridder 24 per pixel and group of 8 channels = LDS 1 + phase index 4 + two sincos 8 + 2 cos 1 + rotation 4
-# + 6 recurrence steps 12 + 8 x 4 = 32 + STS 4 = 66 / 8 = 8.25.
-TC_GRIDDER = {11: (2.0, 10.1, None), 12: (1.5, 12.6, None), 13: (1.375, 12.9, None), 14: (1.25, 13.3, None),
-              15: (1.0, 14.2, None), 21: (0.375, 10.0, None), 22: (0.375, 15.2, None), 23: (2.0, 17.1, None),
-              24: (0.382, 6.91, 4.19), 26: (0.382, 6.91, 4.19)}
-TC_DEGRIDDER = {11: (2.0, 11.5, None), 12: (1.5, 13.5, None), 13: (1.25, 13.2, None), 14: (1.0, 15.5, None),
-                21: (1.0, 10.5, None), 22: (1.006, 14.63, 10.0), 23: (2.0, 18.5, None),
-                24: (0.505, 11.95, 8.25), 28: (0.505, 11.95, 8.25)}
-# planar launches (pixel-pair folding): per NOMINAL (pixel, visibility) item, i.e. half the general path's
-# figures plus the epilogue / builder share; executed counts from profiles/r01_fold_ncu_full.txt
-# (2.79 / 5.02 warp instructions per nominal warp-item; the packed share taken from the general path's captures)
-TC_GRIDDER[29] = (0.191, 3.30, 2.10)
-TC_DEGRIDDER_FOLDED = (0.253, 5.52, 4.13)
-
-
-# tcgen05.mma instructions (M=128, N=16, K=16, both operands in shared memory) per (pixel, visibility) item:
-# one MMA covers 128 rows x 8 K-pairs = 1024 items; the hi + lo phasor kernels issue two per block.
-TC_MMA_PER_ITEM = {"gridder": {21: 1 / 1024, 24: 1 / 1024, 26: 1 / 1024, 22: 2 / 1024, 23: 2 / 1024, 29: 0.5 / 1024},
-                   "degridder": {21: 1 / 1024, 22: 2 / 1024, 23: 2 / 1024, 24: 2 / 1024, 25: 2 / 1024, 28: 2 / 1024}}
-# measured on the B200 (tools/smem_mix.cu, profiles/r01_smem_mix_microbench.log): tcgen05.mma of that shape take
-# 40.0 clocks each on an SM when the pipe stays fed (256 between two commits; 51-55 with a drain every 16) - the
-# 4 KB A tile is fetched from shared memory at ~100 B/clk, 5x the 8 clocks of its math - and concurrent STS.128
-# traffic of the LSU does not slow them (the two paths do not share one crossbar)
-MMA_SS_CLOCKS = 40.0
+CONSTANTS_PATH = os.path.join(ROOT, "profiles", "roofline_constants.json")   # written by tools/ncu_summary.py --json
 
 
 # ----------------------------------------------------------------- shared helpers
@@ -319,6 +286,38 @@ def workload_config(shape: dict, n_gpus: int) -> dict:
 
 
 # --------------------------------------------------------------------- GPU arm
+def load_constants() -> dict:
+    """Per-kernel figures from the committed ncu captures (tools/ncu_summary.py --json): DRAM bytes per subgrid,
+    pipe utilisations.  The roofline fraction itself needs none of them (analytic flops / live time / measured peak)."""
+    try:
+        return json.load(open(CONSTANTS_PATH))
+    except Exception:
+        return {}
+
+
+def stage_flops(shape: dict, kind: str) -> dict:
+    """tcgen05 flops of one launch of the row-column kernels (2 M N K per MMA), counted from the shape.
+    gridder_sep.cu: one M=128 (4 pols x 32 rows) x N=4*XT x K=16 MMA per (tile, timestep, 8-channel block); of the
+    N columns half are the fp16 lo part of the column phasors.  degridder_sep.cu: per tile of 128 visibilities
+    and K step of 8 columns three M=128 x N=8*Ny x K=16 MMAs (hi hi, lo hi, hi lo).
+    `useful` counts the contraction the formulation needs once in the operands' nominal precision (no lo parts,
+    no padding of rows / channels / visibilities); `executed` everything issued."""
+    N, C, S, T = shape["subgrid_size"], shape["nr_channels"], shape["nr_subgrids"], shape["nr_timesteps"]
+    vis = S * T * C
+    useful = 2.0 * vis * (4 * N) * (2 * N) * 2       # complex MAC of 4N rows x N columns (gridder) = 4N x N x 8 flop
+    if kind == "gridder":
+        ytiles, ncb = -(-N // 32), -(-C // 8)
+        executed = 0.0
+        for x0 in range(0, N, 64):
+            xt = min(64, N - x0)
+            executed += 2.0 * 128 * (4 * xt) * 16 * ytiles * S * T * ncb
+    else:
+        kc = -(-(N // 4) // 2)                         # K steps of 16 (8 columns)
+        tiles = S * -(-(T * C) // 128)
+        executed = 2.0 * 128 * (8 * N) * 16 * 3 * kc * tiles
+    return {"useful": useful, "executed": executed}
+
+
 def run_ours(args) -> None:
     import torch
     import torch.distributed as dist
@@ -337,85 +336,121 @@ def run_ours(args) -> None:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
+    strong = args.scaling == "strong"
     shape = rank_shape({}, rank, world)
     sincos = {"fast": idg.SINCOS_FAST, "reduced": idg.SINCOS_REDUCED,
               "accurate": idg.SINCOS_ACCURATE}[args.sincos]
+    # weak scaling: every rank the whole config-2 observation with its own seed.  strong scaling: ONE observation
+    # (seed 0 on every rank) cut by shard.partition_subgrids; a rank keeps its contiguous range of the subgrid
+    # list with the uvw / visibility rows it covers (shard.shard_metadata), nothing is exchanged.
     prob = idg.init_problem_device(
         nr_stations=shape["nr_stations"], nr_timeslots=shape["nr_timeslots"],
         nr_timesteps=shape["nr_timesteps"], nr_channels=shape["nr_channels"],
         subgrid_size=shape["subgrid_size"], grid_size=shape["grid_size"],
-        image_size=shape["image_size"], seed=shape["seed"], device=dev)
+        image_size=shape["image_size"], seed=0 if strong else shape["seed"], device=dev)
+    S_total = prob["nr_subgrids"]
+    if strong and world > 1:
+        meta_np = np.ascontiguousarray(prob["metadata"].cpu().numpy()).view(idg.METADATA_DTYPE).reshape(-1)
+        s0, s1 = idg.partition_subgrids(meta_np["nr_timesteps"], world)[rank]
+        m_loc, t0, t1 = idg.shard_metadata(meta_np, s0, s1)
+        prob["metadata"] = torch.from_numpy(m_loc.view(np.int32).reshape(-1, 9).copy()).to(dev)
+        prob["uvw"] = prob["uvw"][t0:t1].contiguous()
+        prob["visibilities"] = prob["visibilities"][t0:t1].contiguous()
+        prob["subgrids"] = prob["subgrids"][s0:s1].contiguous()
+        prob["nr_subgrids"], prob["total_timesteps"] = s1 - s0, t1 - t0
     S, tt, C_, N = prob["nr_subgrids"], prob["total_timesteps"], prob["nr_channels"], prob["subgrid_size"]
+    my_mvis = 1e-6 * tt * C_
     scal = (S, prob["grid_size"], N, prob["image_size"], 0.0, C_, prob["nr_stations"], tt)
-    tens = (prob["uvw"], prob["wavenumbers"], prob["visibilities"], prob["spheroidal"],
-            prob["aterms"], prob["metadata"], prob["subgrids"])
     sub_in = prob["subgrids"].clone()  # degridder input (the gridder overwrites subgrids)
     vis_out = torch.empty_like(prob["visibilities"])
+    # the same observation off the plane: w ~ N(0, 256 m) on every timestep (the reference's generator writes
+    # w = 0, init.cpp:4-25; a real observation does not)
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    uvw_w = prob["uvw"].clone()
+    uvw_w[:, 2] = torch.randn(uvw_w.shape[0], device=dev, generator=gen) * 256.0
 
-    def step_gridder():
-        idg.gridder(*scal, *tens, sincos=sincos, variant=args.variant)
+    def gridder_step(variant, uvw=None):
+        u = prob["uvw"] if uvw is None else uvw
+        return lambda: idg.gridder(*scal, u, prob["wavenumbers"], prob["visibilities"], prob["spheroidal"],
+                                   prob["aterms"], prob["metadata"], prob["subgrids"], sincos=sincos, variant=variant)
 
-    def step_degridder():
-        idg.degridder(*scal, prob["uvw"], prob["wavenumbers"], vis_out, prob["spheroidal"],
-                      prob["aterms"], prob["metadata"], sub_in, sincos=sincos,
-                      variant=args.degridder_variant)
+    def degridder_step(variant, uvw=None):
+        u = prob["uvw"] if uvw is None else uvw
+        return lambda: idg.degridder(*scal, u, prob["wavenumbers"], vis_out, prob["spheroidal"], prob["aterms"],
+                                     prob["metadata"], sub_in, sincos=sincos, variant=variant)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(step, steps, warmup):
-        """K steps between CUDA events on the launching (torch current) stream,
-        barrier + synchronize on both sides; returns (max-over-ranks seconds, launches)."""
-        for _ in range(warmup):
-            step()
+    def all_max(x: float) -> float:
+        return reduce_max_time(x, dev)
+
+    def timed(step, steps, warmup, min_seconds=1.0, max_rounds=64):
+        """Warm-up: at least `warmup` steps, then on until two consecutive steps agree to 2 % (allocations,
+        module loading and clock ramps stay out of the timed region).  Timed: rounds of EXACTLY `steps` steps,
+        back to back, every step between its own pair of CUDA events on the launching (torch current) stream,
+        repeated until the region is >= min_seconds; barrier + synchronize on both sides.  Seconds per step =
+        whole region / steps in it, max over ranks (so a host-side stall that starves the GPU shows up - compare
+        with the per-step median, which does not see it)."""
+        last, n_warm = None, 0
+        e_a, e_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        while True:
+            e_a.record(); step(); e_b.record(); e_b.synchronize()
+            ms = e_a.elapsed_time(e_b)
+            n_warm += 1
+            if n_warm >= warmup and ((last is not None and abs(ms - last) <= 0.02 * last) or n_warm >= warmup + 40):
+                break
+            last = ms
+        rounds = int(min(max_rounds, max(1, -(-min_seconds // max(steps * ms * 1e-3, 1e-6)))))
+        rounds = int(all_max(float(rounds)))
+        n = rounds * steps
         barrier()
         l0 = idg.launch_count()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(steps):
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(n + 1)]
+        ev[0].record()
+        for i in range(n):
             step()
-        e1.record()
+            ev[i + 1].record()
         barrier()
-        sec = e0.elapsed_time(e1) * 1e-3
-        return reduce_max_time(sec, dev), idg.launch_count() - l0
+        per = sorted(ev[i].elapsed_time(ev[i + 1]) for i in range(n))
+        sec = ev[0].elapsed_time(ev[n]) * 1e-3
+        return {"sec_per_step": all_max(sec) / n, "rounds": rounds, "timed_steps": n, "timed_region_s": sec,
+                "warmup_steps": n_warm, "launches_per_step": (idg.launch_count() - l0) / n,
+                "step_ms": {"min": per[0], "median": per[n // 2], "max": per[-1]}}
 
-    # which kernels variant 0 selects for this shape (idgb200_resolve_variant)
+    def rate(t):
+        """whole-job MVis/s from the max-over-ranks seconds per step"""
+        total = world * shape["mvis"] if not strong else shape["mvis"]
+        return total / t["sec_per_step"]
+
     g_variant = idg.resolve_variant(N, C_, sincos, args.variant, gridder=True)
     d_variant = idg.resolve_variant(N, C_, sincos, args.degridder_variant, gridder=False)
-
-    def step_gridder_fp32():
-        idg.gridder(*scal, *tens, sincos=sincos, variant=10)
-
-    def step_degridder_fp32():
-        idg.degridder(*scal, prob["uvw"], prob["wavenumbers"], vis_out, prob["spheroidal"],
-                      prob["aterms"], prob["metadata"], sub_in, sincos=sincos, variant=4)
 
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    sec_g, launches_g = timed(step_gridder, args.steps, args.warmup)
-    sec_d, launches_d = timed(step_degridder, args.steps, args.warmup)
-    # the FP32/SFU gridder next to the tensor-core one (north_star: tensor cores only if they win)
-    # The synthetic observation is the reference's own (init.cpp:4-25): every w is 0, so the default kernels
-    # take their planar paths (mirror-image pixel pairs share one phasor row: gridder_fold.cu, degridder_tc8.cu).
-    # The same kernels' general path (any w) is timed beside them on the same data: variants 24 / 28.
-    planar = not bool(prob["uvw"][:, 2].any().item())
-    sec_gw = sec_dw = None
-    if planar and g_variant == 29:
-        sec_gw = timed(lambda: idg.gridder(*scal, *tens, sincos=sincos, variant=24), args.steps, args.warmup)[0]
-    if planar and d_variant == 24:
-        sec_dw = timed(lambda: idg.degridder(*scal, prob["uvw"], prob["wavenumbers"], vis_out, prob["spheroidal"],
-                                             prob["aterms"], prob["metadata"], sub_in, sincos=sincos, variant=28),
-                       args.steps, args.warmup)[0]
-    sec_g32 = timed(step_gridder_fp32, args.steps, args.warmup)[0] if g_variant in TC_GRIDDER else None
-    sec_d32 = timed(step_degridder_fp32, args.steps, args.warmup)[0] if d_variant in TC_DEGRIDDER else None
-    step_gridder()   # leave the default kernels' results in prob["subgrids"] / vis_out for the parity sample
-    step_degridder()
+    t_g = timed(gridder_step(args.variant), args.steps, args.warmup)
+    t_d = timed(degridder_step(args.degridder_variant), args.steps, args.warmup)
+    t_gw = timed(gridder_step(args.variant, uvw_w), args.steps, args.warmup)
+    t_dw = timed(degridder_step(args.degridder_variant, uvw_w), args.steps, args.warmup)
+    # comparators on the same data, a single round each: the per-pixel tcgen05 kernels (last round's defaults)
+    # and the FP32 / SFU kernels (north_star: tensor cores only if they win)
+    cmp_t = {}
+    if sincos == idg.SINCOS_FAST and not args.no_compare:
+        for name, mk, v in (("gridder_per_pixel", gridder_step, 24), ("degridder_per_pixel", degridder_step, 28),
+                            ("gridder_fp32", gridder_step, 10), ("degridder_fp32", degridder_step, 4)):
+            try:
+                cmp_t[name] = (v, timed(mk(v, uvw_w), args.steps, args.warmup, min_seconds=0.0))
+            except idg.IdgError:
+                pass
+    gridder_step(args.variant)()   # leave the default kernels' results (planar data) for the parity sample
+    degridder_step(args.degridder_variant)()
+    torch.cuda.synchronize()
     clocks = sampler.stop() if rank == 0 else {}
 
-    # ---- e2e through the host-pointer C ABI, pinned host buffers
+    # ---- e2e through the host-pointer C ABI, pinned host buffers; the copy floor measured the same way
     e2e = None
     if not args.no_e2e:
         host = {}
@@ -431,62 +466,55 @@ def run_ours(args) -> None:
              npy["uvw"], npy["wavenumbers"], npy["visibilities"], npy["spheroidal"],
              npy["aterms"], meta_np, npy["subgrids"])
 
-        def e2e_step():
-            idg.c_run_gridder(*a, sincos=sincos, variant=args.variant)
+        def host_timed(fn, n):
+            for _ in range(2):
+                fn()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(n):
+                fn()            # returns after the D2H of the result completed
+            torch.cuda.synchronize()
+            return all_max(time.perf_counter() - t0) / n
 
         e_steps = max(1, min(args.steps, 5))
-        for _ in range(2):
-            e2e_step()
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(e_steps):
-            e2e_step()          # returns after the D2H of the result completed
-        torch.cuda.synchronize()
-        sec_e = reduce_max_time(time.perf_counter() - t0, dev)
-        h2d = sum(npy[k].nbytes for k in ("uvw", "wavenumbers", "visibilities", "spheroidal",
-                                          "aterms", "metadata"))
-        # what the link gives: one pinned 1 GiB host->device copy on this rank, CUDA events
-        probe_h = torch.empty(1 << 30, dtype=torch.uint8, pin_memory=True)
-        probe_d = torch.empty(1 << 30, dtype=torch.uint8, device=dev)
-        probe_d.copy_(probe_h, non_blocking=True)
-        torch.cuda.synchronize()
-        pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        pe0.record()
-        probe_d.copy_(probe_h, non_blocking=True)
-        pe1.record()
-        torch.cuda.synchronize()
-        h2d_gbs = (1 << 30) / (pe0.elapsed_time(pe1) * 1e-3) * 1e-9
-        del probe_h, probe_d
-        # the degridder the same way: subgrids host -> device, visibilities device -> host
-        def e2e_step_d():
-            idg.c_run_degridder(*a, sincos=sincos, variant=args.degridder_variant)
+        sec_e = host_timed(lambda: idg.c_run_gridder(*a, sincos=sincos, variant=args.variant), e_steps)
+        sec_ed = host_timed(lambda: idg.c_run_degridder(*a, sincos=sincos, variant=args.degridder_variant), e_steps)
+        h2d_g = sum(npy[k].nbytes for k in ("uvw", "wavenumbers", "visibilities", "spheroidal", "aterms", "metadata"))
+        h2d_d = sum(npy[k].nbytes for k in ("uvw", "wavenumbers", "spheroidal", "aterms", "metadata", "subgrids"))
+        # copy floor at this N: the step's own bytes, H2D and D2H at the same time on two streams, all ranks at
+        # once (they share the host's memory and PCIe root), no kernel
+        d_in = torch.empty(h2d_g, dtype=torch.uint8, device=dev)
+        d_outb = torch.empty(npy["subgrids"].nbytes, dtype=torch.uint8, device=dev)
+        h_in = torch.empty(h2d_g, dtype=torch.uint8, pin_memory=True)
+        h_out = torch.empty(npy["subgrids"].nbytes, dtype=torch.uint8, pin_memory=True)
+        s1_, s2_ = torch.cuda.Stream(), torch.cuda.Stream()
 
-        for _ in range(2):
-            e2e_step_d()
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(e_steps):
-            e2e_step_d()
-        torch.cuda.synchronize()
-        sec_ed = reduce_max_time(time.perf_counter() - t0, dev)
-        e2e_degridder = {"value": world * shape["mvis"] * e_steps / sec_ed, "unit": "MVis/s",
-                         "ms_per_step": sec_ed / e_steps * 1e3,
-                         "h2d_bytes_per_step": int(sum(npy[k].nbytes for k in ("uvw", "wavenumbers", "spheroidal", "aterms",
-                                                                               "metadata", "subgrids"))),
-                         "d2h_bytes_per_step": int(npy["visibilities"].nbytes),
-                         "api": "idgb200_c_run_degridder_ex (host pointers, pinned)"}
-        e2e = {"value": world * shape["mvis"] * e_steps / sec_e, "unit": "MVis/s",
-               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(npy["subgrids"].nbytes),
-               "ms_per_step": sec_e / e_steps * 1e3, "steps": e_steps,
-               "api": "idgb200_c_run_gridder_ex (host pointers, pinned; chunked H2D/kernel/D2H on 3 streams)",
-               "pcie_h2d_gbs_measured": h2d_gbs, "h2d_floor_ms": h2d / (h2d_gbs * 1e9) * 1e3,
-               "note": "copy-bound: the step cannot be faster than its host->device bytes over the measured link",
-               "degridder": e2e_degridder}
+        def copy_only():
+            with torch.cuda.stream(s1_):
+                d_in.copy_(h_in, non_blocking=True)
+            with torch.cuda.stream(s2_):
+                h_out.copy_(d_outb, non_blocking=True)
+            s1_.synchronize(); s2_.synchronize()
 
-    # ---- the "next" rows around the two kernels: subgrid FFT, adder, splitter - byte movers,
-    # timed with the same protocol on a scratch copy; algorithmic bytes as in tools/next_rows_bench.py
+        sec_copy = host_timed(copy_only, e_steps)
+        del d_in, d_outb, h_in, h_out
+        total = (world if not strong else 1) * shape["mvis"]
+        e2e = {"value": total / sec_e, "unit": "MVis/s", "h2d_bytes_per_step": int(h2d_g),
+               "d2h_bytes_per_step": int(npy["subgrids"].nbytes), "ms_per_step": sec_e * 1e3, "steps": e_steps,
+               "api": "idgb200_c_run_gridder_ex (host pointers, pinned; chunked H2D / kernel / D2H on 3 streams)",
+               "copy_floor_ms": sec_copy * 1e3, "e2e_over_copy_floor": sec_copy / sec_e,
+               "copy_floor_note": "the same bytes per rank, H2D and D2H concurrently on two streams, every rank at once, "
+                                  "no kernel: what the host's memory and PCIe give at this N; e2e_over_copy_floor = "
+                                  "floor / step (1 = the kernels are fully hidden behind the copies)",
+               "h2d_gbs_in_floor": h2d_g / sec_copy * 1e-9,
+               "degridder": {"value": total / sec_ed, "unit": "MVis/s", "ms_per_step": sec_ed * 1e3,
+                             "h2d_bytes_per_step": int(h2d_d), "d2h_bytes_per_step": int(npy["visibilities"].nbytes),
+                             "api": "idgb200_c_run_degridder_ex (host pointers, pinned)"}}
+        del host, npy
+
+    # ---- the "next" rows around the two kernels: subgrid FFT, adder, splitter - byte movers
     next_rows = None
-    if world == 1:
+    if world == 1 and not args.no_compare:
         G = prob["grid_size"]
         work = sub_in.clone()
         grid = torch.zeros((4, G, G), dtype=torch.complex64, device=dev)
@@ -495,9 +523,9 @@ def run_ours(args) -> None:
         hbm = float(measured_peaks().get("hbm_gbs") or 0.0)
 
         def nr(step, nbytes):
-            sec, _ = timed(step, args.steps, args.warmup)
-            gbs = nbytes * args.steps / sec * 1e-9
-            return {"ms": sec / args.steps * 1e3, "gb_per_s": gbs, "hbm_frac": gbs / hbm if hbm else None,
+            t = timed(step, args.steps, args.warmup, min_seconds=0.0)
+            gbs = nbytes / t["sec_per_step"] * 1e-9
+            return {"ms": t["sec_per_step"] * 1e3, "gb_per_s": gbs, "hbm_frac": gbs / hbm if hbm else None,
                     "algorithmic_bytes": int(nbytes)}
 
         next_rows = {
@@ -505,7 +533,7 @@ def run_ours(args) -> None:
             "adder": nr(lambda: idg.adder(S, G, N, prob["metadata"], work, grid), sg_bytes + grid_bytes),
             "splitter": nr(lambda: idg.splitter(S, G, N, prob["metadata"], work, grid), sg_bytes + grid_bytes),
             "note": "HBM-bound byte movers (hbm_frac against MEASURED_PEAKS.json hbm_gbs); the reference has none "
-                    "of them (parity unpinned, oracle/idg_next_oracle.c); together < 4 % of a gridder launch",
+                    "of them (parity unpinned, oracle/idg_next_oracle.c)",
         }
         del work, grid
 
@@ -516,17 +544,20 @@ def run_ours(args) -> None:
         cores = host_threads()
         lib.set_threads(cores)
         n = max(64, 4 * cores)
-        # the same workload: copy the first n subgrids of the device-generated inputs
         T = shape["nr_timesteps"]
-        cp = oracle_lib.Problem(
-            grid_size=prob["grid_size"], subgrid_size=N, image_size=prob["image_size"], w_step=0.0,
-            nr_channels=C_, nr_stations=prob["nr_stations"],
-            uvw=prob["uvw"][:n * T].cpu().numpy(), wavenumbers=prob["wavenumbers"].cpu().numpy(),
-            visibilities=prob["visibilities"][:n * T].cpu().numpy(),
-            spheroidal=prob["spheroidal"].cpu().numpy(), aterms=prob["aterms"].cpu().numpy(),
-            metadata=np.ascontiguousarray(prob["metadata"][:n].cpu().numpy()).view(
-                oracle_lib.METADATA_DTYPE).reshape(-1),
-            subgrids=sub_in[:n].cpu().numpy())
+
+        def sample(uvw):
+            return oracle_lib.Problem(
+                grid_size=prob["grid_size"], subgrid_size=N, image_size=prob["image_size"], w_step=0.0,
+                nr_channels=C_, nr_stations=prob["nr_stations"],
+                uvw=uvw[:n * T].cpu().numpy(), wavenumbers=prob["wavenumbers"].cpu().numpy(),
+                visibilities=prob["visibilities"][:n * T].cpu().numpy(),
+                spheroidal=prob["spheroidal"].cpu().numpy(), aterms=prob["aterms"].cpu().numpy(),
+                metadata=np.ascontiguousarray(prob["metadata"][:n].cpu().numpy()).view(
+                    oracle_lib.METADATA_DTYPE).reshape(-1),
+                subgrids=sub_in[:n].cpu().numpy())
+
+        cp = sample(prob["uvw"])
         dt = time_cpu(lib, cp, "gridder")          # also a warm-up
         reps = int(max(1, min(20, 12.0 / max(dt, 1e-3))))
         tg = [time_cpu(lib, cp, "gridder") for _ in range(reps)]
@@ -538,185 +569,119 @@ def run_ours(args) -> None:
                       f"OpenMP over subgrids on all {cores} host threads",
             "degridder_value": mv / (sum(td) / len(td)),
         }
-        # parity of the bench-size run on that sample (per-pol max|d|/max|ref|)
-        ref_g = lib.gridder(cp)
-        got_g = prob["subgrids"][:n].cpu().numpy()
-        ref_d = lib.degridder(cp)
-        got_d = vis_out[:n * T].cpu().numpy()
-        parity = {
-            "sample_subgrids": n, "sincos": args.sincos,
-            "gridder_max_rel_per_pol": [float(np.abs(got_g[:, p] - ref_g[:, p]).max() /
-                                              np.abs(ref_g[:, p]).max()) for p in range(4)],
-            "degridder_max_rel_per_pol": [float(np.abs(got_d[..., p] - ref_d[..., p]).max() /
-                                                np.abs(ref_d[..., p]).max()) for p in range(4)],
-        }
+
+        def errs(got, ref, axis):
+            return [float(np.abs(np.take(got, p, axis) - np.take(ref, p, axis)).max() /
+                          np.abs(np.take(ref, p, axis)).max()) for p in range(4)]
+
+        # parity of the bench-size run on that sample (per-pol max|d|/max|ref|), planar and off the plane
+        parity = {"sample_subgrids": n, "sincos": args.sincos, "tolerance": 1e-3,
+                  "gridder_max_rel_per_pol": errs(prob["subgrids"][:n].cpu().numpy(), lib.gridder(cp), 1),
+                  "degridder_max_rel_per_pol": errs(vis_out[:n * T].cpu().numpy(), lib.degridder(cp), 2)}
+        cpw = sample(uvw_w)
+        gridder_step(args.variant, uvw_w)()
+        degridder_step(args.degridder_variant, uvw_w)()
+        torch.cuda.synchronize()
+        parity["general_w"] = {"gridder_max_rel_per_pol": errs(prob["subgrids"][:n].cpu().numpy(), lib.gridder(cpw), 1),
+                               "degridder_max_rel_per_pol": errs(vis_out[:n * T].cpu().numpy(), lib.degridder(cpw), 2)}
 
     ref_gpu = reference_gpu_kernels() if (rank == 0 and world == 1 and not args.no_cpu) else None
 
     if rank == 0:
         peaks = measured_peaks()
+        consts = load_constants()
         sms = idg.sm_count()
         f_max = float(peaks.get("sm_max_mhz") or clocks.get("sm_max_mhz") or 1965.0)
         p_fp32 = sms * SM_FP32_LANES * 2 * f_max * 1e6 * 1e-12       # TFLOP/s
         p_xu = sms * SM_XU_LANES * f_max * 1e6                       # MUFU/s
+        full = shape if not strong else shape
+        shape_launch = dict(shape, nr_subgrids=S)                    # what one launch of this rank processes
         flops = idg.flops_gridder(C_, tt, S, N)
         nbytes = idg.bytes_gridder(C_, tt, S, N)
         hbm_peak = float(peaks.get("hbm_gbs") or 6650.0)
+        tensor_peak = float(peaks.get("bf16_tflops") or 2250.0)
+        items = float(N) * N * tt * C_                               # (pixel, visibility) pairs per launch
 
-        def roof(sec, steps, traffic_per_subgrid, tc, mma_per_item=None):
-            """tc None: FP32 kernel (bound = the FP32 issue port); else (MUFU per item, dispatch
-            cycles per warp-item) of a tensor-core kernel, whose MACs run on tcgen05 and whose roof
-            is the XU (MUFU) pipe or the instruction dispatch port, whichever is busier."""
-            t = sec / steps
-            tf = flops / t * 1e-12
-            items = float(N) * N * tt * C_                     # (pixel, visibility) pairs per launch
-            hbm = {"achieved": nbytes / t * 1e-9, "peak": hbm_peak, "unit": "GB/s",
-                   "frac": nbytes / t * 1e-9 / hbm_peak,
-                   "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks.get("hbm_gbs") else "fallback 6650"}
-            common = {"traffic": traffic_per_subgrid * S,
-                      "traffic_note": "DRAM bytes/launch (dram__bytes_read+write) from the ncu --set full capture "
-                                      "under profiles/, scaled by subgrid count; algorithmic bytes "
-                                      "(bytes_gridder) = %.3f GB/launch" % (nbytes * 1e-9),
-                      "kernel_ms": t * 1e3, "hbm": hbm,
-                      "fp32_model_tflops": tf, "fp32_model_frac": tf / p_fp32,
-                      "fp32_model_note": f"reference flop model (flops_gridder) / ({sms} SMs x 128 FP32 lanes x 2 x "
-                                         f"{f_max:.0f} MHz): the north_star's 'fraction of the FP32+SFU roofline'"}
-            if tc is None:
-                r = dict({"bound": "fp32", "achieved": tf, "peak": p_fp32, "unit": "TFLOP/s", "frac": tf / p_fp32,
-                          "bound_note": "CUDA-core FP32 issue bound (359 flop/B): neither HBM nor tensor is the roof",
-                          "peak_source": f"{sms} SMs x 128 FP32 lanes x 2 x {f_max:.0f} MHz (sm_max_mhz of "
-                                         "MEASURED_PEAKS.json; the file holds no FP32 figure)",
-                          "sfu_frac": 2.0 * items / t / p_xu}, **common)
+        def roof(t, kind, variant):
+            """fp32_frac = flops_gridder / t / FP32 peak, sfu_frac = 2 N^2 vis/s / XU peak, stated plainly
+            for every kernel.  The row-column kernels (variant 30) do the model's MACs as a GEMM on tcgen05 and make
+            64 instead of 1024 phasors per visibility, so those two exceed 1 and bound nothing; their roofline is the
+            tensor pipe: `achieved` = the flops of the contraction the formulation needs (stage_flops: useful) / t against the
+            measured dense tensor peak (MEASURED_PEAKS.json bf16_tflops = the fp16 rate), `executed_frac` with the
+            fp16 lo operand parts and padding it actually issues.  The FP32 kernels are bound by FP32 issue."""
+            sec = t["sec_per_step"]
+            tf = flops / sec * 1e-12
+            r = {"kernel_ms": sec * 1e3, "fp32_frac": tf / p_fp32, "sfu_frac": 2.0 * items / sec / p_xu,
+                 "fp32_model_tflops": tf,
+                 "hbm": {"achieved": nbytes / sec * 1e-9, "peak": hbm_peak, "unit": "GB/s", "frac": nbytes / sec * 1e-9 / hbm_peak,
+                         "algorithmic_bytes": int(nbytes)},
+                 "peaks": {"fp32_tflops": p_fp32, "xu_tmufu": p_xu * 1e-12, "tensor_tflops": tensor_peak,
+                           "source": f"{sms} SMs x 128 FP32 lanes x 2 / x 16 MUFU lanes x {f_max:.0f} MHz (sm_max_mhz); "
+                                     "tensor and HBM: MEASURED_PEAKS.json (burst: kernel timed alone)"}}
+            c = consts.get(f"{kind}_sep" if variant == 30 else f"{kind}_v{variant}", {})
+            per_sg = c.get("dram_bytes_per_subgrid")
+            r["traffic"] = per_sg * S if per_sg else None
+            if c:
+                r["ncu"] = {k: c[k] for k in c if k.endswith("_pct") or k in ("source", "subgrids", "duration_ms")}
+            if variant == 30:
+                fl = stage_flops(shape_launch, kind)
+                r.update({"bound": "tensor", "achieved": fl["useful"] / sec * 1e-12, "peak": tensor_peak, "unit": "TFLOP/s",
+                          "frac": fl["useful"] / sec * 1e-12 / tensor_peak,
+                          "executed_tflops": fl["executed"] / sec * 1e-12,
+                          "executed_frac": fl["executed"] / sec * 1e-12 / tensor_peak,
+                          "flops_per_launch": fl})
             else:
-                mufu_per_item, inst_per_item, floor_per_item = tc
-                mufu = mufu_per_item * items / t               # MUFU.SIN + MUFU.COS executed per second
-                p_issue = sms * 4 * f_max * 1e6                 # dispatch cycles / s (1 per SMSP and clock)
-                issue = inst_per_item * items / 32.0 / t
-                sfu_frac, issue_frac = mufu / p_xu, issue / p_issue
-                # the same port, counting only the minimal instruction mix of the formulation: what
-                # fraction of the dispatch roof does useful work (the kernel-quality figure)
-                useful_frac = None if floor_per_item is None else floor_per_item * items / 32.0 / t / p_issue
-                note = ("tcgen05 kernel: the complex MACs run on the tensor pipe (6-8 %% busy); what bounds it is "
-                        "generating the phasor operand: %.3f MUFU and %.2f dispatch cycles (instructions + 1 per "
-                        "packed fp32x2 instruction) per (pixel, visibility) against the XU pipe and the "
-                        "sub-partition's dispatch port (fp32_model_frac > 1 is the flop model's MACs and most of "
-                        "its sincos having left the FP32 / XU pipes)" % (mufu_per_item, inst_per_item))
-                if sfu_frac >= issue_frac:
-                    r = dict({"bound": "sfu", "achieved": mufu * 1e-12, "peak": p_xu * 1e-12, "unit": "TMUFU/s",
-                              "frac": sfu_frac, "peak_source": f"{sms} SMs x 16 MUFU lanes x {f_max:.0f} MHz"})
-                else:
-                    useful = useful_frac if useful_frac is not None else issue_frac
-                    r = dict({"bound": "issue", "achieved": useful * p_issue * 1e-12, "peak": p_issue * 1e-12,
-                              "unit": "T dispatch-cycles/s", "frac": useful,
-                              "frac_note": "useful dispatch cycles (minimal instruction mix of the formulation, "
-                                           "%.2f per warp-item) / peak; issue_frac beside it counts every executed "
-                                           "instruction (%.2f per warp-item, ncu)" % (floor_per_item or inst_per_item,
-                                                                                      inst_per_item),
-                              "peak_source": f"{sms} SMs x 4 sub-partitions x {f_max:.0f} MHz; dispatch cycles per "
-                                             "item from the ncu capture under profiles/"})
-                if mma_per_item:
-                    # the busiest resource: the tensor core's shared-memory operand fetch (one small-N MMA per
-                    # 1024 items still reads its whole 4 KB A tile)
-                    p_mma = sms * f_max * 1e6 / MMA_SS_CLOCKS
-                    mma = mma_per_item * items / t
-                    # ... but only when it is busier than the dispatch port with everything it executes: the
-                    # ablation builds (tools/ablate.py, profiles/r01_ablation.log, DESIGN.md 4.9) show the
-                    # instruction stream that makes the phasors to be 82 % / 77 % of the default kernels' time,
-                    # the MMAs and operand stores adding the rest by interference
-                    if mma / p_mma >= max(sfu_frac, issue_frac):
-                        r = {"bound": "tensor", "achieved": mma * 1e-9, "peak": p_mma * 1e-9,
-                             "unit": "G tcgen05.mma/s (M=128, N=16, K=16, operands in shared memory)",
-                             "frac": mma / p_mma, "useful_issue_frac": useful_frac,
-                             "peak_source": f"{sms} SMs x {f_max:.0f} MHz / {MMA_SS_CLOCKS} clocks per MMA, measured "
-                                            "back to back on this GPU type (tools/smem_mix.cu, "
-                                            "profiles/r01_smem_mix_microbench.log)",
-                             "frac_note": "share of the time the SM's tensor pipe needs for the launch's MMAs at the "
-                                          "measured rate: with N = 16 an MMA is bound by fetching its 4 KB A tile from "
-                                          "shared memory, not by its math (pipe_tensor_cycles_active 11-13 % in ncu)"}
-                r.update({"bound_note": note, "sfu_frac": sfu_frac, "issue_frac": issue_frac,
-                          "useful_issue_frac": useful_frac,
-                          "bound_evidence": "ablation builds of the general-path kernels (no MMAs, operand stores "
-                                            "predicated off): 10.53 of 12.85 ms (gridder) and 17.61 of 22.80 ms "
-                                            "(degridder) are the instruction stream alone, at 90 % / 94 % of the "
-                                            "dispatch port (profiles/r01_ablation.log); the tensor pipe sustains "
-                                            "41.7 clocks per N = 16 MMA from 12-24 issuing warps "
-                                            "(profiles/r01_mma_commit_microbench.log); tensor_frac counts the folded "
-                                            "gridder's N = 32 MMAs at that rate",
-                          "tensor_frac": (mma_per_item * items / t) / (sms * f_max * 1e6 / MMA_SS_CLOCKS)
-                          if mma_per_item else None}, **common)
+                r.update({"bound": "fp32" if variant in (10, 4) else "issue", "achieved": tf, "peak": p_fp32,
+                          "unit": "TFLOP/s (reference flop model)", "frac": tf / p_fp32})
             if clocks.get("sm_mhz"):
                 r["frac_at_measured_clock"] = r["frac"] * f_max / clocks["sm_mhz"]
             return r
 
-        tc_g, tc_d = TC_GRIDDER.get(g_variant), TC_DEGRIDDER.get(d_variant)
-        mma_g, mma_d = TC_MMA_PER_ITEM["gridder"].get(g_variant), TC_MMA_PER_ITEM["degridder"].get(d_variant)
-        if planar and d_variant == 24:
-            tc_d, mma_d = TC_DEGRIDDER_FOLDED, mma_d / 2
-        if g_variant == 29 and not planar:
-            tc_g, mma_g = TC_GRIDDER[24], TC_MMA_PER_ITEM["gridder"][24]
-        total_mvis = world * shape["mvis"]
+        def entry(t, kind, variant, what=None):
+            e = {"value": rate(t), "unit": "MVis/s", "variant": variant, "ms_per_step": t["sec_per_step"] * 1e3,
+                 "tflops": (world if not strong else 1) * idg.flops_gridder(C_, shape["total_timesteps"], S_total, N)
+                           / t["sec_per_step"] * 1e-12 if not strong else
+                           idg.flops_gridder(C_, shape["total_timesteps"], S_total, N) / t["sec_per_step"] * 1e-12,
+                 "step_ms": t["step_ms"], "timed_steps": t["timed_steps"], "rounds": t["rounds"],
+                 "timed_region_s": t["timed_region_s"], "warmup_steps": t["warmup_steps"],
+                 "gpu_launches_per_step": t["launches_per_step"], "roofline": roof(t, kind, variant)}
+            if what:
+                e["what"] = what
+            return e
 
-        def general_w(sec, variant, tc, mma, traffic):
-            if sec is None:
-                return None
-            return {"value": total_mvis * args.steps / sec, "unit": "MVis/s", "variant": variant,
-                    "ms_per_step": sec / args.steps * 1e3, "tflops": world * flops * args.steps / sec * 1e-12,
-                    "what": "the same launch through the kernel's general path (any w: no pixel-pair folding), "
-                            "which is what a subgrid with a single w != 0 takes",
-                    "roofline": roof(sec, args.steps, traffic, tc, mma)}
+        top = entry(t_g, "gridder", g_variant)
         out = {
-            "metric": "gridder_mvis_per_s", "value": total_mvis * args.steps / sec_g,
+            "metric": "gridder_mvis_per_s", "value": top["value"],
             "unit": "MVis/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": sec_g / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "ms_per_step": top["ms_per_step"], "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None,
-            "dtype": "f32 (phasors and accumulation), fp16 x fp16 -> f32 tcgen05 operands" if tc_g is not None
-                     else "f32",
+            "dtype": "f32 phasors and accumulation; fp16 (hi + lo where stated) tcgen05 operands" if g_variant >= 20 else "f32",
             "data": "synthetic",
             "config": dict(workload_config(shape, world), sincos=args.sincos,
                            gridder_variant=g_variant, degridder_variant=d_variant,
-                           gridder_kernel=("tcgen05: fp16 phasor tile x fp16 hi+lo visibilities, f32 accumulate in "
-                                           "TMEM" + ("; phasors of equally spaced channels from the first channel of each "
-                                                     "8-channel block by one rotation and the three-term recurrence (the "
-                                                     "reference's gridder_v8 rotates every channel)"
-                                                     if g_variant in (21, 24, 26, 29) else "")
-                                           + ("; planar subgrids (every w = 0, checked per subgrid on the device): one phasor row per "
-                                              "mirror-image pixel pair, N = 32 MMAs, E +- i F recombined in the epilogue "
-                                              "(gridder_fold.cu)" if g_variant == 29 and planar else "")
-                                           if tc_g is not None else "FP32 FFMA2 + MUFU"),
-                           degridder_kernel=(("tcgen05: fp16 hi+lo phasor tile x fp16 hi+lo pixels, f32 accumulate in "
-                                              "TMEM; phasors of equally spaced channel quads by rotation"
-                                              if d_variant == 22 else
-                                              "tcgen05, two M-tiles per warp: fp16 hi+lo phasor tile x fp16 hi+lo pixels, f32 "
-                                              "accumulate in TMEM; phasors of equally spaced groups of 8 channels by the "
-                                              "three-term recurrence" + ("; planar subgrids (every w = 0, checked per "
-                                              "subgrid): summed over mirror-image pixel pairs, half the K dimension"
-                                              if planar else "") if d_variant == 24 else "tcgen05, opt-in variant")
-                                             if tc_d is not None else "FP32 FFMA2 + MUFU")),
-            "tflops": world * flops * args.steps / sec_g * 1e-12,
-            # ncu --set full, 3675-subgrid launches: 343.1 MB (tcgen05 gridder), 314.7 MB (tcgen05 degridder), FP32 kernels from the
-            # 1740-subgrid captures (profiles/)
-            "roofline": roof(sec_g, args.steps, (339.1e6 if g_variant == 29 and planar else 343.1e6) / 3675 if tc_g is not None else 145.165e6 / 1740,
-                             tc_g, mma_g),
-            "planar": planar,
-            "gridder_general_w": general_w(sec_gw, 24, TC_GRIDDER[24], TC_MMA_PER_ITEM["gridder"][24], 343.1e6 / 3675),
-            "degridder": {"value": total_mvis * args.steps / sec_d, "unit": "MVis/s",
-                          "ms_per_step": sec_d / args.steps * 1e3,
-                          "tflops": world * flops * args.steps / sec_d * 1e-12,
-                          "roofline": roof(sec_d, args.steps, 314.7e6 / 3675 if tc_d is not None
-                                           else 128.329e6 / 1740, tc_d, mma_d)},
-            "degridder_general_w": general_w(sec_dw, 28, TC_DEGRIDDER[24], TC_MMA_PER_ITEM["degridder"][24],
-                                             314.7e6 / 3675),
-            "gridder_fp32": None if sec_g32 is None else {
-                "value": total_mvis * args.steps / sec_g32, "unit": "MVis/s", "variant": 10,
-                "ms_per_step": sec_g32 / args.steps * 1e3,
-                "roofline": roof(sec_g32, args.steps, 145.165e6 / 1740, None)},
-            "degridder_fp32": None if sec_d32 is None else {
-                "value": total_mvis * args.steps / sec_d32, "unit": "MVis/s", "variant": 4,
-                "ms_per_step": sec_d32 / args.steps * 1e3,
-                "roofline": roof(sec_d32, args.steps, 128.329e6 / 1740, None)},
+                           sharding=(f"one observation of {S_total} subgrids cut into {world} contiguous ranges balanced by "
+                                     f"timesteps (shard.py), no collective" if strong else
+                                     f"subgrid list, {world} independent shard(s) of {S_total} subgrids, no collective"),
+                           timing="per-step CUDA events; rounds of `steps` steps until the region is >= 1 s; warm-up until two "
+                                  "consecutive steps agree to 2 %",
+                           gridder_kernel="gridder_sep.cu: row-column form, one tcgen05 GEMM per subgrid with the visibilities as K "
+                                          "(A = fp16(Y vis), B = fp16 hi + lo column phasors), per-subgrid separability check on the "
+                                          "device, per-pixel kernel behind it" if g_variant == 30 else f"variant {g_variant}",
+                           degridder_kernel="degridder_sep.cu: row-column form, tcgen05 GEMM over the columns (fp16 hi + lo both "
+                                            "operands), the sum over the rows on the CUDA cores out of TMEM" if d_variant == 30
+                                            else f"variant {d_variant}"),
+            "tflops": top["tflops"], "step_ms": top["step_ms"], "timed_steps": top["timed_steps"], "rounds": top["rounds"],
+            "timed_region_s": top["timed_region_s"], "warmup_steps": top["warmup_steps"],
+            "roofline": top["roofline"],
+            "degridder_value": rate(t_d), "degridder_ms_per_step": t_d["sec_per_step"] * 1e3,
+            "degridder": entry(t_d, "degridder", d_variant),
+            "general_w": {"what": "the same observation with w ~ N(0, 256 m) on every timestep (the reference's generator writes "
+                                  "w = 0): the default kernels take the same path",
+                          "gridder": entry(t_gw, "gridder", g_variant), "degridder": entry(t_dw, "degridder", d_variant)},
+            "comparators": {name: entry(t, name.split("_")[0], v, "same data (w != 0), one round") for name, (v, t) in cmp_t.items()},
             "reference_gpu": ref_gpu,
             "cpu_baseline": cpu_baseline, "parity": parity, "e2e": e2e, "next_rows": next_rows,
-            "gpu_launches": int(launches_g), "degridder_gpu_launches": int(launches_d),
+            "gpu_launches": int(round(t_g["launches_per_step"] * args.steps)),
             "clocks": clocks, "device": idg.device_name(),
         }
         emit(out)
@@ -731,11 +696,13 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--sincos", default="fast", choices=["fast", "reduced", "accurate"])
     ap.add_argument("--variant", type=int, default=0)
     ap.add_argument("--degridder-variant", type=int, default=0)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-compare", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

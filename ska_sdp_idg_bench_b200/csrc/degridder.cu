@@ -42,6 +42,7 @@ constexpr int TILE = 1024;  // pixels resident in shared memory at a time (64 KB
 template <int NT, int V, int SCHEME, int MODE, int MINB>
 __global__ void __launch_bounds__(NT, MINB)
 degridder_kernel(const KernelArgs a) {
+  if (a.todo && !a.todo[blockIdx.x]) return;   // degridder_sep.cu has degridded this subgrid
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float4 *s_pix = reinterpret_cast<float4 *>(smem_raw);   // [3][TILE] records, component-major
   float4 *s_lmno = s_pix + 3 * TILE;                       // [TILE]    (l, m, n, phase_offset)
@@ -219,39 +220,61 @@ cudaError_t launch_t(const KernelArgs &a, int mode, cudaStream_t stream) {
 //            phasors from the FP32 polynomial; 21 with the channel rotation of variant 22
 //         22 tensor-core kernel, fp16 hi + lo phasors (FP32-class accuracy), phasors of equally
 //            spaced channel quads by rotation from the quad's first channel; 23 without the rotation
-int resolve_degridder_variant(int subgrid_size, int nr_channels, int sincos_mode, int variant) {
-  if (variant != 0) return variant;
+// the per-pixel kernel of a FAST launch: 24 / 22 (degridder_tc8.cu / degridder_tc.cu) where the shape fills
+// their tiles, else the FP32 kernel
+static int fallback_degridder_variant(int subgrid_size, int nr_channels) {
   // the tensor kernel pads the channels to quads of 4 and the pixels to stages of 8
   const int npix = subgrid_size * subgrid_size, ncg = (nr_channels + 3) / 4;
-  const bool tc = sincos_mode == IDGB200_SINCOS_FAST && 4 * nr_channels >= 3 * ncg * 4 && npix >= 256;
+  const bool tc = 4 * nr_channels >= 3 * ncg * 4 && npix >= 256;
   // channel counts that fill groups of 8: the two-tiles-per-warp kernel (degridder_tc8.cu)
   return tc ? ((nr_channels & 7) ? 22 : 24) : 4;
 }
 
+int resolve_degridder_variant(int subgrid_size, int nr_channels, int sincos_mode, int variant) {
+  if (variant != 0) return variant;
+  if (sincos_mode != IDGB200_SINCOS_FAST) return 4;
+  // 30: the row-column kernel (degridder_sep.cu), with the per-pixel kernel of this shape behind it
+  if (degridder_sep_supports(subgrid_size, nr_channels)) return 30;
+  return fallback_degridder_variant(subgrid_size, nr_channels);
+}
+
 cudaError_t launch_degridder(const KernelArgs &a, int sincos_mode, int variant, cudaStream_t stream, int *kernels) {
-  if (kernels) *kernels = a.nr_subgrids == 0 ? 0 : 1;   // every variant is one kernel
+  int nk_local = 0;
+  int &nk = kernels ? *kernels : nk_local;
+  nk = 0;
   if (a.nr_subgrids == 0) return cudaSuccess;
   variant = resolve_degridder_variant(a.subgrid_size, a.nr_channels, sincos_mode, variant);
+  const bool fast = sincos_mode == IDGB200_SINCOS_FAST;
+  nk = 1;
   switch (variant) {
     case 4: return launch_t<256, 8, 3, 2>(a, sincos_mode, stream);
-    case 1: return launch_t<256, 4, 1, 2>(a, sincos_mode, stream);
-    case 2: return launch_t<256, 4, 3, 3>(a, sincos_mode, stream);
-    case 3: return launch_t<128, 8, 3, 3>(a, sincos_mode, stream);
-    case 11: case 12: case 13: case 14:   // tensor-core kernel; 12..14: 2, 3, 4 of 8 pixels by FP32 polynomial
-      return sincos_mode == IDGB200_SINCOS_FAST ? launch_degridder_tc(a, variant - 11, false, stream)
-                                                : cudaErrorInvalidValue;
-    case 21:   // tensor-core kernel, fp16 phasors, rotation recurrence over each quad of channels
-      return sincos_mode == IDGB200_SINCOS_FAST ? launch_degridder_tc(a, 0, true, stream) : cudaErrorInvalidValue;
-    case 22:   // the same with fp16 hi + lo phasors (FP32-class accuracy); 23: hi + lo without the recurrence
-      return sincos_mode == IDGB200_SINCOS_FAST ? launch_degridder_tc(a, 10, true, stream) : cudaErrorInvalidValue;
+    case 22:   // per-pixel tensor-core kernel (degridder_tc.cu), fp16 hi + lo phasors, rotation + recurrence over
+               // each quad of equally spaced channels; 23: without the recurrence
+      return fast ? launch_degridder_tc(a, 10, true, stream) : cudaErrorInvalidValue;
     case 23:
-      return sincos_mode == IDGB200_SINCOS_FAST ? launch_degridder_tc(a, 10, false, stream) : cudaErrorInvalidValue;
+      return fast ? launch_degridder_tc(a, 10, false, stream) : cudaErrorInvalidValue;
     case 24:   // two M-tiles per warp, groups of 8 channels, fp16 hi + lo phasors (nr_channels % 8 == 0), planar
     case 25:   // subgrids (w = 0) folded onto half the pixels; 25: no recurrence, 28: no folding (24 before it)
     case 28:
-      return sincos_mode == IDGB200_SINCOS_FAST && !(a.nr_channels & 7)
-                 ? launch_degridder_tc8(a, variant != 25, variant == 24, stream)
-                 : cudaErrorInvalidValue;
+      return fast && !(a.nr_channels & 7) ? launch_degridder_tc8(a, variant != 25, variant == 24, stream)
+                                          : cudaErrorInvalidValue;
+    case 30: {   // degridder_sep.cu (row-column form); subgrids it declines go to the per-pixel kernel behind it
+      if (!fast || !degridder_sep_supports(a.subgrid_size, a.nr_channels)) return cudaErrorInvalidValue;
+      ScratchLease lease;
+      cudaError_t e = scratch_acquire((size_t)a.nr_subgrids, stream, &lease);
+      if (e != cudaSuccess) return e;
+      nk = 2;
+      e = launch_degridder_sep(a, lease.ptr, stream);
+      if (e == cudaSuccess) {
+        KernelArgs b = a;
+        b.todo = lease.ptr;
+        const int fb = fallback_degridder_variant(a.subgrid_size, a.nr_channels);
+        e = fb == 4 ? launch_t<256, 8, 3, 2>(b, sincos_mode, stream)
+            : fb == 24 ? launch_degridder_tc8(b, true, true, stream) : launch_degridder_tc(b, 10, true, stream);
+      }
+      const cudaError_t e2 = scratch_release(lease, stream);
+      return e != cudaSuccess ? e : e2;
+    }
     default: return cudaErrorInvalidValue;
   }
 }

@@ -1,0 +1,345 @@
+// IDG degridder in row-column form on tcgen05 + TMEM (variant 30, the default for FAST sincos and
+// subgrids of up to 32 x 32 pixels).
+//
+// The transpose of gridder_sep.cu.  With the phase split into a column and a row part (see there; the
+// degridder's sign: degridder_reference.cpp:96-112),
+//   vis_v[p] = sum_y Y_v(y) [ sum_x X_v(x) P'[y][x][p] ],      P' = A1 (sph . subgrid) A2^H   (:38-74)
+//   X_v(x) = exp i[(u l_x + w f(l_x^2)) k_c - (u_off l_x + w_off f(l_x^2))],   Y_v(y) likewise with v, m_y
+// (subgrids whose dropped phase term |gamma| r exceeds SEP_PHASE_TOL are left to the per-pixel kernel
+// launched behind this one).  The inner sum is a GEMM per tile of 128 visibilities,
+//   Q[v][(y, p, re|im)] = A[v][(x, cos|sin)] * B[(x, cos|sin)][(y, p, re|im)]      M = 128, K = 2 N, N = 8 N
+//     A = X in fp16 hi + lo (32 phasors per visibility instead of 1024: three-term recurrence over equally
+//         spaced channels, else one sincos per channel),
+//     B = P' in fp16 hi + lo, built once per subgrid (power-of-two scaling into fp16 range),
+//     three products per K step (hi hi, lo hi, hi lo): the operands keep ~22 bits, which the reference's
+//     smooth degridder input needs (its visibilities are small sums of large terms: DESIGN.md 4.6),
+// and the outer sum runs on the CUDA cores straight out of TMEM: thread = visibility (TMEM lane = row), one
+// sincos per (visibility, row y), four complex multiply-adds, then one coalesced 32-byte store per visibility:
+// every visibility of the subgrid's time range is written exactly once.
+//
+// CTA = one subgrid, 4 warps, 2 CTAs per SM (256 TMEM columns each): per tile the warps make the A rows
+// (lane = column x, 32 rows per warp), one thread issues the 12 MMAs, and when they have completed every
+// thread finishes its visibility; while one CTA waits for its MMAs the other one computes.
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+#include "kernels.h"
+#include "tc_common.cuh"
+
+namespace idgb200 {
+
+namespace {
+
+constexpr int DS_THREADS = 128;
+constexpr int DS_A_CH = 128 * 16 + 16;           // one 16-byte K chunk of 128 rows, padded: the 8 chunks a warp's
+                                                 // 4-byte stores touch fall into different banks
+constexpr float SEP_PHASE_TOL = 1e-4f;           // largest dropped phase |gamma| r (rad), as in gridder_sep.cu
+
+__device__ __forceinline__ unsigned pack_h2(const float lo, const float hi) {
+  const __half2 h = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<const unsigned *>(&h);
+}
+__device__ __forceinline__ float residual_h(const float x, const unsigned short h) {
+  const unsigned short minus_one = 0xbc00u;
+  float r;
+  asm("fma.rn.f32.f16 %0, %1, %2, %3;" : "=f"(r) : "h"(h), "h"(minus_one), "f"(x));
+  return r;
+}
+
+__global__ void __launch_bounds__(DS_THREADS, 2)
+degridder_sep_kernel(const KernelArgs a, const int tmem_cols, int *__restrict__ todo) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const int N = a.subgrid_size, C = a.nr_channels, npix = N * N;
+  const int s_local = blockIdx.x, s = a.subgrid_offset + s_local;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  const int KC = N >> 2, KCp = (KC + 1) & ~1;      // 16-byte K chunks (4 columns x (cos, sin)); K steps of 2 chunks
+  const int ncols = 8 * N;                         // n = y * 8 + p * 2 + (re|im)
+  const int b_ch = ncols * 16 + 16;                // one K chunk of B, padded like DS_A_CH
+  const int ncb = (C + 7) >> 3;
+
+  unsigned char *sB = smem;                                             // [hi|lo][KCp][b_ch]
+  unsigned char *sA = sB + 2 * KCp * b_ch;                              // [hi|lo][KCp][DS_A_CH]
+  float4 *sGeo = reinterpret_cast<float4 *>(sA + 2 * KCp * DS_A_CH);    // [N] (m_y, f(m_y^2), offset_y, 0)
+  unsigned long long *mma_done = reinterpret_cast<unsigned long long *>(sGeo + N);
+  unsigned *s_tmem = reinterpret_cast<unsigned *>(mma_done + 1);
+  float *s_red = reinterpret_cast<float *>(s_tmem + 2);                 // [16]
+  float *s_wn = s_red + 16;                                             // [ncb * 8]
+  float *s_dw = s_wn + ncb * 8;                                         // [ncb]
+  int *s_lin = reinterpret_cast<int *>(s_dw + ncb);                     // [ncb]
+
+  const SubgridCtx ctx = load_ctx(a, s);
+  const int nt = ctx.nr_timesteps;
+  const int nvis = nt * C;
+  const int ntiles = (nvis + 127) >> 7;
+  const float *g_uvw = reinterpret_cast<const float *>(a.uvw) + (size_t)ctx.time_offset * 3;
+
+  for (int c = tid; c < ncb * 8; c += DS_THREADS) s_wn[c] = c < C ? a.wavenumbers[c] : 0.f;
+  if (tid < N) {
+    const float m = compute_l(tid, N, a.image_size);
+    const float n_y = compute_n(m, 0.f);
+    sGeo[tid] = make_float4(m, n_y, __fmaf_rn(ctx.w_offset, n_y, __fmul_rn(ctx.v_offset, m)), 0.f);
+  }
+  if (tid == 0) {
+    mbar_init(mma_done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  // ---- separability check (gridder_sep.cu) and channel layout
+  {
+    float wmax = 0.f;
+    for (int t = tid; t < nt; t += DS_THREADS) wmax = fmaxf(wmax, fabsf(__ldg(&g_uvw[3 * t + 2])));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) wmax = fmaxf(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
+    if (lane == 0) s_red[warp] = wmax;
+    for (int cb = tid; cb < ncb; cb += DS_THREADS) {
+      float dw;
+      s_lin[cb] = linear_channels(s_wn, cb * 8, min(8, C - cb * 8), &dw) ? 1 : 0;
+      s_dw[cb] = dw;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      for (int i = 1; i < 4; i++) wmax = fmaxf(wmax, s_red[i]);
+      float kmax = 0.f;
+      for (int c = 0; c < C; c++) kmax = fmaxf(kmax, fabsf(s_wn[c]));
+      const double l0 = (0.5 - (N / 2)) * (double)a.image_size / (double)N;
+      const double s1 = l0 * l0;
+      const double fn = s1 / (1.0 + sqrt(1.0 - s1)), s2 = 2.0 * s1;
+      const double r = s2 > 1.0 ? 1.0 : fabs(s2 / (1.0 + sqrt(1.0 - s2)) - 2.0 * fn);
+      const double gmax = (double)fabsf(ctx.w_offset) + (double)wmax * (double)kmax;
+      const bool sep = gmax * r <= (double)SEP_PHASE_TOL && isfinite(gmax);
+      s_red[12] = sep ? 1.f : 0.f;
+      todo[s_local] = sep ? 0 : 1;
+    }
+    __syncthreads();
+  }
+  if (s_red[12] == 0.f) return;          // the per-pixel kernel behind this launch takes the subgrid
+  if (nvis == 0) return;
+
+  // ---- B = P' (degridder_reference.cpp:38-74) in fp16 hi + lo; the fp32 pixels wait in the A buffer
+  {
+    const size_t plane = (size_t)npix;
+    const size_t at1 = ((size_t)ctx.aterm_index * a.nr_stations + ctx.station1) * plane;
+    const size_t at2 = ((size_t)ctx.aterm_index * a.nr_stations + ctx.station2) * plane;
+    const float2 *sub = a.subgrids + (size_t)s * NR_POL * plane;
+    float4 *sT = reinterpret_cast<float4 *>(sA);     // [npix][2]: 32 N^2 <= 2 KCp DS_A_CH for N <= 32
+    float amax = 0.f;
+    for (int q = tid; q < npix; q += DS_THREADS) {
+      const float sph = __ldg(&a.spheroidal[q]);
+      const int src = subgrid_slot(q, N, a.flags);
+      float2 px[NR_POL];
+#pragma unroll
+      for (int p = 0; p < NR_POL; p++) {
+        const float2 v = __ldg(&sub[p * plane + src]);
+        px[p] = make_float2(__fmul_rn(sph, v.x), __fmul_rn(sph, v.y));
+      }
+      float2 a1[4], a2[4];
+      load_jones(a.aterms, (at1 + q) * NR_POL, a1);
+      load_jones(a.aterms, (at2 + q) * NR_POL, a2);
+      apply_aterm_degridder(px, a1, a2);
+      sT[2 * q] = make_float4(px[0].x, px[0].y, px[1].x, px[1].y);
+      sT[2 * q + 1] = make_float4(px[2].x, px[2].y, px[3].x, px[3].y);
+#pragma unroll
+      for (int p = 0; p < NR_POL; p++) amax = fmaxf(amax, fmaxf(fabsf(px[p].x), fabsf(px[p].y)));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+    if (lane == 0) s_red[warp] = amax;
+    __syncthreads();
+    if (tid == 0) {
+      for (int i = 1; i < 4; i++) amax = fmaxf(amax, s_red[i]);
+      const unsigned eb = (__float_as_uint(amax) >> 23) & 0xffu;
+      const bool ok = eb >= 14u && eb <= 253u;
+      s_red[10] = ok ? __uint_as_float((267u - eb) << 23) : 1.f;           // 2^(13 - E)
+      s_red[11] = ok ? __uint_as_float((eb - 13u) << 23) : 1.f;            // 2^(E - 13)
+    }
+    __syncthreads();
+    const float scale = s_red[10];
+    for (int q = tid; q < npix; q += DS_THREADS) {
+      const int y = q / N, x = q - y * N;
+      const float4 v01 = sT[2 * q], v23 = sT[2 * q + 1];
+      const float pv[8] = {v01.x, v01.y, v01.z, v01.w, v23.x, v23.y, v23.z, v23.w};
+      unsigned char *col = sB + (x >> 2) * b_ch + (x & 3) * 4 + (y * 8) * 16;
+#pragma unroll
+      for (int p = 0; p < NR_POL; p++) {
+        const float re = pv[2 * p] * scale, im = pv[2 * p + 1] * scale;
+        // row (y, p, re): (re, -im) against (cos, sin); row (y, p, im): (im, re)
+        const unsigned h_im = pack_h2(im, re);
+        const unsigned h_re = pack_h2(re, -im);
+        const float r_im = residual_h(im, (unsigned short)(h_im & 0xffffu));
+        const float r_re = residual_h(re, (unsigned short)(h_im >> 16));
+        unsigned char *row = col + (2 * p) * 16;
+        *reinterpret_cast<unsigned *>(row) = h_re;
+        *reinterpret_cast<unsigned *>(row + 16) = h_im;
+        *reinterpret_cast<unsigned *>(row + KCp * b_ch) = pack_h2(r_re, -r_im);
+        *reinterpret_cast<unsigned *>(row + KCp * b_ch + 16) = pack_h2(r_im, r_re);
+      }
+    }
+    __syncthreads();                    // the fp32 pixels have been read: the A buffer is free
+    if (KCp != KC) {                    // the K padding: zero in A (never written again) and in B
+      for (int i = tid; i < 128 * 4; i += DS_THREADS) {
+        *reinterpret_cast<unsigned *>(sA + KC * DS_A_CH + i * 4) = 0u;
+        *reinterpret_cast<unsigned *>(sA + (KCp + KC) * DS_A_CH + i * 4) = 0u;
+      }
+      for (int i = tid; i < ncols * 4; i += DS_THREADS) {
+        *reinterpret_cast<unsigned *>(sB + KC * b_ch + i * 4) = 0u;
+        *reinterpret_cast<unsigned *>(sB + (KCp + KC) * b_ch + i * 4) = 0u;
+      }
+    }
+  }
+  const float unscale = s_red[11];
+
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(tmem_cols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const unsigned tmem_base = *s_tmem;
+
+  // lane = column x of the A operand
+  const int xl = min(lane, N - 1);
+  const float l = compute_l(xl, N, a.image_size);
+  const float n_x = compute_n(l, 0.f);
+  const float off_x = __fmaf_rn(ctx.w_offset, n_x, __fmul_rn(ctx.u_offset, l));
+  unsigned char *a_col = sA + (lane >> 2) * DS_A_CH + (lane & 3) * 4;
+  // instruction descriptor: D = F32, A = B = F16, K-major, N = 8 N, M = 128
+  const unsigned idesc = (1u << 4) | (((unsigned)ncols >> 3) << 17) | ((128u >> 4) << 24);
+  float2 *g_out = const_cast<float2 *>(a.visibilities) + (size_t)ctx.time_offset * C * NR_POL;
+
+  for (int tile = 0; tile < ntiles; tile++) {
+    // ---- A rows 32 warp .. + 31 of the tile: X_v(x), v = flat (t, c) index, hi + lo
+    {
+      int gv = tile * 128 + warp * 32;
+      int t = gv / C, c = gv - t * C;
+      float2 cur = make_float2(0.f, 0.f), prev = cur;
+      float c2 = 0.f, idx = 0.f;
+      bool start = true;
+      for (int i = 0; i < 32; i++, gv++) {
+        unsigned hi = 0u, lo = 0u;
+        if (gv < nvis) {
+          const int cb = c >> 3;
+          const bool lin = s_lin[cb] != 0;
+          if (start || (c & 7) == 0) {
+            if (start || c == 0) idx = __fmaf_rn(__ldg(&g_uvw[3 * t + 2]), n_x, __fmul_rn(__ldg(&g_uvw[3 * t]), l));
+            cur = phasor<IDGB200_SINCOS_FAST>(__fmaf_rn(idx, s_wn[c], -off_x));
+            if (lin) {   // prev = cur * conj(d), d = e^{i idx dw}: the three-term recurrence runs from here
+              const float2 d = phasor<IDGB200_SINCOS_FAST>(__fmul_rn(idx, s_dw[cb]));
+              prev = make_float2(__fmaf_rn(cur.x, d.x, __fmul_rn(cur.y, d.y)), __fmaf_rn(cur.y, d.x, -__fmul_rn(cur.x, d.y)));
+              c2 = __fadd_rn(d.x, d.x);
+            }
+            start = false;
+          } else if (lin) {
+            const float2 nxt = ffma2(cur, make_float2(c2, c2), make_float2(-prev.x, -prev.y));
+            prev = cur;
+            cur = nxt;
+          } else {
+            cur = phasor<IDGB200_SINCOS_FAST>(__fmaf_rn(idx, s_wn[c], -off_x));
+          }
+          hi = pack_h2(cur.x, cur.y);
+          lo = pack_h2(residual_h(cur.x, (unsigned short)(hi & 0xffffu)), residual_h(cur.y, (unsigned short)(hi >> 16)));
+          if (++c == C) { c = 0; t++; }
+        }
+        if (lane < N) {
+          unsigned char *row = a_col + (warp * 32 + i) * 16;
+          *reinterpret_cast<unsigned *>(row) = hi;
+          *reinterpret_cast<unsigned *>(row + KCp * DS_A_CH) = lo;
+        }
+      }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (elect_one()) {
+        const unsigned a_u = smem_u32(sA), b_u = smem_u32(sB);
+        for (int ks = 0; ks < KCp / 2; ks++) {
+          const unsigned long long a_hi = smem_desc(a_u + 2 * ks * DS_A_CH, DS_A_CH, 128);
+          const unsigned long long a_lo = smem_desc(a_u + (KCp + 2 * ks) * DS_A_CH, DS_A_CH, 128);
+          const unsigned long long b_hi = smem_desc(b_u + 2 * ks * b_ch, b_ch, 128);
+          const unsigned long long b_lo = smem_desc(b_u + (KCp + 2 * ks) * b_ch, b_ch, 128);
+          umma_f16(tmem_base, a_hi, b_hi, idesc, ks > 0 ? 1u : 0u);
+          umma_f16(tmem_base, a_lo, b_hi, idesc, 1u);
+          umma_f16(tmem_base, a_hi, b_lo, idesc, 1u);
+        }
+        umma_commit(mma_done);
+      }
+      __syncwarp();
+    }
+    mbar_wait(mma_done, tile & 1);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+    // ---- the sum over the rows y: thread = visibility tid of the tile
+    {
+      const int gv = tile * 128 + tid;
+      const bool valid = gv < nvis;
+      const int t = valid ? gv / C : 0, c = valid ? gv - t * C : 0;
+      const float k = s_wn[c];
+      const float vt = __ldg(&g_uvw[3 * t + 1]), wt = __ldg(&g_uvw[3 * t + 2]);
+      float2 acc[NR_POL];
+#pragma unroll
+      for (int p = 0; p < NR_POL; p++) acc[p] = make_float2(0.f, 0.f);
+      for (int y0 = 0; y0 < N; y0 += 4) {
+        unsigned r[32];
+        const unsigned taddr = tmem_base + ((unsigned)(warp * 32) << 16) + y0 * 8;
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+            "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+              "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+              "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+              "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+            : "r"(taddr));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int yy = 0; yy < 4; yy++) {
+          const float4 g = sGeo[y0 + yy];           // broadcast
+          const float idx = __fmaf_rn(wt, g.y, __fmul_rn(vt, g.x));
+          const float2 ph = phasor<IDGB200_SINCOS_FAST>(__fmaf_rn(idx, k, -g.z));
+          const float2 phs = make_float2(-ph.y, ph.x);
+#pragma unroll
+          for (int p = 0; p < NR_POL; p++) {      // acc += Q * ph: (qr, qr) * (c, s) + (qi, qi) * (-s, c)
+            const float qr = __uint_as_float(r[yy * 8 + 2 * p]), qi = __uint_as_float(r[yy * 8 + 2 * p + 1]);
+            acc[p] = ffma2(make_float2(qr, qr), ph, acc[p]);
+            acc[p] = ffma2(make_float2(qi, qi), phs, acc[p]);
+          }
+        }
+      }
+      if (valid) {
+        float4 *o = reinterpret_cast<float4 *>(g_out + (size_t)gv * NR_POL);
+        o[0] = make_float4(acc[0].x * unscale, acc[0].y * unscale, acc[1].x * unscale, acc[1].y * unscale);
+        o[1] = make_float4(acc[2].x * unscale, acc[2].y * unscale, acc[3].x * unscale, acc[3].y * unscale);
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();                  // accumulator and A buffer are free for the next tile
+  }
+  if (warp == 0)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols));
+}
+
+}  // namespace
+
+bool degridder_sep_supports(int subgrid_size, int nr_channels) {
+  return subgrid_size >= 4 && subgrid_size % 4 == 0 && subgrid_size <= 32 && nr_channels >= 1 && nr_channels <= 4096;
+}
+
+// d_todo[nr_subgrids] (device): written by this launch - 0 = degridded here, 1 = left to the per-pixel kernel
+// launched behind this one
+cudaError_t launch_degridder_sep(const KernelArgs &a, int *d_todo, cudaStream_t stream) {
+  if (a.nr_subgrids == 0) return cudaSuccess;
+  if (!degridder_sep_supports(a.subgrid_size, a.nr_channels) || !d_todo) return cudaErrorInvalidValue;
+  const int N = a.subgrid_size, KC = N / 4, KCp = (KC + 1) & ~1, ncols = 8 * N, ncb = (a.nr_channels + 7) / 8;
+  int tmem_cols = 32;
+  while (tmem_cols < ncols) tmem_cols *= 2;
+  const size_t smem = (size_t)2 * KCp * (ncols * 16 + 16) + (size_t)2 * KCp * DS_A_CH + (size_t)N * 16 + 8 + 8 + 64 +
+                      (size_t)ncb * 10 * 4;
+  cudaError_t e = cudaFuncSetAttribute(degridder_sep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  degridder_sep_kernel<<<dim3((unsigned)a.nr_subgrids), dim3(DS_THREADS), smem, stream>>>(a, tmem_cols, d_todo);
+  return cudaGetLastError();
+}
+
+}  // namespace idgb200

@@ -138,6 +138,7 @@ __device__ __forceinline__ void dtc_produce_linear(unsigned char *A, const float
 template <unsigned MASK8, bool SPLIT>
 __global__ void __launch_bounds__(D_THREADS, 3)
 degridder_tc_kernel(const KernelArgs a, const int recur) {
+  if (a.todo && !a.todo[blockIdx.x]) return;   // degridder_sep.cu has degridded this subgrid
   extern __shared__ __align__(1024) unsigned char smem[];
   const int N = a.subgrid_size, C = a.nr_channels, npix = N * N;
   const int s = a.subgrid_offset + blockIdx.x;
@@ -379,7 +380,8 @@ degridder_tc_kernel(const KernelArgs a, const int recur) {
 
 }  // namespace
 
-// poly: 0 = all phasors by MUFU; 1..3 = 2, 3, 4 of every 8 pixels by FP32 polynomial;
+// poly: (0..3 = fp16 phasors, by MUFU or partly by FP32 polynomial: outside the stated tolerance on the
+//       reference's degridder input, DESIGN.md 4.6 - no longer built);
 //       10 = fp16 hi + lo phasors (FP32-class accuracy)
 // recur: quads of equally spaced channels get their phasors by rotation
 cudaError_t launch_degridder_tc(const KernelArgs &a, int poly, bool recur, cudaStream_t stream) {
@@ -388,10 +390,6 @@ cudaError_t launch_degridder_tc(const KernelArgs &a, int poly, bool recur, cudaS
                       (D_MAX_TILES * D_STAGES + 2 * D_NG + 1) * 8 + 8 + 48;
   void (*k)(const KernelArgs, int) = nullptr;
   switch (poly) {
-    case 0: k = degridder_tc_kernel<0x00u, false>; break;
-    case 1: k = degridder_tc_kernel<0x44u, false>; break;   // 2 of 8 pixels
-    case 2: k = degridder_tc_kernel<0x92u, false>; break;   // 3 of 8
-    case 3: k = degridder_tc_kernel<0xAAu, false>; break;   // 4 of 8
     case 10: k = degridder_tc_kernel<0x00u, true>; break;   // hi + lo phasors
     default: return cudaErrorInvalidValue;
   }

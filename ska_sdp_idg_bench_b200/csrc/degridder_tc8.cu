@@ -135,6 +135,7 @@ __device__ __forceinline__ void etc_produce(unsigned char *A, const float4 *geo,
 
 __global__ void __launch_bounds__(E_THREADS, 3)
 degridder_tc8_kernel(const KernelArgs a, const int recur, const int fold_ok) {
+  if (a.todo && !a.todo[blockIdx.x]) return;   // degridder_sep.cu has degridded this subgrid
   extern __shared__ __align__(1024) unsigned char smem[];
   const int N = a.subgrid_size, C = a.nr_channels, npix = N * N;
   const int s = a.subgrid_offset + blockIdx.x;

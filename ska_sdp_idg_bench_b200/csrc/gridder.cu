@@ -33,9 +33,6 @@
 //  * phase_offset is hoisted out of the time loop (it does not depend on t) and phase /
 //    phase_index are evaluated in the CPU binary's operation order, so the angle fed to
 //    sincos is bit-identical to the reference's.
-#include <atomic>
-#include <mutex>
-
 #include "common.cuh"
 #include "kernels.h"
 
@@ -354,64 +351,17 @@ cudaError_t launch_t(const KernelArgs &a, int mode, cudaStream_t stream, const i
 
 }  // namespace
 
-// variant: 0 default: FAST sincos and a shape that fills >= 3/4 of its 8-channel blocks and
-//            128-pixel tiles -> tensor-core kernel (= variant 24, or 21 for an odd number of
-//            8-channel blocks; gridder_tc.cu); otherwise the FP32 kernel (= variant 10)
-//         10 FP32 kernel: swizzled FFMA2; 128 threads x 8 pixels (x 4 blocks/SM) when the
+// variant: 0 default: FAST sincos -> 30, the row-column kernel (gridder_sep.cu; subgrid sizes that are a multiple
+//            of 4), else the per-pixel tensor-core kernel (24 / 21) where the shape fills >= 3/4 of its
+//            8-channel blocks and 128-pixel tiles, else 10; other sincos modes -> 10
+//         10 FP32 kernel (this file): swizzled FFMA2; 128 threads x 8 pixels (x 4 blocks/SM) when the
 //            subgrid has >= 1024 pixels, 128 x 4 below that
-//         11 tensor-core kernel (FAST sincos only), every phasor by MUFU
-//         12 tensor-core kernel, 4 of every 16 channels' phasors by FP32 polynomial (13: 5, 14: 6, 15: 8)
-//         21 tensor-core kernel; blocks of 8 equally spaced channels get their phasors by complex
-//            rotation from the block's first channel (2 sincos per pixel and block instead of 8, as
-//            the reference's gridder_v8.cu does unconditionally), other blocks as variant 14
+//         21 per-pixel tensor-core kernel (gridder_tc.cu, FAST sincos only); blocks of 8 equally spaced channels
+//            get their phasors by rotation + three-term recurrence, other blocks by MUFU / FP32 polynomial
 //         24 the same with two channel blocks (K = 32) per stage, single-buffered
-//         22 / 23 as 21 / 11 with fp16 hi + lo phasors (FP32-class accuracy)
-//          1 scalar-FFMA baseline (256 x 4)
-//          2 swizzled FFMA2, 256 threads x 4 pixels
-//          3 swizzled FFMA2, 256 threads x 8 pixels
-//          4 first design: FFMA2 on duplicated records, rotated sums, software pipelined (256 x 4)
-//          5 swizzled FFMA2, 128 threads x 8 pixels, 3 blocks/SM (more registers)
-// One int per launch for variant 26's device-side decision, from a ring that is allocated once per
-// device: the three kernels of a launch are stream-ordered, and 4096 launches would have to be in
-// flight at once for a slot to be reused too early.
-static int *regular_flag_slot() {
-  static std::mutex mu;
-  static int *ring[64] = {};
-  static std::atomic<unsigned> next{0};
-  constexpr unsigned kSlots = 4096;
-  int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
-  {
-    std::lock_guard<std::mutex> lock(mu);
-    if (!ring[dev] && cudaMalloc(&ring[dev], kSlots * sizeof(int)) != cudaSuccess) return nullptr;
-  }
-  return ring[dev] + (next.fetch_add(1) % kSlots);
-}
-
-// The fold / general subgrid lists of a variant-29 launch (gridder_fold.cu): 2 + 2 nr_subgrids ints out of a
-// per-device ring of 32 buffers that grow on demand (cudaFree waits for the device, so a buffer is never
-// pulled from under a running kernel).  Launches on one stream are ordered, so a buffer can only be
-// reused too early if 32 such launches were in flight at once on different streams.
-static int *subgrid_lists_slot(size_t count_ints) {
-  static std::mutex mu;
-  struct Buf { int *p; size_t cap; };
-  static Buf ring[64][32] = {};
-  static unsigned next[64] = {};
-  int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
-  std::lock_guard<std::mutex> lock(mu);
-  Buf &b = ring[dev][next[dev]++ % 32];
-  if (b.cap < count_ints) {
-    if (b.p) cudaFree(b.p);
-    b.p = nullptr;
-    b.cap = 0;
-    const size_t cap = count_ints < (1u << 16) ? (1u << 16) : count_ints + count_ints / 2;
-    if (cudaMalloc(&b.p, cap * sizeof(int)) != cudaSuccess) return nullptr;
-    b.cap = cap;
-  }
-  return b.p;
-}
-
+//         22 / 23 as 21 with fp16 hi + lo phasors (FP32-class accuracy), with / without the recurrence
+//         30 gridder_sep.cu with the per-pixel kernel of the shape (24 / 21 / 10) behind it for the subgrids
+//            it declines
 // the per-pixel kernel of a FAST launch: 24 / 21 (gridder_tc.cu) where the shape fills its tiles, else the FP32 kernel
 static int fallback_gridder_variant(int subgrid_size, int nr_channels) {
   const int npix = subgrid_size * subgrid_size;
@@ -446,9 +396,6 @@ cudaError_t launch_gridder(const KernelArgs &a, int sincos_mode, int variant, cu
     case 10:
       nk = 1;
       return launch_gridder_fp32(a, sincos_mode, stream);
-    case 11: case 12: case 13: case 14: case 15:   // 12..15: 4, 5, 6, 8 of 16 phasors by FP32 polynomial
-      nk = 1;
-      return fast ? launch_gridder_tc(a, variant - 11, false, stream) : cudaErrorInvalidValue;
     case 22:   // as 21 with fp16 hi + lo phasors (FP32-class accuracy); 23: the same without the rotation
       nk = 1;
       return fast ? launch_gridder_tc(a, 10, true, stream) : cudaErrorInvalidValue;
@@ -461,32 +408,6 @@ cudaError_t launch_gridder(const KernelArgs &a, int sincos_mode, int variant, cu
     case 21:   // tensor-core kernel, phasors of equally spaced channel blocks by rotation (else as 12)
       nk = 1;
       return fast ? launch_gridder_tc(a, 3, true, stream) : cudaErrorInvalidValue;
-    case 26:     // gridder_tc8.cu where the channel layout is regular (decided on the device), else 24
-    case 27: {   // gridder_tc4.cu (phasor operand in TMEM) likewise
-      if (!fast) return cudaErrorInvalidValue;
-      int *flag = regular_flag_slot();
-      if (!flag) return cudaErrorMemoryAllocation;
-      nk = 3;
-      e = launch_gridder_regular_check(a, flag, stream);
-      if (e == cudaSuccess) e = variant == 26 ? launch_gridder_tc8(a, flag, stream) : launch_gridder_tc4(a, flag, stream);
-      if (e == cudaSuccess) e = launch_gridder_tc(a, 11, true, stream, flag);
-      return e;
-    }
-    case 29: {   // gridder_fold.cu for the planar subgrids of a regular channel layout, 24 for the others
-      if (!fast) return cudaErrorInvalidValue;
-      nk = 1;
-      if ((a.nr_channels & 15) || (a.subgrid_size & 1) || a.nr_channels > 1024) return launch_gridder_tc(a, 11, true, stream);
-      int *flag = regular_flag_slot();
-      if (!flag) return cudaErrorMemoryAllocation;
-      int *lists = subgrid_lists_slot(2 + 2 * (size_t)a.nr_subgrids);   // { n_fold, n_general, fold[], general[] }
-      if (!lists) return cudaErrorMemoryAllocation;
-      nk = 4;
-      e = launch_gridder_regular_check(a, flag, stream, lists);   // also zeroes the two counts
-      if (e == cudaSuccess) e = launch_gridder_planar_check(a, flag, lists, stream);
-      if (e == cudaSuccess) e = launch_gridder_fold(a, lists, stream);
-      if (e == cudaSuccess) e = launch_gridder_tc(a, 11, true, stream, nullptr, lists);
-      return e;
-    }
     case 30: {   // gridder_sep.cu (row-column form); subgrids it declines go to the per-pixel kernel behind it
       if (!fast || !gridder_sep_supports(a.subgrid_size, a.nr_channels)) return cudaErrorInvalidValue;
       ScratchLease lease;
@@ -497,14 +418,11 @@ cudaError_t launch_gridder(const KernelArgs &a, int sincos_mode, int variant, cu
       if (e == cudaSuccess) {
         const int fb = fallback_gridder_variant(a.subgrid_size, a.nr_channels);
         e = fb == 10 ? launch_gridder_fp32(a, sincos_mode, stream, lease.ptr)
-                     : launch_gridder_tc(a, fb == 24 ? 11 : 3, true, stream, nullptr, nullptr, lease.ptr);
+                     : launch_gridder_tc(a, fb == 24 ? 11 : 3, true, stream, lease.ptr);
       }
       const cudaError_t e2 = scratch_release(lease, stream);
       return e != cudaSuccess ? e : e2;
     }
-    case 16: case 17: case 18: case 19:   // phasor tile in TMEM; 18, 19: fp16 hi + lo phasors
-      nk = 1;
-      return fast ? launch_gridder_tc3(a, variant - 16, stream) : cudaErrorInvalidValue;
     default: return cudaErrorInvalidValue;
   }
 }

@@ -143,15 +143,10 @@ __device__ __forceinline__ void tc_produce_linear(unsigned char *A, const float 
 template <unsigned MASK16, bool SPLIT, bool WIDE = false>
 __global__ void __launch_bounds__(T2_THREADS, 3)
 gridder_tc_kernel(const KernelArgs a, const int slabs, const int tiles_per_cta, const int tmem_cols, const int recur,
-                  const int *__restrict__ skip_flag, const int *__restrict__ lists, const int *__restrict__ todo) {
-  if (skip_flag && *skip_flag) return;   // gridder_tc8.cu has served this (regular) channel layout
-  int s_local = blockIdx.x / slabs;
+                  const int *__restrict__ todo) {
+  const int s_local = blockIdx.x / slabs;
   if (todo && !todo[s_local]) return;    // gridder_sep.cu has gridded this subgrid
   const int slab = blockIdx.x - s_local * slabs;
-  if (lists) {   // gridder_fold.cu has served the fold list: this launch takes the general list (gridder_fold.cu)
-    if (s_local >= lists[1]) return;
-    s_local = lists[2 + a.nr_subgrids + s_local];
-  }
   extern __shared__ __align__(1024) unsigned char smem[];
   const int N = a.subgrid_size, C = a.nr_channels, npix = N * N;
   const int s = a.subgrid_offset + s_local;
@@ -472,12 +467,11 @@ gridder_tc_kernel(const KernelArgs a, const int slabs, const int tiles_per_cta, 
 }  // namespace
 
 // FAST sincos only: the fp16 phasor operand is a FAST-class approximation.
-// poly: 0 = all phasors by MUFU; 1..4 = 4, 5, 6, 8 of every 16 channels by FP32 polynomial;
-//       10 = fp16 hi + lo phasors (FP32-class accuracy), all by MUFU / rotation;
-//       11 = as 3 with 16 channels (K = 32) per stage
+// poly: 3 = where the recurrence does not apply, 6 of every 16 channels' phasors by FP32 polynomial, the rest by
+//       MUFU (the measured optimum: DESIGN.md 4.5); 10 = fp16 hi + lo phasors (FP32-class accuracy), all by
+//       MUFU / rotation; 11 = as 3 with 16 channels (K = 32) per stage
 // recur: blocks of 8 equally spaced channels get their phasors by rotation from the first one
-cudaError_t launch_gridder_tc(const KernelArgs &a, int poly, bool recur, cudaStream_t stream, const int *skip_flag,
-                              const int *lists, const int *todo) {
+cudaError_t launch_gridder_tc(const KernelArgs &a, int poly, bool recur, cudaStream_t stream, const int *todo) {
   if (a.nr_subgrids == 0) return cudaSuccess;
   const int npix = a.subgrid_size * a.subgrid_size;
   const int tiles_total = (npix + 127) / 128;
@@ -491,20 +485,16 @@ cudaError_t launch_gridder_tc(const KernelArgs &a, int poly, bool recur, cudaStr
   const size_t smem = (size_t)tiles_per_cta * T2_STAGES * T2_A_STAGE + T2_NB * T2_B_SLOT +
                       (T2_MAX_TILES * T2_STAGES + T2_NB + 3) * 8 + 8 + 48 + (size_t)ncb * (T2_CB + 2) * 4;
   if (smem > 200 * 1024) return cudaErrorInvalidValue;
-  void (*k)(const KernelArgs, int, int, int, int, const int *, const int *, const int *) = nullptr;
+  void (*k)(const KernelArgs, int, int, int, int, const int *) = nullptr;
   switch (poly) {
-    case 0: k = gridder_tc_kernel<0x0000u, false>; break;
-    case 1: k = gridder_tc_kernel<0x4444u, false>; break;   // 4 of 16: channels 2,6,10,14
-    case 2: k = gridder_tc_kernel<0x2492u, false>; break;   // 5 of 16: 1,4,7,10,13
-    case 3: k = gridder_tc_kernel<0x5252u, false>; break;   // 6 of 16: 1,4,6 | 9,12,14
-    case 4: k = gridder_tc_kernel<0x5555u, false>; break;   // 8 of 16
+    case 3: k = gridder_tc_kernel<0x5252u, false>; break;   // 6 of 16 by polynomial: channels 1,4,6 | 9,12,14
     case 10: k = gridder_tc_kernel<0x0000u, true>; break;   // fp16 hi + lo phasors
     case 11: k = gridder_tc_kernel<0x5252u, false, true>; break;   // as 3 with K = 32 stages
     default: return cudaErrorInvalidValue;
   }
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  k<<<dim3((unsigned)a.nr_subgrids * nslabs), dim3((producer_warps + 1) * 32), smem, stream>>>(a, nslabs, tiles_per_cta, tmem_cols, recur ? 1 : 0, skip_flag, lists, todo);
+  k<<<dim3((unsigned)a.nr_subgrids * nslabs), dim3((producer_warps + 1) * 32), smem, stream>>>(a, nslabs, tiles_per_cta, tmem_cols, recur ? 1 : 0, todo);
   return cudaGetLastError();
 }
 

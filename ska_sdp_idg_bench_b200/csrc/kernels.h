@@ -35,13 +35,9 @@ cudaError_t launch_subgrid_fft(long long nr_planes, int subgrid_size, int direct
 int resolve_gridder_variant(int subgrid_size, int nr_channels, int sincos_mode, int variant);
 int resolve_degridder_variant(int subgrid_size, int nr_channels, int sincos_mode, int variant);
 
-// tcgen05 / TMEM gridder (gridder_tc.cu); FAST sincos only
-// skip_flag (device, may be null): the kernel returns at once when *skip_flag != 0;
-// lists (device, may be null): gridder_fold.cu's { n_fold, n_general, fold[], general[] }: the launch then
-// serves the subgrids of the general list only
+// per-pixel tcgen05 / TMEM gridder (gridder_tc.cu); FAST sincos only
 // todo (device, may be null): per-subgrid flags of this launch; subgrids whose flag is 0 are skipped
-cudaError_t launch_gridder_tc(const KernelArgs &a, int poly, bool recur, cudaStream_t stream,
-                              const int *skip_flag = nullptr, const int *lists = nullptr, const int *todo = nullptr);
+cudaError_t launch_gridder_tc(const KernelArgs &a, int poly, bool recur, cudaStream_t stream, const int *todo = nullptr);
 // FP32 gridder (gridder.cu) with the same per-subgrid gate
 cudaError_t launch_gridder_fp32(const KernelArgs &a, int sincos_mode, cudaStream_t stream, const int *todo = nullptr);
 // row-column gridder (gridder_sep.cu): one GEMM per subgrid with the visibilities as K.  Writes
@@ -49,24 +45,12 @@ cudaError_t launch_gridder_fp32(const KernelArgs &a, int sincos_mode, cudaStream
 // non-separable phase term is too large)
 bool gridder_sep_supports(int subgrid_size, int nr_channels);
 cudaError_t launch_gridder_sep(const KernelArgs &a, int *d_todo, cudaStream_t stream);
-// two M-tiles per warp, regular channel layouts only (gridder_tc8.cu): the check writes *d_flag = 1 when every
-// 8-channel block is equally spaced with one spacing and the blocks pair up; the kernel is a no-op unless it is set
-// d_zero2 (may be null): two ints the same kernel zeroes (gridder_fold.cu's list counts)
-cudaError_t launch_gridder_regular_check(const KernelArgs &a, int *d_flag, cudaStream_t stream, int *d_zero2 = nullptr);
-cudaError_t launch_gridder_tc8(const KernelArgs &a, const int *d_regular_flag, cudaStream_t stream);
-// phasor operand in TMEM, four tiles per group of four warps (gridder_tc4.cu); regular layouts only, same gate
-cudaError_t launch_gridder_tc4(const KernelArgs &a, const int *d_regular_flag, cudaStream_t stream);
-// planar subgrids folded onto mirror-image pixel pairs (gridder_fold.cu): the planar check sorts the launch's
-// subgrids into d_lists[2 + 2 nr_subgrids] = { n_fold, n_general, fold[], general[] } (counts zeroed before; fold =
-// regular channel layout per *d_regular_flag and a planar subgrid); the kernel serves the fold list
-cudaError_t launch_gridder_planar_check(const KernelArgs &a, const int *d_regular_flag, int *d_lists,
-                                        cudaStream_t stream);
-cudaError_t launch_gridder_fold(const KernelArgs &a, const int *d_lists, cudaStream_t stream);
+// row-column degridder (degridder_sep.cu); d_todo as for launch_gridder_sep (the per-pixel kernels read KernelArgs::todo)
+bool degridder_sep_supports(int subgrid_size, int nr_channels);
+cudaError_t launch_degridder_sep(const KernelArgs &a, int *d_todo, cudaStream_t stream);
 cudaError_t launch_degridder_tc(const KernelArgs &a, int poly, bool recur, cudaStream_t stream);
 // two M-tiles per warp, groups of 8 channels (degridder_tc8.cu); nr_channels % 8 == 0
 cudaError_t launch_degridder_tc8(const KernelArgs &a, bool recur, bool fold, cudaStream_t stream);
-// phasor operand written to TMEM from registers (gridder_tc3.cu)
-cudaError_t launch_gridder_tc3(const KernelArgs &a, int mode, cudaStream_t stream);
 
 // per-launch device scratch (scratch.cu): acquire .. release brackets the enqueue of the kernels that use it
 struct ScratchLease {

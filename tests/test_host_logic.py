@@ -100,7 +100,7 @@ def test_argument_validation():
 
 
 def test_mirror_pixels_have_exactly_negated_direction_cosines():
-    """What the planar paths of gridder_fold.cu / degridder_tc8.cu rest on: with the
+    """What the planar path of degridder_tc8.cu rests on: with the
     reference's formula l = float((x + 0.5 - N/2) * image_size / N) (math.hpp:9-12, double intermediate,
     integer N/2) pixel x and its mirror image N-1-x have exactly negated l for EVEN N - and not for odd N,
     which is why odd subgrid sizes never fold - and the fp32 phase chain of gridder_reference.cpp:61-69
@@ -132,23 +132,25 @@ def test_mirror_pixels_have_exactly_negated_direction_cosines():
 
 # ------------------------------------------------------------------------ sharding
 def test_default_variant_selection():
-    """variant 0: tcgen05 gridder only for FAST sincos and shapes that fill its 8-channel /
-    128-pixel tiles; tcgen05 degridder (fp16 hi + lo phasors) likewise."""
-    assert idg.resolve_variant(32, 16, idg.SINCOS_FAST) == 29    # folded kernel behind its device-side gate, else 24
-    assert idg.resolve_variant(24, 16, idg.SINCOS_FAST) == 29
-    assert idg.resolve_variant(32, 12, idg.SINCOS_FAST) == 24    # two blocks, the second one partial: no folding
-    assert idg.resolve_variant(32, 24, idg.SINCOS_FAST) == 21    # 3 blocks of 8 channels
+    """variant 0: the row-column kernels (30) for FAST sincos and the subgrid sizes they take; behind them and
+    for the other shapes the per-pixel tcgen05 kernels where the shape fills their tiles, else the FP32 kernels;
+    FP32 kernels for the other sincos modes."""
+    assert idg.resolve_variant(32, 16, idg.SINCOS_FAST) == 30
+    assert idg.resolve_variant(24, 16, idg.SINCOS_FAST) == 30
+    assert idg.resolve_variant(8, 1, idg.SINCOS_FAST) == 30
+    assert idg.resolve_variant(64, 9, idg.SINCOS_FAST) == 30
+    assert idg.resolve_variant(18, 16, idg.SINCOS_FAST) == 24    # 18 is not a multiple of 4: per-pixel kernel, K = 32 stages
+    assert idg.resolve_variant(18, 24, idg.SINCOS_FAST) == 21    # 3 blocks of 8 channels
+    assert idg.resolve_variant(18, 9, idg.SINCOS_FAST) == 10     # 9 of 16 channels
     assert idg.resolve_variant(32, 16, idg.SINCOS_ACCURATE) == 10
     assert idg.resolve_variant(32, 16, idg.SINCOS_REDUCED) == 10
-    assert idg.resolve_variant(8, 1, idg.SINCOS_FAST) == 10      # 1 of 8 channels, 64 of 128 pixels
-    assert idg.resolve_variant(32, 9, idg.SINCOS_FAST) == 10     # 9 of 16 channels
-    assert idg.resolve_variant(32, 4096, idg.SINCOS_FAST) == 10  # wavenumber tables beyond the smem budget
-    assert idg.resolve_variant(32, 16, idg.SINCOS_FAST, variant=3) == 3
-    assert idg.resolve_variant(32, 16, idg.SINCOS_FAST, gridder=False) == 24   # groups of 8 channels: two tiles per warp
-    assert idg.resolve_variant(32, 12, idg.SINCOS_FAST, gridder=False) == 22   # quads of 4 channels
+    assert idg.resolve_variant(32, 16, idg.SINCOS_FAST, variant=24) == 24
+    assert idg.resolve_variant(32, 16, idg.SINCOS_FAST, gridder=False) == 30
+    assert idg.resolve_variant(8, 16, idg.SINCOS_FAST, gridder=False) == 30
+    assert idg.resolve_variant(64, 16, idg.SINCOS_FAST, gridder=False) == 24   # beyond 32 x 32: two tiles per warp
+    assert idg.resolve_variant(64, 12, idg.SINCOS_FAST, gridder=False) == 22   # quads of 4 channels
+    assert idg.resolve_variant(18, 1, idg.SINCOS_FAST, gridder=False) == 4     # 1 of 4 channels
     assert idg.resolve_variant(32, 16, idg.SINCOS_ACCURATE, gridder=False) == 4
-    assert idg.resolve_variant(32, 1, idg.SINCOS_FAST, gridder=False) == 4     # 1 of 4 channels
-    assert idg.resolve_variant(8, 16, idg.SINCOS_FAST, gridder=False) == 4     # 64 pixels
 
 
 def test_ska_low_scale_chunk_plan_covers_the_observation_once():

@@ -126,14 +126,18 @@ def test_gridder_sep_cancelling_sums():
 @pytest.mark.parametrize("shape", SHAPES)
 @pytest.mark.parametrize("linear", [False, True])
 def test_degridder_sep_vs_oracle(shape, linear):
-    if idg.resolve_variant(32, 16, FAST, 0, gridder=False) != SEP:
-        pytest.skip("row-column degridder not built yet")
     o = oracle()
     p = random_problem(211, **shape)
     if linear:
         with_linear_channels(p)
     ref = o.degridder(p)
     rows = covered_rows(p)
+    if p.subgrid_size > 32:   # the row-column degridder takes subgrids of up to 32 x 32 pixels
+        with pytest.raises(idg.IdgError):
+            run_degridder(p, FAST, SEP)
+        assert idg.resolve_variant(p.subgrid_size, p.nr_channels, FAST, 0, gridder=False) != SEP
+        assert_close(run_degridder(p, FAST, 0)[rows], ref[rows], 2, FAST, f"degridder default {shape}")
+        return
     got = run_degridder(p, FAST, SEP)
     mx, rms = assert_close(got[rows], ref[rows], 2, FAST, f"degridder sep {shape}")
     print(f"degridder sep {shape} linear={linear}: max rel {mx.max():.2e}, rel rms {rms.max():.2e}")
@@ -141,9 +145,42 @@ def test_degridder_sep_vs_oracle(shape, linear):
     assert np.array_equal(run_degridder(p, FAST, 0), got)
 
 
+def test_degridder_sep_declines_wide_fields():
+    """As test_gridder_sep_declines_wide_fields: subgrids that fail the separability check are degridded by the
+    per-pixel kernel launched behind the row-column one, bit for bit."""
+    o = oracle()
+    p = random_problem(212, subgrid_size=32, nr_channels=16, max_timesteps=30, nr_subgrids=5, image_size=0.2, w_step=0.0)
+    s = int(np.argmax(p.metadata["nr_timesteps"]))
+    t0, nt = int(p.metadata[s]["time_offset"]), int(p.metadata[s]["nr_timesteps"])
+    p.uvw[t0:t0 + nt, 2] = 0.0                      # one planar subgrid
+    ref = o.degridder(p)
+    rows = covered_rows(p)
+    got = run_degridder(p, FAST, SEP)
+    assert_close(got[rows], ref[rows], 2, FAST, "degridder sep wide field")
+    per_pixel = run_degridder(p, FAST, 24)
+    mine = np.zeros(p.total_timesteps, bool)
+    mine[t0:t0 + nt] = True
+    assert np.array_equal(got[rows & ~mine], per_pixel[rows & ~mine])
+    assert not np.array_equal(got[mine], per_pixel[mine])
+
+
+def test_degridder_sep_fft_shift_and_empty():
+    p = with_linear_channels(random_problem(213, subgrid_size=32, nr_channels=16, max_timesteps=20, nr_subgrids=4))
+    plain = run_degridder(p, FAST, SEP)
+    h = p.subgrid_size // 2
+    q = random_problem(213, subgrid_size=32, nr_channels=16, max_timesteps=20, nr_subgrids=4)
+    with_linear_channels(q)
+    q.subgrids[:] = np.roll(p.subgrids, (h, h), axis=(2, 3))
+    out = np.full_like(q.visibilities, np.nan)
+    idg.c_run_degridder(q.nr_subgrids, q.grid_size, q.subgrid_size, q.image_size, q.w_step, q.nr_channels,
+                        q.nr_stations, q.uvw, q.wavenumbers, out, q.spheroidal, q.aterms, q.metadata, q.subgrids,
+                        sincos=FAST, variant=SEP, flags=idg.FLAG_FFT_SHIFT)
+    assert np.array_equal(out, plain)
+    p.metadata["nr_timesteps"] = 0
+    assert not run_degridder(p, FAST, SEP).any()
+
+
 def test_degridder_sep_config1():
-    if idg.resolve_variant(32, 16, FAST, 0, gridder=False) != SEP:
-        pytest.skip("row-column degridder not built yet")
     o = oracle()
     p = o.make_problem()
     ref, ref64 = o.degridder(p), o.degridder_f64(p)
