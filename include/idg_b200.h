@@ -151,7 +151,9 @@ uint64_t idgb200_launch_count(void);
  * [4][rows_per_part][grid_size].  One GPU: nr_parts = 1, rows_per_part = grid_size.
  * N GPUs: part r may be a peer (NVLink) address of the slice rank r owns - the
  * adder's atomics then are the reduce-scatter, the splitter's loads the all-gather.
- * The adder accumulates (the caller zeroes); the splitter overwrites every subgrid pixel. */
+ * The adder accumulates (the caller zeroes); the splitter overwrites every subgrid pixel.
+ * Alignment: 8 bytes (one complex64) is enough for every pointer; 16-byte aligned subgrids / grid parts
+ * get the 16-byte stores / reductions. */
 int idgb200_adder(const idgb200_params *params, const idgb200_metadata *d_metadata,
                   const idgb200_cfloat *d_subgrids, idgb200_cfloat *const *grid_parts,
                   int nr_parts, int rows_per_part, void *stream);

@@ -70,9 +70,14 @@ def launch_count() -> int:
 
 
 def _grid_parts(grid_parts, grid_size, rows_per_part):
+    """Host array of part pointers; tensor parts are checked (CUDA, contiguous, complex64, 4 * rows * grid_size
+    elements), integer device addresses (peer memory) are the caller's responsibility."""
     parts = grid_parts if isinstance(grid_parts, (list, tuple)) else [grid_parts]
     rpp = int(grid_size if rows_per_part is None else rows_per_part)
-    arr = (C.c_void_p * len(parts))(*[int(q) if isinstance(q, int) else q.data_ptr() for q in parts])
+    need = 4 * rpp * int(grid_size) * 8
+    ptrs = [int(q) if isinstance(q, int) else _dev_ptr(q, f"grid part {i}", need, "complex64").value
+            for i, q in enumerate(parts)]
+    arr = (C.c_void_p * len(parts))(*ptrs)
     return arr, len(parts), rpp
 
 
@@ -85,7 +90,9 @@ def adder(nr_subgrids, grid_size, subgrid_size, metadata, subgrids, grid_parts, 
     rows [r * rows_per_part, ...) - addresses may be peer memory of other GPUs."""
     arr, n, rpp = _grid_parts(grid_parts, grid_size, rows_per_part)
     p = _params(nr_subgrids, grid_size, subgrid_size, 1.0, 0.0, 1, 1, SINCOS_FAST, 0, flags)
-    _check(lib.idgb200_adder(C.byref(p), C.c_void_p(metadata.data_ptr()), C.c_void_p(subgrids.data_ptr()),
+    N = int(subgrid_size)
+    _check(lib.idgb200_adder(C.byref(p), _dev_ptr(metadata, "metadata", int(nr_subgrids) * 36, "int32"),
+                             _dev_ptr(subgrids, "subgrids", int(nr_subgrids) * N * N * 32, "complex64"),
                              arr, n, rpp, _stream_ptr(stream)))
 
 
@@ -95,15 +102,19 @@ def splitter(nr_subgrids, grid_size, subgrid_size, metadata, subgrids, grid_part
     the grid value under it (0 outside the grid).  ``grid_parts`` as for :func:`adder`."""
     arr, n, rpp = _grid_parts(grid_parts, grid_size, rows_per_part)
     p = _params(nr_subgrids, grid_size, subgrid_size, 1.0, 0.0, 1, 1, SINCOS_FAST, 0, flags)
-    _check(lib.idgb200_splitter(C.byref(p), C.c_void_p(metadata.data_ptr()),
-                                C.c_void_p(subgrids.data_ptr()), arr, n, rpp, _stream_ptr(stream)))
+    N = int(subgrid_size)
+    _check(lib.idgb200_splitter(C.byref(p), _dev_ptr(metadata, "metadata", int(nr_subgrids) * 36, "int32"),
+                                _dev_ptr(subgrids, "subgrids", int(nr_subgrids) * N * N * 32, "complex64"),
+                                arr, n, rpp, _stream_ptr(stream)))
 
 
 def reduce_parts(sources, out, stream=None) -> None:
     """out = sources[0] + sources[1] + ... (in that order).  ``sources``: complex64 CUDA tensors or
     integer device addresses (peer memory allowed) of out.numel() elements each."""
-    arr = (C.c_void_p * len(sources))(*[int(q) if isinstance(q, int) else q.data_ptr() for q in sources])
-    _check(lib.idgb200_reduce_parts(len(sources), arr, int(out.numel()), C.c_void_p(out.data_ptr()),
+    nbytes = int(out.numel()) * 8
+    arr = (C.c_void_p * len(sources))(*[int(q) if isinstance(q, int) else _dev_ptr(q, f"source {i}", nbytes, "complex64").value
+                                        for i, q in enumerate(sources)])
+    _check(lib.idgb200_reduce_parts(len(sources), arr, int(out.numel()), _dev_ptr(out, "out", nbytes, "complex64"),
                                     _stream_ptr(stream)))
 
 
@@ -206,11 +217,13 @@ def c_run_degridder(nr_subgrids, grid_size, subgrid_size, image_size, w_step_in_
 
 
 # ----------------------------------------------------------- device-pointer API
-def _dev_ptr(t, name: str, min_bytes: int) -> C.c_void_p:
+def _dev_ptr(t, name: str, min_bytes: int, dtype: str | None = None) -> C.c_void_p:
     import torch
 
     if not isinstance(t, torch.Tensor) or not t.is_cuda:
         raise TypeError(f"{name}: CUDA torch tensor expected")
+    if dtype is not None and t.dtype != getattr(torch, dtype):
+        raise TypeError(f"{name}: dtype {t.dtype}, expected torch.{dtype}")
     if not t.is_contiguous():
         raise ValueError(f"{name}: must be contiguous")
     if t.numel() * t.element_size() < min_bytes:

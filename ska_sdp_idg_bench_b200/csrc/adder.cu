@@ -122,7 +122,7 @@ template <bool SYS>
 __global__ void __launch_bounds__(256)
 splitter_kernel(const int grid_size, const int subgrid_size, const idgb200_metadata *__restrict__ metadata,
                 float2 *__restrict__ subgrids, const __grid_constant__ AdderParts parts, const int rows_per_part,
-                const int subgrid_offset, const int shift) {
+                const int subgrid_offset, const int shift, const int vec /* pair slots are 16-byte aligned */) {
   const int s = subgrid_offset + blockIdx.x;
   const int N = subgrid_size, G = grid_size;
   const int x0 = metadata[s].x, y0 = metadata[s].y;
@@ -131,7 +131,6 @@ splitter_kernel(const int grid_size, const int subgrid_size, const idgb200_metad
   const int plane = N * N;
   const int P = (N + 1) / 2;
   const float inv_p = __frcp_rn(__int2float_rn(P));
-  const bool vec = !(N & 1) && !(shift & 1);   // pair slots are 16-byte aligned
   for (int idx = threadIdx.x; idx < N * P; idx += blockDim.x) {
     const int y = div_small(idx, P, inv_p), jj = idx - y * P;
     const int xl = 2 * jj, xh = xl + 1, Xl = x0 + xl, Y = y0 + y;
@@ -225,12 +224,15 @@ cudaError_t launch_splitter(int nr_subgrids, int subgrid_offset, int grid_size, 
   AdderParts p{};
   for (int i = 0; i < nr_parts; i++) p.base[i] = const_cast<float2 *>(parts[i]);
   const int shift = (flags & IDGB200_FLAG_FFT_SHIFT) ? subgrid_size / 2 : 0;
+  // 16-byte stores need even pair slots (even N and shift) in a 16-byte aligned subgrid array: a complex64 view
+  // at an odd element offset takes the 8-byte stores
+  const int vec = !(subgrid_size & 1) && !(shift & 1) && !((uintptr_t)subgrids & 15);
   if (nr_parts > 1)
     splitter_kernel<true><<<dim3((unsigned)nr_subgrids), dim3(256), 0, stream>>>(
-        grid_size, subgrid_size, metadata, subgrids, p, rows_per_part, subgrid_offset, shift);
+        grid_size, subgrid_size, metadata, subgrids, p, rows_per_part, subgrid_offset, shift, vec);
   else
     splitter_kernel<false><<<dim3((unsigned)nr_subgrids), dim3(256), 0, stream>>>(
-        grid_size, subgrid_size, metadata, subgrids, p, rows_per_part, subgrid_offset, shift);
+        grid_size, subgrid_size, metadata, subgrids, p, rows_per_part, subgrid_offset, shift, vec);
   return cudaGetLastError();
 }
 

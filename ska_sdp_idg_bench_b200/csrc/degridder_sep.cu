@@ -17,9 +17,12 @@
 // sincos per (visibility, row y), four complex multiply-adds, then one coalesced 32-byte store per visibility:
 // every visibility of the subgrid's time range is written exactly once.
 //
-// CTA = one subgrid, 4 warps, 2 CTAs per SM (256 TMEM columns each): per tile the warps make the A rows
-// (lane = column x, 32 rows per warp), one thread issues the 12 MMAs, and when they have completed every
-// thread finishes its visibility; while one CTA waits for its MMAs the other one computes.
+// CTA = one subgrid, 8 warps, 2 CTAs per SM (256 TMEM columns each).  The rows of the GEMM are enumerated in
+// blocks of 8 channels (row = (timestep * blocks + block) * 8 + channel, channels padded to blocks), 16 blocks
+// per tile: warp w makes the A rows of blocks 2 w, 2 w + 1 (lane = column x; the 8 phasors of a block unrolled),
+// one thread issues the tile's MMAs, and when they have completed warps q and q + 4 (the two warps that may read
+// TMEM lane quadrant q) each sum half of the rows y for their 32 visibilities; the halves meet in shared memory.
+// While one CTA waits for its MMAs the other one computes.
 #include <cuda_fp16.h>
 
 #include "common.cuh"
@@ -30,7 +33,7 @@ namespace idgb200 {
 
 namespace {
 
-constexpr int DS_THREADS = 128;
+constexpr int DS_THREADS = 256;
 constexpr int DS_A_CH = 128 * 16 + 16;           // one 16-byte K chunk of 128 rows, padded: the 8 chunks a warp's
                                                  // 4-byte stores touch fall into different banks
 constexpr float SEP_PHASE_TOL = 1e-4f;           // largest dropped phase |gamma| r (rad), as in gridder_sep.cu
@@ -61,7 +64,8 @@ degridder_sep_kernel(const KernelArgs a, const int tmem_cols, int *__restrict__ 
   unsigned char *sB = smem;                                             // [hi|lo][KCp][b_ch]
   unsigned char *sA = sB + 2 * KCp * b_ch;                              // [hi|lo][KCp][DS_A_CH]
   float4 *sGeo = reinterpret_cast<float4 *>(sA + 2 * KCp * DS_A_CH);    // [N] (m_y, f(m_y^2), offset_y, 0)
-  unsigned long long *mma_done = reinterpret_cast<unsigned long long *>(sGeo + N);
+  float4 *sPart = sGeo + N;                                             // [128][2] partial sums of the upper warps
+  unsigned long long *mma_done = reinterpret_cast<unsigned long long *>(sPart + 256);
   unsigned *s_tmem = reinterpret_cast<unsigned *>(mma_done + 1);
   float *s_red = reinterpret_cast<float *>(s_tmem + 2);                 // [16]
   float *s_wn = s_red + 16;                                             // [ncb * 8]
@@ -70,8 +74,8 @@ degridder_sep_kernel(const KernelArgs a, const int tmem_cols, int *__restrict__ 
 
   const SubgridCtx ctx = load_ctx(a, s);
   const int nt = ctx.nr_timesteps;
-  const int nvis = nt * C;
-  const int ntiles = (nvis + 127) >> 7;
+  const int nblk = nt * ncb;                       // blocks of 8 rows
+  const int ntiles = (nblk + 15) >> 4;
   const float *g_uvw = reinterpret_cast<const float *>(a.uvw) + (size_t)ctx.time_offset * 3;
 
   for (int c = tid; c < ncb * 8; c += DS_THREADS) s_wn[c] = c < C ? a.wavenumbers[c] : 0.f;
@@ -100,7 +104,7 @@ degridder_sep_kernel(const KernelArgs a, const int tmem_cols, int *__restrict__ 
     }
     __syncthreads();
     if (tid == 0) {
-      for (int i = 1; i < 4; i++) wmax = fmaxf(wmax, s_red[i]);
+      for (int i = 1; i < 8; i++) wmax = fmaxf(wmax, s_red[i]);
       float kmax = 0.f;
       for (int c = 0; c < C; c++) kmax = fmaxf(kmax, fabsf(s_wn[c]));
       const double l0 = (0.5 - (N / 2)) * (double)a.image_size / (double)N;
@@ -115,7 +119,7 @@ degridder_sep_kernel(const KernelArgs a, const int tmem_cols, int *__restrict__ 
     __syncthreads();
   }
   if (s_red[12] == 0.f) return;          // the per-pixel kernel behind this launch takes the subgrid
-  if (nvis == 0) return;
+  if (nblk == 0) return;
 
   // ---- B = P' (degridder_reference.cpp:38-74) in fp16 hi + lo; the fp32 pixels wait in the A buffer
   {
@@ -148,7 +152,7 @@ degridder_sep_kernel(const KernelArgs a, const int tmem_cols, int *__restrict__ 
     if (lane == 0) s_red[warp] = amax;
     __syncthreads();
     if (tid == 0) {
-      for (int i = 1; i < 4; i++) amax = fmaxf(amax, s_red[i]);
+      for (int i = 1; i < 8; i++) amax = fmaxf(amax, s_red[i]);
       const unsigned eb = (__float_as_uint(amax) >> 23) & 0xffu;
       const bool ok = eb >= 14u && eb <= 253u;
       s_red[10] = ok ? __uint_as_float((267u - eb) << 23) : 1.f;           // 2^(13 - E)
@@ -200,52 +204,54 @@ degridder_sep_kernel(const KernelArgs a, const int tmem_cols, int *__restrict__ 
   const unsigned tmem_base = *s_tmem;
 
   // lane = column x of the A operand
-  const int xl = min(lane, N - 1);
-  const float l = compute_l(xl, N, a.image_size);
+  const float l = compute_l(min(lane, N - 1), N, a.image_size);
   const float n_x = compute_n(l, 0.f);
   const float off_x = __fmaf_rn(ctx.w_offset, n_x, __fmul_rn(ctx.u_offset, l));
   unsigned char *a_col = sA + (lane >> 2) * DS_A_CH + (lane & 3) * 4;
   // instruction descriptor: D = F32, A = B = F16, K-major, N = 8 N, M = 128
   const unsigned idesc = (1u << 4) | (((unsigned)ncols >> 3) << 17) | ((128u >> 4) << 24);
   float2 *g_out = const_cast<float2 *>(a.visibilities) + (size_t)ctx.time_offset * C * NR_POL;
+  // the rows y of this warp in the sum over the rows: warps 0-3 the first groups of 4, warps 4-7 the rest
+  const int q4 = warp & 3, upper = warp >> 2;
+  const int ng = N >> 2, g_lo = upper ? (ng + 1) >> 1 : 0, g_hi = upper ? ng : (ng + 1) >> 1;
 
   for (int tile = 0; tile < ntiles; tile++) {
-    // ---- A rows 32 warp .. + 31 of the tile: X_v(x), v = flat (t, c) index, hi + lo
-    {
-      int gv = tile * 128 + warp * 32;
-      int t = gv / C, c = gv - t * C;
-      float2 cur = make_float2(0.f, 0.f), prev = cur;
-      float c2 = 0.f, idx = 0.f;
-      bool start = true;
-      for (int i = 0; i < 32; i++, gv++) {
-        unsigned hi = 0u, lo = 0u;
-        if (gv < nvis) {
-          const int cb = c >> 3;
-          const bool lin = s_lin[cb] != 0;
-          if (start || (c & 7) == 0) {
-            if (start || c == 0) idx = __fmaf_rn(__ldg(&g_uvw[3 * t + 2]), n_x, __fmul_rn(__ldg(&g_uvw[3 * t]), l));
-            cur = phasor<IDGB200_SINCOS_FAST>(__fmaf_rn(idx, s_wn[c], -off_x));
-            if (lin) {   // prev = cur * conj(d), d = e^{i idx dw}: the three-term recurrence runs from here
-              const float2 d = phasor<IDGB200_SINCOS_FAST>(__fmul_rn(idx, s_dw[cb]));
-              prev = make_float2(__fmaf_rn(cur.x, d.x, __fmul_rn(cur.y, d.y)), __fmaf_rn(cur.y, d.x, -__fmul_rn(cur.x, d.y)));
-              c2 = __fadd_rn(d.x, d.x);
-            }
-            start = false;
-          } else if (lin) {
-            const float2 nxt = ffma2(cur, make_float2(c2, c2), make_float2(-prev.x, -prev.y));
-            prev = cur;
-            cur = nxt;
-          } else {
-            cur = phasor<IDGB200_SINCOS_FAST>(__fmaf_rn(idx, s_wn[c], -off_x));
-          }
-          hi = pack_h2(cur.x, cur.y);
-          lo = pack_h2(residual_h(cur.x, (unsigned short)(hi & 0xffffu)), residual_h(cur.y, (unsigned short)(hi >> 16)));
-          if (++c == C) { c = 0; t++; }
+    // ---- A rows of blocks 2 warp, 2 warp + 1 of the tile: X_v(x) for the block's 8 channels, hi + lo
+#pragma unroll 1
+    for (int bi = 0; bi < 2; bi++) {
+      const int blk = tile * 16 + warp * 2 + bi;
+      unsigned hi[8], lo[8];
+      if (blk < nblk) {
+        const int t = blk / ncb, cb = blk - t * ncb;
+        const float idx = __fmaf_rn(__ldg(&g_uvw[3 * t + 2]), n_x, __fmul_rn(__ldg(&g_uvw[3 * t]), l));
+        const float *wn8 = s_wn + cb * 8;
+        float2 ph[8];
+        if (s_lin[cb]) {   // first channel by sincos, second by one rotation, then the three-term recurrence
+          ph[0] = phasor<IDGB200_SINCOS_FAST>(__fmaf_rn(idx, wn8[0], -off_x));
+          const float2 d = phasor<IDGB200_SINCOS_FAST>(__fmul_rn(idx, s_dw[cb]));
+          ph[1] = ffma2(make_float2(ph[0].y, ph[0].x), make_float2(-d.y, d.y), __fmul2_rn(ph[0], make_float2(d.x, d.x)));
+          const float c2 = __fadd_rn(d.x, d.x);
+#pragma unroll
+          for (int i = 2; i < 8; i++) ph[i] = ffma2(ph[i - 1], make_float2(c2, c2), make_float2(-ph[i - 2].x, -ph[i - 2].y));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; i++) ph[i] = phasor<IDGB200_SINCOS_FAST>(__fmaf_rn(idx, wn8[i], -off_x));
         }
-        if (lane < N) {
-          unsigned char *row = a_col + (warp * 32 + i) * 16;
-          *reinterpret_cast<unsigned *>(row) = hi;
-          *reinterpret_cast<unsigned *>(row + KCp * DS_A_CH) = lo;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+          hi[i] = pack_h2(ph[i].x, ph[i].y);
+          lo[i] = pack_h2(residual_h(ph[i].x, (unsigned short)(hi[i] & 0xffffu)), residual_h(ph[i].y, (unsigned short)(hi[i] >> 16)));
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; i++) hi[i] = lo[i] = 0u;
+      }
+      if (lane < N) {
+        unsigned char *row = a_col + ((warp * 2 + bi) * 8) * 16;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+          *reinterpret_cast<unsigned *>(row + i * 16) = hi[i];
+          *reinterpret_cast<unsigned *>(row + i * 16 + KCp * DS_A_CH) = lo[i];
         }
       }
     }
@@ -268,22 +274,26 @@ degridder_sep_kernel(const KernelArgs a, const int tmem_cols, int *__restrict__ 
       }
       __syncwarp();
     }
+    // the partial sums of the previous tile meet here (its upper halves were written before the barrier above)
     mbar_wait(mma_done, tile & 1);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
-    // ---- the sum over the rows y: thread = visibility tid of the tile
+    // ---- the sum over the rows y: thread = row 32 q4 + lane of the tile, warps q4 and q4 + 4 half of the rows each
     {
-      const int gv = tile * 128 + tid;
-      const bool valid = gv < nvis;
-      const int t = valid ? gv / C : 0, c = valid ? gv - t * C : 0;
-      const float k = s_wn[c];
+      const int r_tile = q4 * 32 + lane;
+      const int blk = tile * 16 + (r_tile >> 3);
+      const bool in_range = blk < nblk;
+      const int t = in_range ? blk / ncb : 0, cb = in_range ? blk - t * ncb : 0;
+      const int c = cb * 8 + (r_tile & 7);
+      const bool valid = in_range && c < C;
+      const float k = s_wn[cb * 8 + (r_tile & 7)];
       const float vt = __ldg(&g_uvw[3 * t + 1]), wt = __ldg(&g_uvw[3 * t + 2]);
       float2 acc[NR_POL];
 #pragma unroll
       for (int p = 0; p < NR_POL; p++) acc[p] = make_float2(0.f, 0.f);
-      for (int y0 = 0; y0 < N; y0 += 4) {
+      for (int g = g_lo; g < g_hi; g++) {
         unsigned r[32];
-        const unsigned taddr = tmem_base + ((unsigned)(warp * 32) << 16) + y0 * 8;
+        const unsigned taddr = tmem_base + ((unsigned)(q4 * 32) << 16) + g * 32;
         asm volatile(
             "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
             "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
@@ -295,9 +305,9 @@ degridder_sep_kernel(const KernelArgs a, const int tmem_cols, int *__restrict__ 
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
         for (int yy = 0; yy < 4; yy++) {
-          const float4 g = sGeo[y0 + yy];           // broadcast
-          const float idx = __fmaf_rn(wt, g.y, __fmul_rn(vt, g.x));
-          const float2 ph = phasor<IDGB200_SINCOS_FAST>(__fmaf_rn(idx, k, -g.z));
+          const float4 geo = sGeo[g * 4 + yy];        // broadcast
+          const float idx = __fmaf_rn(wt, geo.y, __fmul_rn(vt, geo.x));
+          const float2 ph = phasor<IDGB200_SINCOS_FAST>(__fmaf_rn(idx, k, -geo.z));
           const float2 phs = make_float2(-ph.y, ph.x);
 #pragma unroll
           for (int p = 0; p < NR_POL; p++) {      // acc += Q * ph: (qr, qr) * (c, s) + (qi, qi) * (-s, c)
@@ -307,14 +317,21 @@ degridder_sep_kernel(const KernelArgs a, const int tmem_cols, int *__restrict__ 
           }
         }
       }
-      if (valid) {
-        float4 *o = reinterpret_cast<float4 *>(g_out + (size_t)gv * NR_POL);
-        o[0] = make_float4(acc[0].x * unscale, acc[0].y * unscale, acc[1].x * unscale, acc[1].y * unscale);
-        o[1] = make_float4(acc[2].x * unscale, acc[2].y * unscale, acc[3].x * unscale, acc[3].y * unscale);
+      if (upper) {
+        sPart[2 * r_tile] = make_float4(acc[0].x, acc[0].y, acc[1].x, acc[1].y);
+        sPart[2 * r_tile + 1] = make_float4(acc[2].x, acc[2].y, acc[3].x, acc[3].y);
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncthreads();                  // accumulator and A buffer are free for the next tile; the upper halves are in
+      if (!upper && valid) {
+        const float4 p0 = sPart[2 * r_tile], p1 = sPart[2 * r_tile + 1];
+        float4 *o = reinterpret_cast<float4 *>(g_out + ((size_t)t * C + c) * NR_POL);
+        o[0] = make_float4((acc[0].x + p0.x) * unscale, (acc[0].y + p0.y) * unscale, (acc[1].x + p0.z) * unscale,
+                           (acc[1].y + p0.w) * unscale);
+        o[1] = make_float4((acc[2].x + p1.x) * unscale, (acc[2].y + p1.y) * unscale, (acc[3].x + p1.z) * unscale,
+                           (acc[3].y + p1.w) * unscale);
       }
     }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();                  // accumulator and A buffer are free for the next tile
   }
   if (warp == 0)
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols));
@@ -334,7 +351,7 @@ cudaError_t launch_degridder_sep(const KernelArgs &a, int *d_todo, cudaStream_t 
   const int N = a.subgrid_size, KC = N / 4, KCp = (KC + 1) & ~1, ncols = 8 * N, ncb = (a.nr_channels + 7) / 8;
   int tmem_cols = 32;
   while (tmem_cols < ncols) tmem_cols *= 2;
-  const size_t smem = (size_t)2 * KCp * (ncols * 16 + 16) + (size_t)2 * KCp * DS_A_CH + (size_t)N * 16 + 8 + 8 + 64 +
+  const size_t smem = (size_t)2 * KCp * (ncols * 16 + 16) + (size_t)2 * KCp * DS_A_CH + (size_t)N * 16 + 256 * 16 + 8 + 8 + 64 +
                       (size_t)ncb * 10 * 4;
   cudaError_t e = cudaFuncSetAttribute(degridder_sep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;

@@ -8,6 +8,11 @@ nvcc has no hook between its internal steps, so this replays the command list th
 runs csrc/sass_tune.py on the .cubin right after ptxas wrote it.  Everything else is
 nvcc's own pipeline, so the object file is what `nvcc -c` would have produced with a
 few control bits of some FFMA2 instructions changed (see sass_tune.py).
+
+The bit positions sass_tune.py edits were established for ptxas 12.9 (TUNED_TOOLKITS).  With any other
+toolkit, or when the replay or the tuning step fails for any reason, the object is built by the plain
+nvcc command instead, with a warning: the tuning only buys a few percent on the FP32 kernels and the
+untuned object computes the same bits (tests/test_gpu_parity.py::test_sass_tuned_equals_untuned_bitwise).
 """
 from __future__ import annotations
 
@@ -17,6 +22,16 @@ import subprocess
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
+TUNED_TOOLKITS = ("12.9",)   # CUDA releases whose ptxas encodes FFMA2 as sass_tune.py expects
+
+
+def toolkit_release(nvcc: str) -> str | None:
+    try:
+        out = subprocess.run([nvcc, "--version"], capture_output=True, text=True).stdout
+    except OSError:
+        return None
+    m = re.search(r"release (\d+\.\d+)", out)
+    return m.group(1) if m else None
 
 
 def main(argv) -> int:
@@ -26,6 +41,20 @@ def main(argv) -> int:
     split = argv.index("--")
     opts, cmd = argv[1:split], argv[split + 1:]
     tune = "--no-tune" not in opts and os.environ.get("IDGB200_NO_SASS_TUNE", "0") != "1"
+    if tune and toolkit_release(cmd[0]) not in TUNED_TOOLKITS:
+        sys.stderr.write(f"nvcc_tuned: CUDA {toolkit_release(cmd[0])} is not in {TUNED_TOOLKITS}: building untuned\n")
+        tune = False
+    if not tune:
+        return subprocess.run(cmd).returncode
+    rc = tuned(opts, cmd)
+    if rc != 0:
+        sys.stderr.write("nvcc_tuned: WARNING: the tuned build failed, falling back to the plain nvcc object\n")
+        return subprocess.run(cmd).returncode
+    return 0
+
+
+def tuned(opts, cmd) -> int:
+    tune = True
     kernels = opts[opts.index("--tune-kernels") + 1] if "--tune-kernels" in opts else "."
 
     dry = subprocess.run(cmd + ["-dryrun"], capture_output=True, text=True)

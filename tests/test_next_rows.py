@@ -180,6 +180,27 @@ def test_splitter_gpu_vs_oracle_bitwise(shape, flags):
     back = torch.empty_like(sg)
     idg.splitter(q.nr_subgrids, 2 * N, N, meta, back, g2, flags=flags)
     assert torch.equal(back, sg)
+    # a subgrid array that is only 8-byte aligned (a complex64 view at an odd element offset) takes the 8-byte
+    # stores instead of faulting; the adder likewise reads it
+    flat = torch.full((sg.numel() + 1,), float("nan"), dtype=torch.complex64, device=dev)
+    odd = flat[1:].view(sg.shape)
+    assert odd.data_ptr() % 16 == 8
+    idg.splitter(q.nr_subgrids, 2 * N, N, meta, odd, g2, flags=flags)
+    assert torch.equal(odd, sg)
+    g3 = torch.zeros_like(g2)
+    idg.adder(q.nr_subgrids, 2 * N, N, meta, odd, g3, flags=flags)
+    assert torch.equal(g3, g2)
+    # argument validation of the Python mirror: wrong device, dtype, size, layout raise instead of reaching the kernel
+    with pytest.raises(TypeError):
+        idg.splitter(q.nr_subgrids, 2 * N, N, meta.cpu(), back, g2)
+    with pytest.raises(TypeError):
+        idg.splitter(q.nr_subgrids, 2 * N, N, meta.to(torch.int64), back, g2)
+    with pytest.raises(ValueError):
+        idg.adder(q.nr_subgrids + 1, 2 * N, N, meta, sg, g2)
+    with pytest.raises(ValueError):
+        idg.adder(q.nr_subgrids, 2 * N, N, meta, sg, g2[:, : N])          # short (and non-contiguous) grid part
+    with pytest.raises(ValueError):
+        idg.reduce_parts([g2, g2[:, :N].contiguous()], torch.empty_like(g2))
 
 
 @pytest.mark.gpu
