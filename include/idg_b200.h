@@ -170,6 +170,13 @@ int idgb200_splitter(const idgb200_params *params, const idgb200_metadata *d_met
 int idgb200_reduce_parts(int nr_sources, const idgb200_cfloat *const *sources, int64_t count,
                          idgb200_cfloat *d_out, void *stream);
 
+/* How N GPUs should add their shards of the subgrids into one row-scattered grid (measured on 2 and 8 B200s,
+ * DESIGN.md 4.8): 1 = push - every rank's idgb200_adder reduces straight into the owners' slices through peer
+ * addresses (grid_parts = the owners' slices) - when a rank has fewer subgrid pixels than the grid has cells
+ * (nr_subgrids * N^2 < G^2); 0 = local grid + reduce-scatter (idgb200_reduce_parts over peer addresses, or
+ * ncclReduceScatter).  ska_sdp_idg_bench_b200/grid_adder_rs.py implements both on symmetric memory. */
+int idgb200_adder_rs_mode(int64_t nr_subgrids, int subgrid_size, int grid_size);
+
 /* Subgrid FFT: in-place 2-D DFT of each of the nr_subgrids * 4 planes of N x N pixels.
  *   direction = +1 (forward, after the gridder):  B[ky][kx] = sum A[y][x] exp(-2 pi i (ky y + kx x) / N)
  *   direction = -1 (backward, before the degridder): exp(+...), scaled by 1 / N^2
@@ -260,6 +267,15 @@ typedef struct {
                          PowerSensor measurement of util.cpp:131-155: W = joules / seconds,
                          GFLOP/s/W = gflops / joules, MVis/J = mvis / joules (common.cpp:47-54) */
 } idgb200_perf;
+
+/* The reference's report line and key,value CSV (app/common/common.cpp:27-56 and :58-98; called by its
+ * runners at app/CUDA/util.cpp:157-160): same text, keys, order and number format, byte for byte
+ * (tests/test_host_logic.py pins both against the reference's own functions).  seconds = time per launch,
+ * gflops / gbytes / mvis = work per launch, joules = energy per launch (0 = columns left out).  The CSV goes
+ * to $OUTPUT_PATH (default ".") as <device_name with '/' -> '-'>-<name><file_extension>. */
+void idgb200_report(const char *name, double seconds, double gflops, double gbytes, double mvis, double joules);
+void idgb200_report_csv(const char *name, const char *device_name, const char *file_extension, double seconds,
+                        double gflops, double gbytes, double mvis, double joules);
 
 int idgb200_p_run_gridder(idgb200_perf *result /* may be NULL */);
 int idgb200_p_run_degridder(idgb200_perf *result /* may be NULL */);

@@ -4,7 +4,7 @@
  * reference legs may load this library, and only as the checker or the reported
  * CPU baseline.  The product (ska_sdp_idg_bench_b200/) never links or calls it.
  *
- * Parity status: PINNED.  tests/test_oracle_vs_reference.py compares every
+ * Parity status: PINNED.  tests/test_oracle.py compares every
  * function below bit for bit with the reference's own code compiled from
  * /root/reference (oracle/_ref/libidgref.so), and tests/golden/ holds outputs of
  * that reference build for the reference's correctness shape.

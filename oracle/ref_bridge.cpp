@@ -2,7 +2,7 @@
 //
 // extern "C" bridge over the *unmodified* reference CPU implementation
 // (/root/reference/app/CPU/kernels/{gridder,degridder}_reference.cpp and
-// app/common/{init,common}.cpp).  oracle/build_ref.sh compiles those sources
+// app/common/{init,common}.cpp).  oracle/Makefile (target ref) compiles those sources
 // where they lie and links them with this file into oracle/_ref/libidgref.so.
 // Only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs may
 // load that library, and only as the checker / reported baseline.
@@ -15,6 +15,7 @@
 //   cpu::c_run_degridder_reference   app/lib-cpu.hpp:20-29
 //   initialize_*                     app/common/init.hpp:8-41
 //   flops_gridder / bytes_gridder    app/common/common.hpp:36-42
+//   report / report_csv              app/common/common.hpp:28-34 (common.cpp:27-98)
 #include <complex>
 #include <cstdint>
 #include <cstdlib>
@@ -188,6 +189,18 @@ uint64_t idgref_bytes_gridder(uint64_t nr_channels, uint64_t nr_timesteps,
                               uint64_t nr_correlations) {
   return bytes_gridder(nr_channels, nr_timesteps, nr_subgrids, subgrid_size,
                        nr_correlations);
+}
+
+// ---- report line and CSV (app/common/common.cpp:27-98), as the reference's runners call them
+// (app/CUDA/util.cpp:157-160): the line goes to stdout, the CSV to $OUTPUT_PATH/<device>-<name><ext>
+void idgref_report(const char *name, double seconds, double gflops, double gbytes, double mvis,
+                   double joules) {
+  report(name, seconds, gflops, gbytes, mvis, joules);
+}
+
+void idgref_report_csv(const char *name, const char *device_name, const char *file_extension,
+                       double seconds, double gflops, double gbytes, double mvis, double joules) {
+  report_csv(name, device_name, file_extension, seconds, gflops, gbytes, mvis, joules);
 }
 
 } // extern "C"

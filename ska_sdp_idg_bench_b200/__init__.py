@@ -14,6 +14,7 @@ from .api import (FLAG_FFT_SHIFT, IdgError, SINCOS_ACCURATE, SINCOS_FAST, SINCOS
                   init_problem_device, launch_count, p_run_degridder, p_run_gridder,
                   print_device_info, reduce_parts, resolve_variant, sm_count, splitter, subgrid_fft)
 from .layout import BASELINE_DTYPE, METADATA_DTYPE, NR_CORRELATIONS, IMAGE_SIZE, W_STEP
+from .grid_adder_rs import GridAdderRS, adder_rs_mode
 from .shard import partition_subgrids, shard_metadata
 
 __all__ = [
@@ -21,5 +22,5 @@ __all__ = [
     "c_run_degridder", "gridder", "degridder", "p_run_gridder", "p_run_degridder",
     "flops_gridder", "bytes_gridder", "print_device_info", "device_name", "sm_count",
     "launch_count", "resolve_variant", "adder", "reduce_parts", "splitter", "subgrid_fft", "FLAG_FFT_SHIFT", "init_problem_device", "METADATA_DTYPE", "BASELINE_DTYPE",
-    "NR_CORRELATIONS", "IMAGE_SIZE", "W_STEP", "partition_subgrids", "shard_metadata",
+    "NR_CORRELATIONS", "IMAGE_SIZE", "W_STEP", "partition_subgrids", "shard_metadata", "GridAdderRS", "adder_rs_mode",
 ]

@@ -40,6 +40,7 @@ SYMBOLS = {
     "idgb200_splitter": (C.c_int, [C.POINTER(Params), _P, _P, C.POINTER(C.c_void_p), C.c_int, C.c_int, _P]),
     "idgb200_reduce_parts": (C.c_int, [C.c_int, C.POINTER(C.c_void_p), C.c_int64, _P, _P]),
     "idgb200_subgrid_fft": (C.c_int, [C.c_int64, C.c_int, C.c_int, _P, _P]),
+    "idgb200_adder_rs_mode": (C.c_int, [C.c_int64, C.c_int, C.c_int]),
     "idgb200_c_run_gridder": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int,
                                         C.c_int, C.c_int64, C.c_int] + [_P] * 7),
     "idgb200_c_run_degridder": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int,
@@ -48,6 +49,8 @@ SYMBOLS = {
     "idgb200_c_run_degridder_ex": (C.c_int, [C.POINTER(Params), C.c_int64, C.c_int] + [_P] * 7),
     "idgb200_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_size_t]),
     "idgb200_host_free": (C.c_int, [_P]),
+    "idgb200_report": (None, [C.c_char_p] + [C.c_double] * 5),
+    "idgb200_report_csv": (None, [C.c_char_p, C.c_char_p, C.c_char_p] + [C.c_double] * 5),
     "idgb200_p_run_gridder": (C.c_int, [C.POINTER(Perf)]),
     "idgb200_p_run_degridder": (C.c_int, [C.POINTER(Perf)]),
     "idgb200_init_uvw": (C.c_int, [C.c_uint32, C.c_int64, C.c_int, C.c_uint32, _P, _P]),

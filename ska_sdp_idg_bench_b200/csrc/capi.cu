@@ -475,7 +475,7 @@ void report(const char *name, double seconds, double gflops, double gbytes, doub
   std::printf("%20s: %7.2f ms", name, seconds * 1e3);
   if (gflops != 0) std::printf(", %7.2f GFLOP/s", gflops / seconds);
   if (gbytes != 0) std::printf(", %7.2f GB/s", gbytes / seconds);
-  if (gflops != 0 && gbytes != 0) std::printf(", %7.2f FLOP/byte", gflops / gbytes);
+  if (gflops != 0 && gbytes != 0) std::printf(", %7.2f FLOP/byte", (double)(float)(gflops / gbytes));
   if (mvis != 0) std::printf(", %7.2f MVis/s", mvis / seconds);
   if (joules != 0)   // common.cpp:47-54
     std::printf(", %7.2f W, %7.2f GFLOP/s/W, %7.2f MVis/J", joules / seconds, gflops / joules, mvis / joules);
@@ -483,20 +483,27 @@ void report(const char *name, double seconds, double gflops, double gbytes, doub
   std::fflush(stdout);
 }
 
-// key,value CSV of the reference (app/common/common.cpp:58-98)
-void report_csv(const char *name, double seconds, double gflops, double gbytes, double mvis, double joules) {
-  char dev[256] = "";
-  idgb200_device_name(dev, sizeof dev);
-  for (char *c = dev; *c; c++)
-    if (*c == '/') *c = '-';
+// key,value CSV of the reference (app/common/common.cpp:58-98): same file name, keys, order and number format
+void report_csv(const char *name, const char *device_name, const char *file_extension, double seconds, double gflops,
+                double gbytes, double mvis, double joules) {
+  if (!device_name || !*device_name || !file_extension || !*file_extension) {
+    std::printf(">>> Device name or file extension not provided\n");
+    return;
+  }
   const char *dir = std::getenv("OUTPUT_PATH");
-  if (!dir) return;  // unlike the reference, only written when asked for
-  std::string path = std::string(dir) + "/" + dev + "-" + name + "-cuda.csv";
+  const std::string file_path = dir ? dir : ".";
+  std::printf("Saving output in %s\n", file_path.c_str());
+  std::string dev = device_name;
+  for (char &c : dev)
+    if (c == '/') c = '-';
+  const std::string path = file_path + "/" + dev + "-" + name + file_extension;
+  std::printf("%s\n", path.c_str());
+  std::fflush(stdout);
   if (FILE *f = std::fopen(path.c_str(), "w")) {
     std::fprintf(f, "ms,%.2f\n", seconds * 1e3);
     if (gflops != 0) std::fprintf(f, "GFLOP/s,%.2f\n", gflops / seconds);
     if (gbytes != 0) std::fprintf(f, "GB/s,%.2f\n", gbytes / seconds);
-    if (gflops != 0 && gbytes != 0) std::fprintf(f, "FLOP/Byte,%.2f\n", gflops / gbytes);
+    if (gflops != 0 && gbytes != 0) std::fprintf(f, "FLOP/Byte,%.2f\n", (double)(float)(gflops / gbytes));
     if (mvis != 0) std::fprintf(f, "MVis/s,%.2f\n", mvis / seconds);
     if (joules != 0) {   // common.cpp:88-95
       std::fprintf(f, "W,%.2f\n", joules / seconds);
@@ -504,7 +511,6 @@ void report_csv(const char *name, double seconds, double gflops, double gbytes, 
       std::fprintf(f, "MVis/J,%.2f\n", mvis / joules);
     }
     std::fclose(f);
-    std::printf("Saving output in %s\n", path.c_str());
   }
 }
 
@@ -640,7 +646,11 @@ int perf_run(bool gridding, idgb200_perf *result) {
   }
   const char *name = gridding ? "gridder_b200" : "degridder_b200";
   report(name, seconds, gflops, gbytes, mvis, joules);
-  report_csv(name, seconds, gflops, gbytes, mvis, joules);
+  if (std::getenv("OUTPUT_PATH")) {   // unlike the reference (which defaults to "."), only written when asked for
+    char dev[256] = "";
+    idgb200_device_name(dev, sizeof dev);
+    report_csv(name, dev, "-cuda.csv", seconds, gflops, gbytes, mvis, joules);
+  }
   if (result) {
     result->joules = joules;
     result->seconds = seconds;
@@ -770,6 +780,15 @@ int idgb200_degridder(const idgb200_params *p, const idgb200_uvw *d_uvw, const f
 
 uint64_t idgb200_launch_count(void) { return g_launches.load(); }
 
+void idgb200_report(const char *name, double seconds, double gflops, double gbytes, double mvis, double joules) {
+  report(name ? name : "", seconds, gflops, gbytes, mvis, joules);
+}
+
+void idgb200_report_csv(const char *name, const char *device_name, const char *file_extension, double seconds,
+                        double gflops, double gbytes, double mvis, double joules) {
+  report_csv(name ? name : "", device_name, file_extension, seconds, gflops, gbytes, mvis, joules);
+}
+
 int idgb200_adder(const idgb200_params *p, const idgb200_metadata *d_meta, const idgb200_cfloat *d_sg,
                   idgb200_cfloat *const *grid_parts, int nr_parts, int rows_per_part, void *stream) {
   int rc = check_params(p);
@@ -826,6 +845,11 @@ int idgb200_reduce_parts(int nr_sources, const idgb200_cfloat *const *sources, i
   if (e != cudaSuccess) return (int)e;
   g_launches++;
   return IDGB200_OK;
+}
+
+int idgb200_adder_rs_mode(int64_t nr_subgrids, int subgrid_size, int grid_size) {
+  if (nr_subgrids < 0 || subgrid_size <= 0 || grid_size <= 0) return IDGB200_EINVAL;
+  return nr_subgrids * (int64_t)subgrid_size * subgrid_size < (int64_t)grid_size * grid_size ? 1 : 0;
 }
 
 int idgb200_subgrid_fft(int64_t nr_subgrids, int subgrid_size, int direction, idgb200_cfloat *d_sg,

@@ -4,6 +4,7 @@ sharding logic is right (incl. a world_size-2 gloo run), and - since there is no
 GPU here - that every compute entry point refuses to run instead of falling back."""
 import ctypes as C
 import os
+import sys
 import re
 
 import numpy as np
@@ -128,6 +129,71 @@ def test_mirror_pixels_have_exactly_negated_direction_cosines():
                 assert phase(l[x], l[y]) == -phase(l[N - 1 - x], l[N - 1 - y])
     l = np.array([compute_l(x, 31, 0.01) for x in range(31)], np.float32)
     assert not np.array_equal(l, -l[::-1])
+
+
+# ------------------------------------------- report line + CSV against the reference's own
+def _capture_fd1(fn):
+    """Run fn with the process's stdout (fd 1) redirected into a file; returns what C / C++ code wrote."""
+    import tempfile
+    sys.stdout.flush()
+    saved = os.dup(1)
+    with tempfile.TemporaryFile() as tmp:
+        os.dup2(tmp.fileno(), 1)
+        try:
+            fn()
+            C.CDLL(None).fflush(None)
+        finally:
+            os.dup2(saved, 1)
+            os.close(saved)
+        tmp.seek(0)
+        return tmp.read().decode()
+
+
+@pytest.mark.parametrize("numbers", [
+    (7.0579e-3, 1779.19, 4.95488, 50.176, 0.0),          # a perf run without an energy reading
+    (12.3456e-3, 1779.19, 4.95488, 50.176, 10.87),       # with one: W, GFLOP/s/W, MVis/J columns
+    (35.0e-3, 0.0, 4.95488, 50.176, 0.0),                # no flop figure: GFLOP/s and FLOP/Byte left out
+    (1.5e-3, 12.5, 0.0, 0.0, 0.0),
+])
+def test_report_line_and_csv_match_the_reference_byte_for_byte(numbers, tmp_path):
+    """idgb200_report / idgb200_report_csv against the reference's report / report_csv
+    (app/common/common.cpp:27-56, 58-98, through oracle/_ref's bridge): the same line on stdout, the same
+    file name (<device with / -> ->-<name>-cuda.csv under $OUTPUT_PATH), keys, order and number format."""
+    from oracle_lib import reference
+    ref = reference()
+    if ref is None:
+        pytest.skip("oracle/_ref not built (needs /root/reference at build time)")
+    seconds, gflops, gbytes, mvis, joules = numbers
+    dbl = [C.c_double(x) for x in numbers]
+    f_ref, f_ref_csv = ref.lib.idgref_report, ref.lib.idgref_report_csv
+    f_ref.restype = f_ref_csv.restype = None
+    lib = idg._lib.lib
+    name, device = b"gridder_b200", b"NVIDIA B200/SXM"
+    line_ref = _capture_fd1(lambda: f_ref(name, *dbl))
+    line_ours = _capture_fd1(lambda: lib.idgb200_report(name, *numbers))
+    assert line_ours == line_ref and "ms" in line_ref
+    old = os.environ.get("OUTPUT_PATH")
+    try:
+        d_ref, d_ours = tmp_path / "ref", tmp_path / "ours"
+        d_ref.mkdir(); d_ours.mkdir()
+        os.environ["OUTPUT_PATH"] = str(d_ref)
+        out_ref = _capture_fd1(lambda: f_ref_csv(name, device, b"-cuda.csv", *dbl))
+        os.environ["OUTPUT_PATH"] = str(d_ours)
+        out_ours = _capture_fd1(lambda: lib.idgb200_report_csv(name, device, b"-cuda.csv", *numbers))
+    finally:
+        if old is None:
+            os.environ.pop("OUTPUT_PATH", None)
+        else:
+            os.environ["OUTPUT_PATH"] = old
+    files_ref, files_ours = sorted(os.listdir(d_ref)), sorted(os.listdir(d_ours))
+    assert files_ours == files_ref == ["NVIDIA B200-SXM-gridder_b200-cuda.csv"]
+    assert (d_ours / files_ours[0]).read_bytes() == (d_ref / files_ref[0]).read_bytes()
+    assert out_ours.replace(str(d_ours), "X") == out_ref.replace(str(d_ref), "X")
+    keys = [ln.split(",")[0] for ln in (d_ours / files_ours[0]).read_text().splitlines()]
+    want = ["ms"] + (["GFLOP/s"] if gflops else []) + (["GB/s"] if gbytes else []) + \
+           (["FLOP/Byte"] if gflops and gbytes else []) + (["MVis/s"] if mvis else []) + \
+           (["W", "GFLOP/s/W", "MVis/J"] if joules else [])
+    assert keys == want
 
 
 # ------------------------------------------------------------------------ sharding
