@@ -387,20 +387,22 @@ def run_ours(args) -> None:
     def all_max(x: float) -> float:
         return reduce_max_time(x, dev)
 
-    def timed(step, steps, warmup, min_seconds=1.0, max_rounds=64):
+    def timed(step, steps, warmup, min_seconds=1.0, max_rounds=64, adaptive=True):
         """Warm-up: at least `warmup` steps, then on until two consecutive steps agree to 2 % (allocations,
         module loading and clock ramps stay out of the timed region).  Timed: rounds of EXACTLY `steps` steps,
         back to back, every step between its own pair of CUDA events on the launching (torch current) stream,
         repeated until the region is >= min_seconds; barrier + synchronize on both sides.  Seconds per step =
         whole region / steps in it, max over ranks (so a host-side stall that starves the GPU shows up - compare
-        with the per-step median, which does not see it)."""
+        with the per-step median, which does not see it).  adaptive=False: exactly `warmup` warm-up steps - for steps
+        that synchronise the ranks with each other, which every rank must call the same number of times."""
         last, n_warm = None, 0
         e_a, e_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         while True:
             e_a.record(); step(); e_b.record(); e_b.synchronize()
             ms = e_a.elapsed_time(e_b)
             n_warm += 1
-            if n_warm >= warmup and ((last is not None and abs(ms - last) <= 0.02 * last) or n_warm >= warmup + 40):
+            if n_warm >= warmup and (not adaptive or (last is not None and abs(ms - last) <= 0.02 * last)
+                                     or n_warm >= warmup + 40):
                 break
             last = ms
         rounds = int(min(max_rounds, max(1, -(-min_seconds // max(steps * ms * 1e-3, 1e-6)))))
@@ -536,6 +538,23 @@ def run_ours(args) -> None:
                     "of them (parity unpinned, oracle/idg_next_oracle.c)",
         }
         del work, grid
+
+    # ---- N > 1: the grid adder with the grid row-scattered over the ranks (BASELINE config 5): the one
+    # step of the pipeline with a real exchange.  Every rank adds its (FFT'd) subgrids; push / pull / nccl as in
+    # ska_sdp_idg_bench_b200/grid_adder_rs.py, `auto` = the library's rule (idgb200_adder_rs_mode)
+    adder_rs = None
+    if world > 1 and not args.no_compare:
+        G = prob["grid_size"]
+        work = sub_in.clone()
+        idg.subgrid_fft(S, N, work, 1)
+        rs = idg.GridAdderRS(G, dev)
+        adder_rs = {"grid_size": G, "subgrid_size": N, "subgrids_per_gpu": S, "auto_mode": idg.adder_rs_mode(S, N, G),
+                    "what": "memset + adder + reduce-scatter of the 4 x G x G grid by rows, ms per call, max over ranks"}
+        for mode in ("push", "pull", "nccl"):
+            t = timed(lambda: rs.add(S, N, prob["metadata"], work, mode=mode, flags=idg.FLAG_FFT_SHIFT),
+                      args.steps, args.warmup, min_seconds=0.0, adaptive=False)
+            adder_rs[mode + "_ms"] = t["sec_per_step"] * 1e3
+        del work, rs
 
     # ---- CPU baseline + parity sample, rank 0 at N=1 only
     cpu_baseline, parity = None, None
@@ -680,7 +699,7 @@ def run_ours(args) -> None:
                           "gridder": entry(t_gw, "gridder", g_variant), "degridder": entry(t_dw, "degridder", d_variant)},
             "comparators": {name: entry(t, name.split("_")[0], v, "same data (w != 0), one round") for name, (v, t) in cmp_t.items()},
             "reference_gpu": ref_gpu,
-            "cpu_baseline": cpu_baseline, "parity": parity, "e2e": e2e, "next_rows": next_rows,
+            "cpu_baseline": cpu_baseline, "parity": parity, "e2e": e2e, "next_rows": next_rows, "adder_rs": adder_rs,
             "gpu_launches": int(round(t_g["launches_per_step"] * args.steps)),
             "clocks": clocks, "device": idg.device_name(),
         }

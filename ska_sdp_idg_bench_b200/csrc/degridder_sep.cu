@@ -49,6 +49,21 @@ __device__ __forceinline__ float residual_h(const float x, const unsigned short 
   return r;
 }
 
+// All 8 warps wait for the tile's MMAs (~1 us); a try_wait's own suspension is short (ncu: ~10 polls per warp and
+// tile, 13 % of the kernel's instructions), so they sleep between polls and leave the issue slots to the other CTA
+__device__ __forceinline__ void mbar_wait_sleep(unsigned long long *bar_ptr, const unsigned parity) {
+  const unsigned bar = smem_u32(bar_ptr);
+  unsigned done;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+               : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+  for (int spin = 0; !done; spin++) {
+    __nanosleep(150);
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    if (spin > (1 << 22)) __trap();   // a lost arrival must fail loudly, not hang the GPU
+  }
+}
+
 __global__ void __launch_bounds__(DS_THREADS, 2)
 degridder_sep_kernel(const KernelArgs a, const int tmem_cols, int *__restrict__ todo) {
   extern __shared__ __align__(1024) unsigned char smem[];
@@ -215,6 +230,9 @@ degridder_sep_kernel(const KernelArgs a, const int tmem_cols, int *__restrict__ 
   const int q4 = warp & 3, upper = warp >> 2;
   const int ng = N >> 2, g_lo = upper ? (ng + 1) >> 1 : 0, g_hi = upper ? ng : (ng + 1) >> 1;
 
+  // (timestep, block) of the warp's first block of the tile, stepped by 16 blocks per tile
+  int pt = (warp * 2) / ncb, pcb = warp * 2 - pt * ncb;
+  const int step_t = 16 / ncb, step_cb = 16 - step_t * ncb;
   for (int tile = 0; tile < ntiles; tile++) {
     // ---- A rows of blocks 2 warp, 2 warp + 1 of the tile: X_v(x) for the block's 8 channels, hi + lo
 #pragma unroll 1
@@ -222,7 +240,8 @@ degridder_sep_kernel(const KernelArgs a, const int tmem_cols, int *__restrict__ 
       const int blk = tile * 16 + warp * 2 + bi;
       unsigned hi[8], lo[8];
       if (blk < nblk) {
-        const int t = blk / ncb, cb = blk - t * ncb;
+        int t = pt, cb = pcb + bi;
+        if (cb >= ncb) { cb -= ncb; t++; }
         const float idx = __fmaf_rn(__ldg(&g_uvw[3 * t + 2]), n_x, __fmul_rn(__ldg(&g_uvw[3 * t]), l));
         const float *wn8 = s_wn + cb * 8;
         float2 ph[8];
@@ -255,6 +274,8 @@ degridder_sep_kernel(const KernelArgs a, const int tmem_cols, int *__restrict__ 
         }
       }
     }
+    pt += step_t; pcb += step_cb;
+    if (pcb >= ncb) { pcb -= ncb; pt++; }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
     if (warp == 0) {
@@ -274,8 +295,7 @@ degridder_sep_kernel(const KernelArgs a, const int tmem_cols, int *__restrict__ 
       }
       __syncwarp();
     }
-    // the partial sums of the previous tile meet here (its upper halves were written before the barrier above)
-    mbar_wait(mma_done, tile & 1);
+    mbar_wait_sleep(mma_done, tile & 1);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
     // ---- the sum over the rows y: thread = row 32 q4 + lane of the tile, warps q4 and q4 + 4 half of the rows each
