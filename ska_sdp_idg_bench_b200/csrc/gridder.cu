@@ -56,7 +56,7 @@ struct Layout<1> { static constexpr int F4_PER_VIS = 2; static constexpr int ACC
 
 template <int NT, int P, int SCHEME, int MODE, int MINB>
 __global__ void __launch_bounds__(NT, MINB)
-gridder_kernel(const KernelArgs a, const int slabs, const int vis_per_chunk, const int *__restrict__ todo) {
+gridder_kernel(const KernelArgs a, const int slabs, const int vis_per_chunk, const int *__restrict__ gate, const int gate_want) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int F4 = Layout<SCHEME>::F4_PER_VIS;
   constexpr int NACC = Layout<SCHEME>::ACC;
@@ -67,7 +67,7 @@ gridder_kernel(const KernelArgs a, const int slabs, const int vis_per_chunk, con
   const int C = a.nr_channels;
   const int npix = N * N;
   const int s_local = blockIdx.x / slabs;
-  if (todo && !todo[s_local]) return;   // gridder_sep.cu has gridded this subgrid
+  if (gate && gate[s_local] != gate_want) return;   // gridder_sep.cu has gridded this subgrid
   const int slab = blockIdx.x - s_local * slabs;
   const int s = a.subgrid_offset + s_local;
   const int tid = threadIdx.x;
@@ -325,7 +325,7 @@ gridder_kernel(const KernelArgs a, const int slabs, const int vis_per_chunk, con
 }
 
 template <int NT, int P, int SCHEME, int MINB>
-cudaError_t launch_t(const KernelArgs &a, int mode, cudaStream_t stream, const int *todo = nullptr) {
+cudaError_t launch_t(const KernelArgs &a, int mode, cudaStream_t stream, const int *gate = nullptr, int gate_want = 1) {
   const int npix = a.subgrid_size * a.subgrid_size;
   const int slabs = (npix + NT * P - 1) / (NT * P);
   const int C = a.nr_channels;
@@ -336,7 +336,7 @@ cudaError_t launch_t(const KernelArgs &a, int mode, cudaStream_t stream, const i
                       (P % 4 == 0 ? (size_t)3 * (P / 4) * NT * 16 : 0) + (size_t)2 * TB * 3 * 4 +
                       (size_t)(C + 1) * 4;
   if (smem > 200 * 1024) return cudaErrorInvalidValue;
-  void (*k)(const KernelArgs, int, int, const int *) = nullptr;
+  void (*k)(const KernelArgs, int, int, const int *, int) = nullptr;
   switch (mode) {
     case IDGB200_SINCOS_FAST: k = gridder_kernel<NT, P, SCHEME, IDGB200_SINCOS_FAST, MINB>; break;
     case IDGB200_SINCOS_REDUCED: k = gridder_kernel<NT, P, SCHEME, IDGB200_SINCOS_REDUCED, MINB>; break;
@@ -345,7 +345,7 @@ cudaError_t launch_t(const KernelArgs &a, int mode, cudaStream_t stream, const i
   }
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  k<<<dim3((unsigned)a.nr_subgrids * slabs), dim3(NT), smem, stream>>>(a, slabs, vis_per_chunk, todo);
+  k<<<dim3((unsigned)a.nr_subgrids * slabs), dim3(NT), smem, stream>>>(a, slabs, vis_per_chunk, gate, gate_want);
   return cudaGetLastError();
 }
 
@@ -378,10 +378,10 @@ int resolve_gridder_variant(int subgrid_size, int nr_channels, int sincos_mode, 
   return fallback_gridder_variant(subgrid_size, nr_channels);
 }
 
-cudaError_t launch_gridder_fp32(const KernelArgs &a, int sincos_mode, cudaStream_t stream, const int *todo) {
+cudaError_t launch_gridder_fp32(const KernelArgs &a, int sincos_mode, cudaStream_t stream, const int *gate, int gate_want) {
   if (a.nr_subgrids == 0) return cudaSuccess;
-  return a.subgrid_size * a.subgrid_size >= 1024 ? launch_t<128, 8, 3, 4>(a, sincos_mode, stream, todo)
-                                                 : launch_t<128, 4, 3, 4>(a, sincos_mode, stream, todo);
+  return a.subgrid_size * a.subgrid_size >= 1024 ? launch_t<128, 8, 3, 4>(a, sincos_mode, stream, gate, gate_want)
+                                                 : launch_t<128, 4, 3, 4>(a, sincos_mode, stream, gate, gate_want);
 }
 
 cudaError_t launch_gridder(const KernelArgs &a, int sincos_mode, int variant, cudaStream_t stream, int *kernels) {
@@ -408,18 +408,25 @@ cudaError_t launch_gridder(const KernelArgs &a, int sincos_mode, int variant, cu
     case 21:   // tensor-core kernel, phasors of equally spaced channel blocks by rotation (else as 12)
       nk = 1;
       return fast ? launch_gridder_tc(a, 3, true, stream) : cudaErrorInvalidValue;
-    case 30: {   // gridder_sep.cu (row-column form); subgrids it declines go to the per-pixel kernel behind it
+    case 30: {   // gridder_sep.cu (row-column form) and, gated per subgrid by what it finds, two kernels behind it:
+                 // the per-pixel kernel of the shape for the subgrids that are not separable (todo[s] == 1) and the
+                 // FP32 kernel for those whose sums cancel below the fp16 operand's error model (every tile counted
+                 // in cancel[s]); both arrays are zeroed on the stream first
       if (!fast || !gridder_sep_supports(a.subgrid_size, a.nr_channels)) return cudaErrorInvalidValue;
       ScratchLease lease;
-      e = scratch_acquire((size_t)a.nr_subgrids, stream, &lease);
+      e = scratch_acquire(2 * (size_t)a.nr_subgrids, stream, &lease);
       if (e != cudaSuccess) return e;
-      nk = 2;
-      e = launch_gridder_sep(a, lease.ptr, stream);
+      int *todo = lease.ptr, *cancel = lease.ptr + a.nr_subgrids;
+      nk = 3;
+      e = cudaMemsetAsync(lease.ptr, 0, 2 * (size_t)a.nr_subgrids * sizeof(int), stream);
+      int tiles = 0;
+      if (e == cudaSuccess) e = launch_gridder_sep(a, todo, cancel, &tiles, stream);
       if (e == cudaSuccess) {
         const int fb = fallback_gridder_variant(a.subgrid_size, a.nr_channels);
-        e = fb == 10 ? launch_gridder_fp32(a, sincos_mode, stream, lease.ptr)
-                     : launch_gridder_tc(a, fb == 24 ? 11 : 3, true, stream, lease.ptr);
+        e = fb == 10 ? launch_gridder_fp32(a, sincos_mode, stream, todo, 1)
+                     : launch_gridder_tc(a, fb == 24 ? 11 : 3, true, stream, todo);
       }
+      if (e == cudaSuccess) e = launch_gridder_fp32(a, sincos_mode, stream, cancel, tiles);
       const cudaError_t e2 = scratch_release(lease, stream);
       return e != cudaSuccess ? e : e2;
     }

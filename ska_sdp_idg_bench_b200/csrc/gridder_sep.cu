@@ -46,6 +46,12 @@ constexpr int GS_CB = 8;                         // channels per stage -> K = 16
 constexpr int GS_A_BYTES = 128 * 32;             // 128 rows x 16 fp16
 constexpr int GS_VSLOTS = 4;                     // visibility ring slots per warp (256 B each)
 constexpr float SEP_PHASE_TOL = 1e-4f;           // largest dropped phase |gamma| r (rad)
+// Cancellation guard.  The A operand is rounded to fp16 once per term, so a pixel's error is ~2e-4 sqrt(sum |vis|^2)
+// whatever the sum comes to: relative to the RESULT it only stays inside the tolerance while the sums do not cancel.
+// Incoherent (noise-like) visibilities give max_pixels |D_p| ~ 2.6 E_p, E_p = sqrt(sum_v |vis_v[p]|^2); a tile whose
+// pixel sums ALL stay below GS_CANCEL E_p in every polarisation is counted in cancel[subgrid], and a subgrid all of
+// whose tiles are is redone by the FP32 kernel launched behind this one.  Unflagged: max error <~ 7.5e-4 / GS_CANCEL.
+constexpr float GS_CANCEL = 1.0f;
 
 // 8 phasors of one stage: equally spaced channels by rotation + three-term recurrence (gridder_tc.cu),
 // otherwise one sincos per channel.  ph[c] = scale * exp i(off - idx * wn[c]).
@@ -96,7 +102,8 @@ __device__ __forceinline__ void mbar_wait_sleep(const unsigned bar, const unsign
 // XPL: columns per lane (1: tiles of <= 32 columns, 2: of 33..64)
 template <int XPL>
 __global__ void __launch_bounds__(GS_THREADS, XPL == 1 ? 3 : 2)
-gridder_sep_kernel(const KernelArgs a, const int ytiles, const int xtiles, const int tmem_cols, int *__restrict__ todo) {
+gridder_sep_kernel(const KernelArgs a, const int ytiles, const int xtiles, const int tmem_cols, int *__restrict__ todo,
+                   int *__restrict__ cancel) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const int N = a.subgrid_size, C = a.nr_channels;
   const int tiles = ytiles * xtiles;
@@ -117,8 +124,8 @@ gridder_sep_kernel(const KernelArgs a, const int ytiles, const int xtiles, const
   unsigned long long *empty = full + GS_W * 2;                                         // [GS_W][2]
   unsigned long long *done = empty + GS_W * 2;
   unsigned *s_tmem = reinterpret_cast<unsigned *>(done + 1);
-  float *s_red = reinterpret_cast<float *>(s_tmem + 2);   // [16] reductions, scale, verdict
-  float *s_wn = s_red + 16;                               // [ncb * 8], zero padded
+  float *s_red = reinterpret_cast<float *>(s_tmem + 2);   // [48] reductions, scale, verdict, sum |vis|^2 per polarisation
+  float *s_wn = s_red + 48;                               // [ncb * 8], zero padded
   float *s_dw = s_wn + ncb * GS_CB;                       // [ncb]
   int *s_lin = reinterpret_cast<int *>(s_dw + ncb);       // [ncb]
 
@@ -138,19 +145,26 @@ gridder_sep_kernel(const KernelArgs a, const int ytiles, const int xtiles, const
 
   // ---- per subgrid: fp16 scale of the visibilities (gridder_tc.cu) and the separability check
   {
-    float amax = 0.f, wmax = 0.f;
+    float amax = 0.f, wmax = 0.f, ss0 = 0.f, ss1 = 0.f;   // ss: sum |vis|^2 of polarisations (0, 1) (even tid) / (2, 3)
     const float4 *v4 = reinterpret_cast<const float4 *>(g_vis);
-    for (int i = tid; i < nt * C * 2; i += GS_THREADS) {
+    for (int i = tid; i < nt * C * 2; i += GS_THREADS) {    // GS_THREADS is even: a thread keeps its parity
       const float4 q = __ldg(&v4[i]);
       amax = fmaxf(fmaxf(amax, fmaxf(fabsf(q.x), fabsf(q.y))), fmaxf(fabsf(q.z), fabsf(q.w)));
+      ss0 = __fmaf_rn(q.x, q.x, __fmaf_rn(q.y, q.y, ss0));
+      ss1 = __fmaf_rn(q.z, q.z, __fmaf_rn(q.w, q.w, ss1));
     }
     for (int t = tid; t < nt; t += GS_THREADS) wmax = fmaxf(wmax, fabsf(__ldg(&g_uvw[3 * t + 2])));
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
       wmax = fmaxf(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
+      if (o > 1) {   // lanes of one parity
+        ss0 += __shfl_xor_sync(0xffffffffu, ss0, o);
+        ss1 += __shfl_xor_sync(0xffffffffu, ss1, o);
+      }
     }
     if (lane == 0) { s_red[warp] = amax; s_red[5 + warp] = wmax; }
+    if (lane < 2) { s_red[20 + warp * 4 + 2 * lane] = ss0; s_red[20 + warp * 4 + 2 * lane + 1] = ss1; }
     for (int cb = tid; cb < ncb; cb += GS_THREADS) {
       float dw;
       s_lin[cb] = linear_channels(s_wn, cb * GS_CB, min(GS_CB, C - cb * GS_CB), &dw) ? 1 : 0;
@@ -173,7 +187,12 @@ gridder_sep_kernel(const KernelArgs a, const int ytiles, const int xtiles, const
       const double gmax = (double)fabsf(ctx.w_offset) + (double)wmax * (double)kmax;
       const bool sep = gmax * r <= (double)SEP_PHASE_TOL && isfinite(gmax);
       s_red[12] = sep ? 1.f : 0.f;
-      if (tile == 0) todo[s_local] = sep ? 0 : 1;
+      if (tile == 0 && !sep) todo[s_local] = 1;
+      for (int p = 0; p < NR_POL; p++) {          // E_p^2 = sum_v |vis_v[p]|^2
+        float e2 = 0.f;
+        for (int i = 0; i <= GS_W; i++) e2 += s_red[20 + i * 4 + p];
+        s_red[16 + p] = e2;
+      }
     }
     __syncthreads();
   }
@@ -342,6 +361,7 @@ gridder_sep_kernel(const KernelArgs a, const int ytiles, const int xtiles, const
   const int pitch = XT + 1;
   if (warp < GS_W) {
     float2 *row = sD + (warp * 32 + lane) * pitch;
+    float m2 = 0.f;                                 // max |D|^2 of this row (cancellation guard)
     for (int c0 = 0; c0 < XT; c0 += 4) {
       unsigned r[16];
       if (nstages > 0) {
@@ -357,13 +377,24 @@ gridder_sep_kernel(const KernelArgs a, const int ytiles, const int xtiles, const
         for (int i = 0; i < 16; i++) r[i] = 0u;
       }
 #pragma unroll
-      for (int i = 0; i < 4; i++)   // column groups: hi re, hi im, lo re, lo im
-        row[c0 + i] = make_float2((__uint_as_float(r[i]) + __uint_as_float(r[8 + i])) * vis_unscale,
-                                  (__uint_as_float(r[4 + i]) + __uint_as_float(r[12 + i])) * vis_unscale);
+      for (int i = 0; i < 4; i++) {   // column groups: hi re, hi im, lo re, lo im
+        const float2 d = make_float2((__uint_as_float(r[i]) + __uint_as_float(r[8 + i])) * vis_unscale,
+                                     (__uint_as_float(r[4 + i]) + __uint_as_float(r[12 + i])) * vis_unscale);
+        row[c0 + i] = d;
+        m2 = fmaxf(m2, __fmaf_rn(d.x, d.x, __fmul_rn(d.y, d.y)));
+      }
     }
+    if (lane >= ny) m2 = 0.f;                       // rows beyond the tile
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m2 = fmaxf(m2, __shfl_xor_sync(0xffffffffu, m2, o));
+    // polarisation `warp`: every pixel sum of the tile below GS_CANCEL E_p (a polarisation without signal does not object)
+    if (lane == 0) s_red[40 + warp] = (m2 < GS_CANCEL * GS_CANCEL * s_red[16 + warp] || s_red[16 + warp] == 0.f) ? 1.f : 0.f;
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (tid == 0 && nstages > 0 && s_red[40] + s_red[41] + s_red[42] + s_red[43] == 4.f &&
+      s_red[16] + s_red[17] + s_red[18] + s_red[19] > 0.f)
+    atomicAdd(&cancel[s_local], 1);
   {
     const size_t plane = (size_t)N * N;
     const size_t at1 = ((size_t)ctx.aterm_index * a.nr_stations + ctx.station1) * plane;
@@ -397,11 +428,13 @@ bool gridder_sep_supports(int subgrid_size, int nr_channels) {
   return subgrid_size >= 4 && subgrid_size % 4 == 0 && subgrid_size <= 2048 && nr_channels >= 1 && nr_channels <= 4096;
 }
 
-// d_todo[nr_subgrids] (device): written by this launch - 0 = gridded here, 1 = the subgrid's dropped phase term
-// exceeds SEP_PHASE_TOL and it is left to the per-pixel kernel launched behind this one
-cudaError_t launch_gridder_sep(const KernelArgs &a, int *d_todo, cudaStream_t stream) {
+// d_todo / d_cancel [nr_subgrids] (device, zeroed by the caller on the same stream): d_todo[s] = 1 where the subgrid's
+// dropped phase term exceeds SEP_PHASE_TOL (left to the per-pixel kernel launched behind this one), d_cancel[s] = the
+// number of the subgrid's tiles whose sums cancel (== *tiles_per_subgrid: redone by the FP32 kernel behind it)
+cudaError_t launch_gridder_sep(const KernelArgs &a, int *d_todo, int *d_cancel, int *tiles_per_subgrid, cudaStream_t stream) {
+  if (tiles_per_subgrid) *tiles_per_subgrid = ((a.subgrid_size + 31) / 32) * ((a.subgrid_size + 63) / 64);
   if (a.nr_subgrids == 0) return cudaSuccess;
-  if (!gridder_sep_supports(a.subgrid_size, a.nr_channels) || !d_todo) return cudaErrorInvalidValue;
+  if (!gridder_sep_supports(a.subgrid_size, a.nr_channels) || !d_todo || !d_cancel) return cudaErrorInvalidValue;
   const int N = a.subgrid_size;
   const int ytiles = (N + 31) / 32, xtiles = (N + 63) / 64;
   const int xt_max = N < 64 ? N : 64;
@@ -410,11 +443,11 @@ cudaError_t launch_gridder_sep(const KernelArgs &a, int *d_todo, cudaStream_t st
   while (tmem_cols < 4 * xt_max) tmem_cols *= 2;
   const int ncb = (a.nr_channels + GS_CB - 1) / GS_CB;
   const size_t stage_bytes = GS_A_BYTES + (wide ? 4 * 64 * 32 : 4 * 32 * 32);
-  const size_t smem = GS_W * 2 * stage_bytes + GS_W * GS_VSLOTS * 256 + (4 * GS_W + 1) * 8 + 8 + 64 + (size_t)ncb * (GS_CB + 2) * 4;
+  const size_t smem = GS_W * 2 * stage_bytes + GS_W * GS_VSLOTS * 256 + (4 * GS_W + 1) * 8 + 8 + 192 + (size_t)ncb * (GS_CB + 2) * 4;
   auto k = wide ? gridder_sep_kernel<2> : gridder_sep_kernel<1>;
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  k<<<dim3((unsigned)a.nr_subgrids * ytiles * xtiles), dim3(GS_THREADS), smem, stream>>>(a, ytiles, xtiles, tmem_cols, d_todo);
+  k<<<dim3((unsigned)a.nr_subgrids * ytiles * xtiles), dim3(GS_THREADS), smem, stream>>>(a, ytiles, xtiles, tmem_cols, d_todo, d_cancel);
   return cudaGetLastError();
 }
 

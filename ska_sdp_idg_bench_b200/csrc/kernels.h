@@ -39,12 +39,15 @@ int resolve_degridder_variant(int subgrid_size, int nr_channels, int sincos_mode
 // todo (device, may be null): per-subgrid flags of this launch; subgrids whose flag is 0 are skipped
 cudaError_t launch_gridder_tc(const KernelArgs &a, int poly, bool recur, cudaStream_t stream, const int *todo = nullptr);
 // FP32 gridder (gridder.cu) with the same per-subgrid gate
-cudaError_t launch_gridder_fp32(const KernelArgs &a, int sincos_mode, cudaStream_t stream, const int *todo = nullptr);
+// gate (device, may be null): the launch serves the subgrids with gate[s] == gate_want only
+cudaError_t launch_gridder_fp32(const KernelArgs &a, int sincos_mode, cudaStream_t stream, const int *gate = nullptr,
+                                int gate_want = 1);
 // row-column gridder (gridder_sep.cu): one GEMM per subgrid with the visibilities as K.  Writes
-// d_todo[nr_subgrids]: 0 = gridded, 1 = left to the per-pixel kernel launched behind it (the subgrid's
-// non-separable phase term is too large)
+// d_todo[nr_subgrids] = 1 where the subgrid is left to the per-pixel kernel launched behind it (its non-separable
+// phase term is too large); d_cancel[nr_subgrids] += 1 per tile whose pixel sums all cancel below the fp16 operand's
+// error model (== *tiles_per_subgrid: the FP32 kernel behind it redoes the subgrid).  Both zeroed by the caller.
 bool gridder_sep_supports(int subgrid_size, int nr_channels);
-cudaError_t launch_gridder_sep(const KernelArgs &a, int *d_todo, cudaStream_t stream);
+cudaError_t launch_gridder_sep(const KernelArgs &a, int *d_todo, int *d_cancel, int *tiles_per_subgrid, cudaStream_t stream);
 // row-column degridder (degridder_sep.cu); d_todo as for launch_gridder_sep (the per-pixel kernels read KernelArgs::todo)
 bool degridder_sep_supports(int subgrid_size, int nr_channels);
 cudaError_t launch_degridder_sep(const KernelArgs &a, int *d_todo, cudaStream_t stream);
