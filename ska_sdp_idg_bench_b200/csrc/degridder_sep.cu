@@ -235,8 +235,8 @@ degridder_sep_kernel(const KernelArgs a, const int tmem_cols, int *__restrict__ 
   const int step_t = 16 / ncb, step_cb = 16 - step_t * ncb;
   for (int tile = 0; tile < ntiles; tile++) {
     // ---- A rows of blocks 2 warp, 2 warp + 1 of the tile: X_v(x) for the block's 8 channels, hi + lo
-#pragma unroll 1
-    for (int bi = 0; bi < 2; bi++) {
+#pragma unroll
+    for (int bi = 0; bi < 2; bi++) {   // both blocks unrolled: two independent chains in flight
       const int blk = tile * 16 + warp * 2 + bi;
       unsigned hi[8], lo[8];
       if (blk < nblk) {

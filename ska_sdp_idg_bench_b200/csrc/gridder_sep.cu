@@ -53,26 +53,6 @@ constexpr float SEP_PHASE_TOL = 1e-4f;           // largest dropped phase |gamma
 // whose tiles are is redone by the FP32 kernel launched behind this one.  Unflagged: max error <~ 7.5e-4 / GS_CANCEL.
 constexpr float GS_CANCEL = 1.0f;
 
-// 8 phasors of one stage: equally spaced channels by rotation + three-term recurrence (gridder_tc.cu),
-// otherwise one sincos per channel.  ph[c] = scale * exp i(off - idx * wn[c]).
-__device__ __forceinline__ void stage_phasors(float2 (&ph)[GS_CB], const float idx, const float off, const float *wn8,
-                                              const bool linear, const float dw, const float scale) {
-  if (linear) {
-    float2 p0 = phasor<IDGB200_SINCOS_FAST>(__fmaf_rn(-idx, wn8[0], off));
-    const float2 d = phasor<IDGB200_SINCOS_FAST>(__fmul_rn(-idx, dw));
-    p0 = __fmul2_rn(p0, make_float2(scale, scale));
-    ph[0] = p0;
-    ph[1] = ffma2(make_float2(p0.y, p0.x), make_float2(-d.y, d.y), __fmul2_rn(p0, make_float2(d.x, d.x)));
-    const float c2 = __fadd_rn(d.x, d.x);
-#pragma unroll
-    for (int i = 2; i < GS_CB; i++) ph[i] = ffma2(ph[i - 1], make_float2(c2, c2), make_float2(-ph[i - 2].x, -ph[i - 2].y));
-  } else {
-#pragma unroll
-    for (int i = 0; i < GS_CB; i++)
-      ph[i] = __fmul2_rn(phasor<IDGB200_SINCOS_FAST>(__fmaf_rn(-idx, wn8[i], off)), make_float2(scale, scale));
-  }
-}
-
 __device__ __forceinline__ unsigned pack_h2(const float lo, const float hi) {
   const __half2 h = __floats2half2_rn(lo, hi);
   return *reinterpret_cast<const unsigned *>(&h);
@@ -259,25 +239,65 @@ gridder_sep_kernel(const KernelArgs a, const int ytiles, const int xtiles, const
       cp_async_commit();
       ft += dt; fcb += dcb;
       if (fcb >= ncb) { fcb -= ncb; ft++; }
+      // ---- the stage's phasors first, row and column chains together in one straight-line block (they only need
+      // registers, so they run before the waits for the visibilities and for the stage buffer)
+      const float *wn8 = s_wn + cb * GS_CB;
+      const bool lin = s_lin[cb] != 0;
+      const float dw = s_dw[cb];
+      float2 phy[GS_CB], phx[XPL][GS_CB];
+      {
+        float idx[1 + XPL], off[1 + XPL];
+        idx[0] = __fmaf_rn(w, n_y, __fmul_rn(v, m));
+        off[0] = off_y;
+#pragma unroll
+        for (int xi = 0; xi < XPL; xi++) {
+          idx[1 + xi] = __fmaf_rn(w, n_x[xi], __fmul_rn(u, l[xi]));
+          off[1 + xi] = off_x[xi];
+        }
+        if (lin) {   // first channel by sincos, second by one rotation, then ph[c+1] = 2 cos(delta) ph[c] - ph[c-1]
+          float2 p0[1 + XPL], p1[1 + XPL];
+          float c2[1 + XPL];
+#pragma unroll
+          for (int q = 0; q < 1 + XPL; q++) {
+            p0[q] = phasor<IDGB200_SINCOS_FAST>(__fmaf_rn(-idx[q], wn8[0], off[q]));
+            const float2 d = phasor<IDGB200_SINCOS_FAST>(__fmul_rn(-idx[q], dw));
+            if (q == 0) p0[q] = __fmul2_rn(p0[q], make_float2(vis_scale, vis_scale));
+            p1[q] = ffma2(make_float2(p0[q].y, p0[q].x), make_float2(-d.y, d.y), __fmul2_rn(p0[q], make_float2(d.x, d.x)));
+            c2[q] = __fadd_rn(d.x, d.x);
+          }
+          phy[0] = p0[0]; phy[1] = p1[0];
+#pragma unroll
+          for (int xi = 0; xi < XPL; xi++) { phx[xi][0] = p0[1 + xi]; phx[xi][1] = p1[1 + xi]; }
+#pragma unroll
+          for (int i = 2; i < GS_CB; i++) {
+            phy[i] = ffma2(phy[i - 1], make_float2(c2[0], c2[0]), make_float2(-phy[i - 2].x, -phy[i - 2].y));
+#pragma unroll
+            for (int xi = 0; xi < XPL; xi++)
+              phx[xi][i] = ffma2(phx[xi][i - 1], make_float2(c2[1 + xi], c2[1 + xi]), make_float2(-phx[xi][i - 2].x, -phx[xi][i - 2].y));
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < GS_CB; i++) {
+            phy[i] = __fmul2_rn(phasor<IDGB200_SINCOS_FAST>(__fmaf_rn(-idx[0], wn8[i], off[0])), make_float2(vis_scale, vis_scale));
+#pragma unroll
+            for (int xi = 0; xi < XPL; xi++) phx[xi][i] = phasor<IDGB200_SINCOS_FAST>(__fmaf_rn(-idx[1 + xi], wn8[i], off[1 + xi]));
+          }
+        }
+      }
       asm volatile("cp.async.wait_group 2;\n" ::: "memory");
       __syncwarp();
       if (j >= 2) mbar_wait_u(empty_u + buf * 8, ((j >> 1) - 1) & 1);
 
       unsigned char *A = my_stage + buf * stage_bytes, *B = A + GS_A_BYTES;
-      const float *wn8 = s_wn + cb * GS_CB;
-      const bool lin = s_lin[cb] != 0;
-      const float dw = s_dw[cb];
       {
         // ---- A rows (p, y): fp16 of scale * Y_c(y) * vis[c][p]
-        float2 ph[GS_CB];
-        stage_phasors(ph, __fmaf_rn(w, n_y, __fmul_rn(v, m)), off_y, wn8, lin, dw, vis_scale);
         const float4 *vs = reinterpret_cast<const float4 *>(my_vis + (j & (GS_VSLOTS - 1)) * 256);
 #pragma unroll
         for (int kc = 0; kc < 2; kc++) {
           unsigned pk[NR_POL][4];
 #pragma unroll
           for (int i = 0; i < 4; i++) {
-            const float2 y = ph[kc * 4 + i];
+            const float2 y = phy[kc * 4 + i];
             const float2 yxx = make_float2(y.x, y.x), yny = make_float2(-y.y, y.y);
             const float4 q0 = vs[(kc * 4 + i) * 2], q1 = vs[(kc * 4 + i) * 2 + 1];   // broadcast loads
             const float2 vv[NR_POL] = {make_float2(q0.x, q0.y), make_float2(q0.z, q0.w), make_float2(q1.x, q1.y),
@@ -296,23 +316,21 @@ gridder_sep_kernel(const KernelArgs a, const int ytiles, const int xtiles, const
 #pragma unroll
       for (int xi = 0; xi < XPL; xi++) {
         // ---- B rows of column x: (hi|lo, re|im) x XT; re row = (cos, -sin), im row = (sin, cos) per visibility
-        float2 ph[GS_CB];
-        stage_phasors(ph, __fmaf_rn(w, n_x[xi], __fmul_rn(u, l[xi])), off_x[xi], wn8, lin, dw, 1.f);
         const int xx = lane + 32 * xi;
-        if (xx < XT) {
 #pragma unroll
-          for (int kc = 0; kc < 2; kc++) {
-            unsigned hre[4], him[4], lre[4], lim[4];
+        for (int kc = 0; kc < 2; kc++) {
+          unsigned hre[4], him[4], lre[4], lim[4];
 #pragma unroll
-            for (int i = 0; i < 4; i++) {
-              const float2 x = ph[kc * 4 + i];
-              him[i] = pack_h2(x.y, x.x);
-              hre[i] = pack_h2(x.x, -x.y);
-              const float rs = residual_h(x.y, (unsigned short)(him[i] & 0xffffu));
-              const float rc = residual_h(x.x, (unsigned short)(him[i] >> 16));
-              lim[i] = pack_h2(rs, rc);
-              lre[i] = pack_h2(rc, -rs);
-            }
+          for (int i = 0; i < 4; i++) {
+            const float2 x = phx[xi][kc * 4 + i];
+            him[i] = pack_h2(x.y, x.x);
+            hre[i] = pack_h2(x.x, -x.y);
+            const float rs = residual_h(x.y, (unsigned short)(him[i] & 0xffffu));
+            const float rc = residual_h(x.x, (unsigned short)(him[i] >> 16));
+            lim[i] = pack_h2(rs, rc);
+            lre[i] = pack_h2(rc, -rs);
+          }
+          if (xx < XT) {
             unsigned char *Bk = B + kc * (4 * XT * 16) + xx * 16;
             *reinterpret_cast<uint4 *>(Bk) = make_uint4(hre[0], hre[1], hre[2], hre[3]);
             *reinterpret_cast<uint4 *>(Bk + XT * 16) = make_uint4(him[0], him[1], him[2], him[3]);

@@ -43,6 +43,8 @@ def main():
     ap.add_argument("--chunks-per-rank", type=int, default=2)
     ap.add_argument("--full", action="store_true", help="the whole observation (all chunks)")
     ap.add_argument("--sincos", default="fast", choices=["fast", "reduced", "accurate"])
+    ap.add_argument("--w-sigma", type=float, default=0.0,
+                    help="w ~ N(0, sigma) metres on every timestep (the reference's generator writes w = 0)")
     args = ap.parse_args()
 
     import torch
@@ -74,6 +76,9 @@ def main():
         prob = idg.init_problem_device(nr_stations=NR_STATIONS, nr_timeslots=1, nr_timesteps=NR_TIMESTEPS,
                                        nr_channels=NR_CHANNELS, subgrid_size=SUBGRID, nr_subgrids=S,
                                        seed=1 + ts * 1000 + q, device=dev)
+        if args.w_sigma > 0:
+            gen = torch.Generator(device=dev).manual_seed(7 + ts * 1000 + q)
+            prob["uvw"][:, 2] = torch.randn(prob["uvw"].shape[0], device=dev, generator=gen) * args.w_sigma
         scal = (S, prob["grid_size"], SUBGRID, prob["image_size"], 0.0, NR_CHANNELS, NR_STATIONS,
                 prob["total_timesteps"])
         sub_in = prob["subgrids"].clone()
@@ -117,7 +122,7 @@ def main():
                           "mvis_per_s": total_vis / (float(mx[1]) * 1e-3) * 1e-6,
                           "variant": idg.resolve_variant(SUBGRID, NR_CHANNELS, sincos, 0, gridder=False)},
             "wall_seconds_incl_input_generation": float(mx[3]),
-            "sincos": args.sincos, "data": "synthetic, generated on device per chunk",
+            "sincos": args.sincos, "w_sigma_m": args.w_sigma, "data": "synthetic, generated on device per chunk",
             "sharding": "chunks dealt round-robin over ranks, no collective on the kernel path",
         }
         print(json.dumps(out))
