@@ -387,7 +387,7 @@ def run_ours(args) -> None:
     def all_max(x: float) -> float:
         return reduce_max_time(x, dev)
 
-    def timed(step, steps, warmup, min_seconds=1.0, max_rounds=64, adaptive=True):
+    def timed(step, steps, warmup, min_seconds=None, max_rounds=64, adaptive=True):
         """Warm-up: at least `warmup` steps, then on until two consecutive steps agree to 2 % (allocations,
         module loading and clock ramps stay out of the timed region).  Timed: rounds of EXACTLY `steps` steps,
         back to back, every step between its own pair of CUDA events on the launching (torch current) stream,
@@ -395,6 +395,8 @@ def run_ours(args) -> None:
         whole region / steps in it, max over ranks (so a host-side stall that starves the GPU shows up - compare
         with the per-step median, which does not see it).  adaptive=False: exactly `warmup` warm-up steps - for steps
         that synchronise the ranks with each other, which every rank must call the same number of times."""
+        if min_seconds is None:
+            min_seconds = args.min_seconds
         last, n_warm = None, 0
         e_a, e_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         while True:
@@ -722,6 +724,9 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-compare", action="store_true")
+    ap.add_argument("--min-seconds", type=float, default=1.0,
+                    help="rounds of --steps steps are repeated until the timed region is this long (0: one round; "
+                         "for runs under ncu)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

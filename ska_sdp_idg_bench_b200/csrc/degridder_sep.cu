@@ -37,6 +37,7 @@ constexpr int DS_THREADS = 256;
 constexpr int DS_A_CH = 128 * 16 + 16;           // one 16-byte K chunk of 128 rows, padded: the 8 chunks a warp's
                                                  // 4-byte stores touch fall into different banks
 constexpr float SEP_PHASE_TOL = 1e-4f;           // largest dropped phase |gamma| r (rad), as in gridder_sep.cu
+constexpr int DS_UVW_STAGED = 384;               // timesteps whose uvw are staged in shared memory (longer subgrids read global)
 
 __device__ __forceinline__ unsigned pack_h2(const float lo, const float hi) {
   const __half2 h = __floats2half2_rn(lo, hi);
@@ -80,7 +81,8 @@ degridder_sep_kernel(const KernelArgs a, const int tmem_cols, int *__restrict__ 
   unsigned char *sA = sB + 2 * KCp * b_ch;                              // [hi|lo][KCp][DS_A_CH]
   float4 *sGeo = reinterpret_cast<float4 *>(sA + 2 * KCp * DS_A_CH);    // [N] (m_y, f(m_y^2), offset_y, 0)
   float4 *sPart = sGeo + N;                                             // [128][2] partial sums of the upper warps
-  unsigned long long *mma_done = reinterpret_cast<unsigned long long *>(sPart + 256);
+  float *s_uvw = reinterpret_cast<float *>(sPart + 256);                // [DS_UVW_STAGED][3]
+  unsigned long long *mma_done = reinterpret_cast<unsigned long long *>(s_uvw + DS_UVW_STAGED * 3);
   unsigned *s_tmem = reinterpret_cast<unsigned *>(mma_done + 1);
   float *s_red = reinterpret_cast<float *>(s_tmem + 2);                 // [16]
   float *s_wn = s_red + 16;                                             // [ncb * 8]
@@ -94,6 +96,10 @@ degridder_sep_kernel(const KernelArgs a, const int tmem_cols, int *__restrict__ 
   const float *g_uvw = reinterpret_cast<const float *>(a.uvw) + (size_t)ctx.time_offset * 3;
 
   for (int c = tid; c < ncb * 8; c += DS_THREADS) s_wn[c] = c < C ? a.wavenumbers[c] : 0.f;
+  const bool staged = nt <= DS_UVW_STAGED;   // uvw of the whole subgrid in shared memory: no global load in the tile loop
+  if (staged)
+    for (int i = tid; i < nt * 3; i += DS_THREADS) s_uvw[i] = __ldg(&g_uvw[i]);
+  auto uvw_at = [&](int i) { return staged ? s_uvw[i] : __ldg(&g_uvw[i]); };
   if (tid < N) {
     const float m = compute_l(tid, N, a.image_size);
     const float n_y = compute_n(m, 0.f);
@@ -242,7 +248,7 @@ degridder_sep_kernel(const KernelArgs a, const int tmem_cols, int *__restrict__ 
       if (blk < nblk) {
         int t = pt, cb = pcb + bi;
         if (cb >= ncb) { cb -= ncb; t++; }
-        const float idx = __fmaf_rn(__ldg(&g_uvw[3 * t + 2]), n_x, __fmul_rn(__ldg(&g_uvw[3 * t]), l));
+        const float idx = __fmaf_rn(uvw_at(3 * t + 2), n_x, __fmul_rn(uvw_at(3 * t), l));
         const float *wn8 = s_wn + cb * 8;
         float2 ph[8];
         if (s_lin[cb]) {   // first channel by sincos, second by one rotation, then the three-term recurrence
@@ -307,7 +313,7 @@ degridder_sep_kernel(const KernelArgs a, const int tmem_cols, int *__restrict__ 
       const int c = cb * 8 + (r_tile & 7);
       const bool valid = in_range && c < C;
       const float k = s_wn[cb * 8 + (r_tile & 7)];
-      const float vt = __ldg(&g_uvw[3 * t + 1]), wt = __ldg(&g_uvw[3 * t + 2]);
+      const float vt = uvw_at(3 * t + 1), wt = uvw_at(3 * t + 2);
       float2 acc[NR_POL];
 #pragma unroll
       for (int p = 0; p < NR_POL; p++) acc[p] = make_float2(0.f, 0.f);
@@ -371,7 +377,7 @@ cudaError_t launch_degridder_sep(const KernelArgs &a, int *d_todo, cudaStream_t 
   const int N = a.subgrid_size, KC = N / 4, KCp = (KC + 1) & ~1, ncols = 8 * N, ncb = (a.nr_channels + 7) / 8;
   int tmem_cols = 32;
   while (tmem_cols < ncols) tmem_cols *= 2;
-  const size_t smem = (size_t)2 * KCp * (ncols * 16 + 16) + (size_t)2 * KCp * DS_A_CH + (size_t)N * 16 + 256 * 16 + 8 + 8 + 64 +
+  const size_t smem = (size_t)2 * KCp * (ncols * 16 + 16) + (size_t)2 * KCp * DS_A_CH + (size_t)N * 16 + 256 * 16 + DS_UVW_STAGED * 12 + 8 + 8 + 64 +
                       (size_t)ncb * 10 * 4;
   cudaError_t e = cudaFuncSetAttribute(degridder_sep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;

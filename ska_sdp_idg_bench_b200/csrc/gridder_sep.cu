@@ -216,29 +216,32 @@ gridder_sep_kernel(const KernelArgs a, const int ytiles, const int xtiles, const
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(src), "r"(valid ? 16 : 0));
       }
     };
-    // my stages: flat index warp + j * GS_W -> (t, cb); one step = dt timesteps and dcb blocks
+    // my stages: flat index warp + j * GS_W -> (t, cb); one step = dt timesteps and dcb blocks.  Global loads are
+    // issued at the END of an iteration, behind the stage's fence (fence.proxy.async is a MEMBAR.ALL.CTA in SASS: it
+    // waits for every load in flight, so anything issued ahead of it is paid at the fence): the visibilities of the
+    // stage three ahead into the ring (4 slots), uvw of the stage two ahead into registers.
     const int dt = GS_W / ncb, dcb = GS_W - dt * ncb;
-    int ft = warp / ncb, fcb = warp - ft * ncb;  // stage being fetched
-    for (int pre = 0; pre < 2; pre++) {
+    auto advance = [&](int &tt, int &cc) {
+      tt += dt; cc += dcb;
+      if (cc >= ncb) { cc -= ncb; tt++; }
+    };
+    int ft = warp / ncb, fcb = warp - ft * ncb;  // stage whose visibilities are fetched next
+    for (int pre = 0; pre < 3; pre++) {
       if (ft < nt) fetch_vis(ft, fcb, pre);
       cp_async_commit();
-      ft += dt; fcb += dcb;
-      if (fcb >= ncb) { fcb -= ncb; ft++; }
+      advance(ft, fcb);
     }
     int t = warp / ncb, cb = warp - t * ncb;
-    float u = 0.f, v = 0.f, w = 0.f;
-    if (t < nt) { u = __ldg(&g_uvw[3 * t]); v = __ldg(&g_uvw[3 * t + 1]); w = __ldg(&g_uvw[3 * t + 2]); }
+    int ut = t, ucb = cb;                        // stage whose uvw are loaded next
+    float u = 0.f, v = 0.f, w = 0.f, u1 = 0.f, v1 = 0.f, w1 = 0.f;
+    if (ut < nt) { u = __ldg(&g_uvw[3 * ut]); v = __ldg(&g_uvw[3 * ut + 1]); w = __ldg(&g_uvw[3 * ut + 2]); }
+    advance(ut, ucb);
+    if (ut < nt) { u1 = __ldg(&g_uvw[3 * ut]); v1 = __ldg(&g_uvw[3 * ut + 1]); w1 = __ldg(&g_uvw[3 * ut + 2]); }
+    advance(ut, ucb);
     for (int j = 0; t < nt; j++) {
       const int buf = j & 1;
-      // next stage's coordinates and uvw, this stage's visibilities
-      int tn = t + dt, cbn = cb + dcb;
-      if (cbn >= ncb) { cbn -= ncb; tn++; }
-      float un = 0.f, vn = 0.f, wnx = 0.f;
-      if (tn < nt) { un = __ldg(&g_uvw[3 * tn]); vn = __ldg(&g_uvw[3 * tn + 1]); wnx = __ldg(&g_uvw[3 * tn + 2]); }
-      if (ft < nt) fetch_vis(ft, fcb, (j + 2) & (GS_VSLOTS - 1));
-      cp_async_commit();
-      ft += dt; fcb += dcb;
-      if (fcb >= ncb) { fcb -= ncb; ft++; }
+      int tn = t, cbn = cb;
+      advance(tn, cbn);
       // ---- the stage's phasors first, row and column chains together in one straight-line block (they only need
       // registers, so they run before the waits for the visibilities and for the stage buffer)
       const float *wn8 = s_wn + cb * GS_CB;
@@ -342,7 +345,16 @@ gridder_sep_kernel(const KernelArgs a, const int ytiles, const int xtiles, const
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncwarp();
       if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(full_u + buf * 8) : "memory");
-      t = tn; cb = cbn; u = un; v = vn; w = wnx;
+      // behind the fence: visibilities of stage j + 3 (its slot held stage j - 1), uvw of stage j + 2
+      if (ft < nt) fetch_vis(ft, fcb, (j + 3) & (GS_VSLOTS - 1));
+      cp_async_commit();
+      advance(ft, fcb);
+      float u2 = 0.f, v2 = 0.f, w2 = 0.f;
+      if (ut < nt) { u2 = __ldg(&g_uvw[3 * ut]); v2 = __ldg(&g_uvw[3 * ut + 1]); w2 = __ldg(&g_uvw[3 * ut + 2]); }
+      advance(ut, ucb);
+      t = tn; cb = cbn;
+      u = u1; v = v1; w = w1;
+      u1 = u2; v1 = v2; w1 = w2;
     }
     asm volatile("cp.async.wait_all;\n" ::: "memory");
   } else {
