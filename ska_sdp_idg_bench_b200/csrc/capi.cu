@@ -85,7 +85,7 @@ KernelArgs make_args(const idgb200_params *p, const idgb200_uvw *uvw, const floa
   a.nr_subgrids = p->nr_subgrids;
   a.subgrid_offset = 0;
   a.flags = p->flags;
-  a.todo = nullptr;
+  a.list = nullptr;
   return a;
 }
 

@@ -39,10 +39,8 @@ constexpr int TILE = 1024;  // pixels resident in shared memory at a time (64 KB
 
 // SCHEME 3 (default): swizzled FFMA2 on 48-byte pixel records
 // SCHEME 1: scalar FFMA baseline (same records)
-template <int NT, int V, int SCHEME, int MODE, int MINB>
-__global__ void __launch_bounds__(NT, MINB)
-degridder_kernel(const KernelArgs a) {
-  if (a.todo && !a.todo[blockIdx.x]) return;   // degridder_sep.cu has degridded this subgrid
+template <int NT, int V, int SCHEME, int MODE>
+__device__ __forceinline__ void degridder_body(const KernelArgs &a, const int s_local) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float4 *s_pix = reinterpret_cast<float4 *>(smem_raw);   // [3][TILE] records, component-major
   float4 *s_lmno = s_pix + 3 * TILE;                       // [TILE]    (l, m, n, phase_offset)
@@ -50,7 +48,7 @@ degridder_kernel(const KernelArgs a) {
   const int N = a.subgrid_size;
   const int C = a.nr_channels;
   const int npix = N * N;
-  const int s = a.subgrid_offset + blockIdx.x;
+  const int s = a.subgrid_offset + s_local;
   const int tid = threadIdx.x;
   const SubgridCtx ctx = load_ctx(a, s);
   const int nt = ctx.nr_timesteps;
@@ -191,19 +189,38 @@ degridder_kernel(const KernelArgs a) {
   }
 }
 
+// LIST = false: CTA = subgrid blockIdx.x; LIST = true: a fixed number of CTAs loop over the subgrids of a.list
+template <int NT, int V, int SCHEME, int MODE, int MINB, bool LIST>
+__global__ void __launch_bounds__(NT, MINB)
+degridder_kernel(const KernelArgs a) {
+  if (!LIST) {
+    degridder_body<NT, V, SCHEME, MODE>(a, blockIdx.x);
+  } else {
+    const int total = a.list[0];
+    for (int i = blockIdx.x; i < total; i += gridDim.x) {
+      degridder_body<NT, V, SCHEME, MODE>(a, a.list[1 + i]);
+      __syncthreads();
+    }
+  }
+}
+
 template <int NT, int V, int SCHEME, int MINB>
 cudaError_t launch_t(const KernelArgs &a, int mode, cudaStream_t stream) {
   const size_t smem = (size_t)4 * TILE * sizeof(float4);
   void (*k)(const KernelArgs) = nullptr;
+  const bool list = a.list != nullptr;
   switch (mode) {
-    case IDGB200_SINCOS_FAST: k = degridder_kernel<NT, V, SCHEME, IDGB200_SINCOS_FAST, MINB>; break;
-    case IDGB200_SINCOS_REDUCED: k = degridder_kernel<NT, V, SCHEME, IDGB200_SINCOS_REDUCED, MINB>; break;
-    case IDGB200_SINCOS_ACCURATE: k = degridder_kernel<NT, V, SCHEME, IDGB200_SINCOS_ACCURATE, MINB>; break;
+    case IDGB200_SINCOS_FAST:
+      k = list ? degridder_kernel<NT, V, SCHEME, IDGB200_SINCOS_FAST, MINB, true> : degridder_kernel<NT, V, SCHEME, IDGB200_SINCOS_FAST, MINB, false>;
+      break;
+    case IDGB200_SINCOS_REDUCED: k = degridder_kernel<NT, V, SCHEME, IDGB200_SINCOS_REDUCED, MINB, false>; break;
+    case IDGB200_SINCOS_ACCURATE: k = degridder_kernel<NT, V, SCHEME, IDGB200_SINCOS_ACCURATE, MINB, false>; break;
     default: return cudaErrorInvalidValue;
   }
+  if (list && mode != IDGB200_SINCOS_FAST) return cudaErrorInvalidValue;   // work lists come from the FAST row-column kernel
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  k<<<dim3((unsigned)a.nr_subgrids), dim3(NT), smem, stream>>>(a);
+  k<<<dim3((unsigned)(list && a.nr_subgrids > LIST_MODE_CTAS ? LIST_MODE_CTAS : a.nr_subgrids)), dim3(NT), smem, stream>>>(a);
   return cudaGetLastError();
 }
 
@@ -260,14 +277,15 @@ cudaError_t launch_degridder(const KernelArgs &a, int sincos_mode, int variant, 
                                           : cudaErrorInvalidValue;
     case 30: {   // degridder_sep.cu (row-column form); subgrids it declines go to the per-pixel kernel behind it
       if (!fast || !degridder_sep_supports(a.subgrid_size, a.nr_channels)) return cudaErrorInvalidValue;
-      ScratchLease lease;
-      cudaError_t e = scratch_acquire((size_t)a.nr_subgrids, stream, &lease);
+      ScratchLease lease;   // { n_todo, todo[S] }: the subgrids the row-column kernel leaves to the per-pixel kernel
+      cudaError_t e = scratch_acquire((size_t)a.nr_subgrids + 1, stream, &lease);
       if (e != cudaSuccess) return e;
       nk = 2;
-      e = launch_degridder_sep(a, lease.ptr, stream);
+      e = cudaMemsetAsync(lease.ptr, 0, sizeof(int), stream);
+      if (e == cudaSuccess) e = launch_degridder_sep(a, lease.ptr, stream);
       if (e == cudaSuccess) {
         KernelArgs b = a;
-        b.todo = lease.ptr;
+        b.list = lease.ptr;
         const int fb = fallback_degridder_variant(a.subgrid_size, a.nr_channels);
         e = fb == 4 ? launch_t<256, 8, 3, 2>(b, sincos_mode, stream)
             : fb == 24 ? launch_degridder_tc8(b, true, true, stream) : launch_degridder_tc(b, 10, true, stream);

@@ -135,7 +135,7 @@ degridder_sep_kernel(const KernelArgs a, const int tmem_cols, int *__restrict__ 
       const double gmax = (double)fabsf(ctx.w_offset) + (double)wmax * (double)kmax;
       const bool sep = gmax * r <= (double)SEP_PHASE_TOL && isfinite(gmax);
       s_red[12] = sep ? 1.f : 0.f;
-      todo[s_local] = sep ? 0 : 1;
+      if (!sep) todo[1 + atomicAdd(&todo[0], 1)] = s_local;   // work list of the per-pixel kernel
     }
     __syncthreads();
   }
@@ -369,8 +369,8 @@ bool degridder_sep_supports(int subgrid_size, int nr_channels) {
   return subgrid_size >= 4 && subgrid_size % 4 == 0 && subgrid_size <= 32 && nr_channels >= 1 && nr_channels <= 4096;
 }
 
-// d_todo[nr_subgrids] (device): written by this launch - 0 = degridded here, 1 = left to the per-pixel kernel
-// launched behind this one
+// d_todo = { n, subgrid[n] } (device; n zeroed by the caller on the same stream): the subgrids left to the per-pixel
+// kernel launched behind this one
 cudaError_t launch_degridder_sep(const KernelArgs &a, int *d_todo, cudaStream_t stream) {
   if (a.nr_subgrids == 0) return cudaSuccess;
   if (!degridder_sep_supports(a.subgrid_size, a.nr_channels) || !d_todo) return cudaErrorInvalidValue;

@@ -135,13 +135,11 @@ __device__ __forceinline__ void dtc_produce_linear(unsigned char *A, const float
 // SPLIT: fp16 hi + lo phasors: the tile's two A buffers hold the hi and the lo block of ONE stage (two
 //        MMAs against the same B slot; a warp then waits for its own MMAs every stage)
 // recur: quads of equally spaced channels get their phasors by rotation from the quad's first channel
-template <unsigned MASK8, bool SPLIT>
-__global__ void __launch_bounds__(D_THREADS, 3)
-degridder_tc_kernel(const KernelArgs a, const int recur) {
-  if (a.todo && !a.todo[blockIdx.x]) return;   // degridder_sep.cu has degridded this subgrid
+template <unsigned MASK8, bool SPLIT, bool LIST>
+__device__ __forceinline__ void degridder_tc_body(const KernelArgs &a, const int recur, const int s_local) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const int N = a.subgrid_size, C = a.nr_channels, npix = N * N;
-  const int s = a.subgrid_offset + blockIdx.x;
+  const int s = a.subgrid_offset + s_local;
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);     // warp-uniform for the compiler too
   constexpr int NW = D_MAX_TILES;                             // producer warps; warp NW builds B
@@ -180,7 +178,7 @@ degridder_tc_kernel(const KernelArgs a, const int recur) {
   }
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(D_TMEM_COLS));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    if (!LIST) asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);   // a list-mode CTA allocates again
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -378,6 +376,22 @@ degridder_tc_kernel(const KernelArgs a, const int recur) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(D_TMEM_COLS));
 }
 
+// LIST = false: CTA = subgrid blockIdx.x; LIST = true: a fixed number of CTAs loop over the subgrids of a.list
+// (what degridder_sep.cu left: the work is rare, the launch must be cheap when the list is empty)
+template <unsigned MASK8, bool SPLIT, bool LIST>
+__global__ void __launch_bounds__(D_THREADS, 3)
+degridder_tc_kernel(const KernelArgs a, const int recur) {
+  if (!LIST) {
+    degridder_tc_body<MASK8, SPLIT, false>(a, recur, blockIdx.x);
+  } else {
+    const int total = a.list[0];
+    for (int i = blockIdx.x; i < total; i += gridDim.x) {
+      degridder_tc_body<MASK8, SPLIT, true>(a, recur, a.list[1 + i]);
+      __syncthreads();
+    }
+  }
+}
+
 }  // namespace
 
 // poly: (0..3 = fp16 phasors, by MUFU or partly by FP32 polynomial: outside the stated tolerance on the
@@ -390,12 +404,14 @@ cudaError_t launch_degridder_tc(const KernelArgs &a, int poly, bool recur, cudaS
                       (D_MAX_TILES * D_STAGES + 2 * D_NG + 1) * 8 + 8 + 48;
   void (*k)(const KernelArgs, int) = nullptr;
   switch (poly) {
-    case 10: k = degridder_tc_kernel<0x00u, true>; break;   // hi + lo phasors
+    case 10:   // hi + lo phasors
+      k = a.list ? degridder_tc_kernel<0x00u, true, true> : degridder_tc_kernel<0x00u, true, false>;
+      break;
     default: return cudaErrorInvalidValue;
   }
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  k<<<dim3((unsigned)a.nr_subgrids), dim3(D_THREADS), smem, stream>>>(a, recur ? 1 : 0);
+  k<<<dim3((unsigned)(a.list && a.nr_subgrids > LIST_MODE_CTAS ? LIST_MODE_CTAS : a.nr_subgrids)), dim3(D_THREADS), smem, stream>>>(a, recur ? 1 : 0);
   return cudaGetLastError();
 }
 

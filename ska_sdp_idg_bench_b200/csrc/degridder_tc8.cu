@@ -133,12 +133,11 @@ __device__ __forceinline__ void etc_produce(unsigned char *A, const float4 *geo,
   }
 }
 
-__global__ void __launch_bounds__(E_THREADS, 3)
-degridder_tc8_kernel(const KernelArgs a, const int recur, const int fold_ok) {
-  if (a.todo && !a.todo[blockIdx.x]) return;   // degridder_sep.cu has degridded this subgrid
+template <bool LIST>
+__device__ __forceinline__ void degridder_tc8_body(const KernelArgs &a, const int recur, const int fold_ok, const int s_local) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const int N = a.subgrid_size, C = a.nr_channels, npix = N * N;
-  const int s = a.subgrid_offset + blockIdx.x;
+  const int s = a.subgrid_offset + s_local;
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);     // warp-uniform for the compiler too
   constexpr int NW = E_PAIRS;                                 // producer warps; warp NW builds B
@@ -175,7 +174,7 @@ degridder_tc8_kernel(const KernelArgs a, const int recur, const int fold_ok) {
   }
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(E_TMEM_COLS));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    if (!LIST) asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);   // a list-mode CTA allocates again
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -423,6 +422,22 @@ degridder_tc8_kernel(const KernelArgs a, const int recur, const int fold_ok) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(E_TMEM_COLS));
 }
 
+// LIST = false: CTA = subgrid blockIdx.x; LIST = true: a fixed number of CTAs loop over the subgrids of a.list
+// (what degridder_sep.cu left: the work is rare, the launch must be cheap when the list is empty)
+template <bool LIST>
+__global__ void __launch_bounds__(E_THREADS, 3)
+degridder_tc8_kernel(const KernelArgs a, const int recur, const int fold_ok) {
+  if (!LIST) {
+    degridder_tc8_body<false>(a, recur, fold_ok, blockIdx.x);
+  } else {
+    const int total = a.list[0];
+    for (int i = blockIdx.x; i < total; i += gridDim.x) {
+      degridder_tc8_body<true>(a, recur, fold_ok, a.list[1 + i]);
+      __syncthreads();
+    }
+  }
+}
+
 }  // namespace
 
 // nr_channels must be a multiple of 8; recur: octs of equally spaced channels get their phasors by recurrence
@@ -432,10 +447,10 @@ cudaError_t launch_degridder_tc8(const KernelArgs &a, bool recur, bool fold, cud
   if (a.nr_channels & 7) return cudaErrorInvalidValue;
   const size_t smem = (size_t)E_PAIRS * E_A_WARP + E_NG * E_GROUP * (E_B_SLOT + E_G_SLOT) + 2 * 32 * 8 * 4 +
                       (E_PAIRS + 2 * E_NG + 1) * 8 + 8 + 48;
-  auto k = degridder_tc8_kernel;
+  auto k = a.list ? degridder_tc8_kernel<true> : degridder_tc8_kernel<false>;
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  k<<<dim3((unsigned)a.nr_subgrids), dim3(E_THREADS), smem, stream>>>(a, recur ? 1 : 0, fold ? 1 : 0);
+  k<<<dim3((unsigned)(a.list && a.nr_subgrids > LIST_MODE_CTAS ? LIST_MODE_CTAS : a.nr_subgrids)), dim3(E_THREADS), smem, stream>>>(a, recur ? 1 : 0, fold ? 1 : 0);
   return cudaGetLastError();
 }
 

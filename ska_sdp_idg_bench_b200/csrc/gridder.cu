@@ -54,9 +54,8 @@ struct Layout<0> { static constexpr int F4_PER_VIS = 4; static constexpr int ACC
 template <>
 struct Layout<1> { static constexpr int F4_PER_VIS = 2; static constexpr int ACC = 4; };
 
-template <int NT, int P, int SCHEME, int MODE, int MINB>
-__global__ void __launch_bounds__(NT, MINB)
-gridder_kernel(const KernelArgs a, const int slabs, const int vis_per_chunk, const int *__restrict__ gate, const int gate_want) {
+template <int NT, int P, int SCHEME, int MODE>
+__device__ __forceinline__ void gridder_body(const KernelArgs &a, const int vis_per_chunk, const int s_local, const int slab) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int F4 = Layout<SCHEME>::F4_PER_VIS;
   constexpr int NACC = Layout<SCHEME>::ACC;
@@ -66,9 +65,6 @@ gridder_kernel(const KernelArgs a, const int slabs, const int vis_per_chunk, con
   const int N = a.subgrid_size;
   const int C = a.nr_channels;
   const int npix = N * N;
-  const int s_local = blockIdx.x / slabs;
-  if (gate && gate[s_local] != gate_want) return;   // gridder_sep.cu has gridded this subgrid
-  const int slab = blockIdx.x - s_local * slabs;
   const int s = a.subgrid_offset + s_local;
   const int tid = threadIdx.x;
 
@@ -324,8 +320,25 @@ gridder_kernel(const KernelArgs a, const int slabs, const int vis_per_chunk, con
   }
 }
 
+// LIST = false: CTA (s, slab) = blockIdx.x; LIST = true: a fixed number of CTAs loop over the subgrids of a.list
+template <int NT, int P, int SCHEME, int MODE, int MINB, bool LIST>
+__global__ void __launch_bounds__(NT, MINB)
+gridder_kernel(const KernelArgs a, const int slabs, const int vis_per_chunk) {
+  if (!LIST) {
+    const int s_local = blockIdx.x / slabs;
+    gridder_body<NT, P, SCHEME, MODE>(a, vis_per_chunk, s_local, blockIdx.x - s_local * slabs);
+  } else {
+    const int total = a.list[0] * slabs;
+    for (int item = blockIdx.x; item < total; item += gridDim.x) {
+      const int i = item / slabs;
+      gridder_body<NT, P, SCHEME, MODE>(a, vis_per_chunk, a.list[1 + i], item - i * slabs);
+      __syncthreads();
+    }
+  }
+}
+
 template <int NT, int P, int SCHEME, int MINB>
-cudaError_t launch_t(const KernelArgs &a, int mode, cudaStream_t stream, const int *gate = nullptr, int gate_want = 1) {
+cudaError_t launch_t(const KernelArgs &a, int mode, cudaStream_t stream) {
   const int npix = a.subgrid_size * a.subgrid_size;
   const int slabs = (npix + NT * P - 1) / (NT * P);
   const int C = a.nr_channels;
@@ -336,16 +349,21 @@ cudaError_t launch_t(const KernelArgs &a, int mode, cudaStream_t stream, const i
                       (P % 4 == 0 ? (size_t)3 * (P / 4) * NT * 16 : 0) + (size_t)2 * TB * 3 * 4 +
                       (size_t)(C + 1) * 4;
   if (smem > 200 * 1024) return cudaErrorInvalidValue;
-  void (*k)(const KernelArgs, int, int, const int *, int) = nullptr;
+  void (*k)(const KernelArgs, int, int) = nullptr;
+  const bool list = a.list != nullptr;
   switch (mode) {
-    case IDGB200_SINCOS_FAST: k = gridder_kernel<NT, P, SCHEME, IDGB200_SINCOS_FAST, MINB>; break;
-    case IDGB200_SINCOS_REDUCED: k = gridder_kernel<NT, P, SCHEME, IDGB200_SINCOS_REDUCED, MINB>; break;
-    case IDGB200_SINCOS_ACCURATE: k = gridder_kernel<NT, P, SCHEME, IDGB200_SINCOS_ACCURATE, MINB>; break;
+    case IDGB200_SINCOS_FAST:
+      k = list ? gridder_kernel<NT, P, SCHEME, IDGB200_SINCOS_FAST, MINB, true> : gridder_kernel<NT, P, SCHEME, IDGB200_SINCOS_FAST, MINB, false>;
+      break;
+    case IDGB200_SINCOS_REDUCED: k = gridder_kernel<NT, P, SCHEME, IDGB200_SINCOS_REDUCED, MINB, false>; break;
+    case IDGB200_SINCOS_ACCURATE: k = gridder_kernel<NT, P, SCHEME, IDGB200_SINCOS_ACCURATE, MINB, false>; break;
     default: return cudaErrorInvalidValue;
   }
+  if (list && mode != IDGB200_SINCOS_FAST) return cudaErrorInvalidValue;   // work lists come from the FAST row-column kernels
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  k<<<dim3((unsigned)a.nr_subgrids * slabs), dim3(NT), smem, stream>>>(a, slabs, vis_per_chunk, gate, gate_want);
+  const long long ctas = (long long)a.nr_subgrids * slabs;
+  k<<<dim3((unsigned)(list && ctas > LIST_MODE_CTAS ? LIST_MODE_CTAS : ctas)), dim3(NT), smem, stream>>>(a, slabs, vis_per_chunk);
   return cudaGetLastError();
 }
 
@@ -378,10 +396,10 @@ int resolve_gridder_variant(int subgrid_size, int nr_channels, int sincos_mode, 
   return fallback_gridder_variant(subgrid_size, nr_channels);
 }
 
-cudaError_t launch_gridder_fp32(const KernelArgs &a, int sincos_mode, cudaStream_t stream, const int *gate, int gate_want) {
+cudaError_t launch_gridder_fp32(const KernelArgs &a, int sincos_mode, cudaStream_t stream) {
   if (a.nr_subgrids == 0) return cudaSuccess;
-  return a.subgrid_size * a.subgrid_size >= 1024 ? launch_t<128, 8, 3, 4>(a, sincos_mode, stream, gate, gate_want)
-                                                 : launch_t<128, 4, 3, 4>(a, sincos_mode, stream, gate, gate_want);
+  return a.subgrid_size * a.subgrid_size >= 1024 ? launch_t<128, 8, 3, 4>(a, sincos_mode, stream)
+                                                 : launch_t<128, 4, 3, 4>(a, sincos_mode, stream);
 }
 
 cudaError_t launch_gridder(const KernelArgs &a, int sincos_mode, int variant, cudaStream_t stream, int *kernels) {
@@ -408,25 +426,29 @@ cudaError_t launch_gridder(const KernelArgs &a, int sincos_mode, int variant, cu
     case 21:   // tensor-core kernel, phasors of equally spaced channel blocks by rotation (else as 12)
       nk = 1;
       return fast ? launch_gridder_tc(a, 3, true, stream) : cudaErrorInvalidValue;
-    case 30: {   // gridder_sep.cu (row-column form) and, gated per subgrid by what it finds, two kernels behind it:
-                 // the per-pixel kernel of the shape for the subgrids that are not separable (todo[s] == 1) and the
-                 // FP32 kernel for those whose sums cancel below the fp16 operand's error model (every tile counted
-                 // in cancel[s]); both arrays are zeroed on the stream first
+    case 30: {   // gridder_sep.cu (row-column form) and, behind it, two list-mode launches over what it finds: the
+                 // per-pixel kernel of the shape for the subgrids that are not separable and the FP32 kernel for those
+                 // whose sums cancel below the fp16 operand's error model.  Scratch (zeroed on the stream first):
+                 // { n_todo, todo[S], n_cancel, cancel[S], cancel tiles per subgrid [S] }
       if (!fast || !gridder_sep_supports(a.subgrid_size, a.nr_channels)) return cudaErrorInvalidValue;
+      const size_t S = (size_t)a.nr_subgrids;
       ScratchLease lease;
-      e = scratch_acquire(2 * (size_t)a.nr_subgrids, stream, &lease);
+      e = scratch_acquire(3 * S + 2, stream, &lease);
       if (e != cudaSuccess) return e;
-      int *todo = lease.ptr, *cancel = lease.ptr + a.nr_subgrids;
+      int *todo = lease.ptr, *cancel = lease.ptr + S + 1, *cancel_tiles = lease.ptr + 2 * S + 2;
       nk = 3;
-      e = cudaMemsetAsync(lease.ptr, 0, 2 * (size_t)a.nr_subgrids * sizeof(int), stream);
-      int tiles = 0;
-      if (e == cudaSuccess) e = launch_gridder_sep(a, todo, cancel, &tiles, stream);
+      e = cudaMemsetAsync(lease.ptr, 0, (3 * S + 2) * sizeof(int), stream);
+      if (e == cudaSuccess) e = launch_gridder_sep(a, todo, cancel, cancel_tiles, stream);
+      KernelArgs b = a;
       if (e == cudaSuccess) {
+        b.list = todo;
         const int fb = fallback_gridder_variant(a.subgrid_size, a.nr_channels);
-        e = fb == 10 ? launch_gridder_fp32(a, sincos_mode, stream, todo, 1)
-                     : launch_gridder_tc(a, fb == 24 ? 11 : 3, true, stream, todo);
+        e = fb == 10 ? launch_gridder_fp32(b, sincos_mode, stream) : launch_gridder_tc(b, fb == 24 ? 11 : 3, true, stream);
       }
-      if (e == cudaSuccess) e = launch_gridder_fp32(a, sincos_mode, stream, cancel, tiles);
+      if (e == cudaSuccess) {
+        b.list = cancel;
+        e = launch_gridder_fp32(b, sincos_mode, stream);
+      }
       const cudaError_t e2 = scratch_release(lease, stream);
       return e != cudaSuccess ? e : e2;
     }

@@ -15,7 +15,7 @@
 //     B = X in fp16 hi + lo: 32 phasors per visibility,                                 N = 4 x 32 columns
 // instead of one phasor per (pixel, visibility) - 1024 of them - in gridder_tc.cu: ~35 instead of ~220 dispatch
 // cycles per visibility and subgrid, and one M=128 N=128 K=16 MMA per 8 visibilities instead of eight N=16 ones.
-// Subgrids that fail the check are left to the per-pixel kernel launched behind this one (todo flags).
+// Subgrids that fail the check are left to the per-pixel kernel launched behind this one (a work list).
 // Error model: one fp16 rounding per term (of Y vis; X keeps ~22 bits), the same class as gridder_tc.cu's fp16
 // phasor; the two half phases are evaluated in fp32 like the reference's single one (tools/sep_prototype.py
 // measures the formulation against the oracle in float64).
@@ -83,7 +83,7 @@ __device__ __forceinline__ void mbar_wait_sleep(const unsigned bar, const unsign
 template <int XPL>
 __global__ void __launch_bounds__(GS_THREADS, XPL == 1 ? 3 : 2)
 gridder_sep_kernel(const KernelArgs a, const int ytiles, const int xtiles, const int tmem_cols, int *__restrict__ todo,
-                   int *__restrict__ cancel) {
+                   int *__restrict__ cancel, int *__restrict__ cancel_tiles) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const int N = a.subgrid_size, C = a.nr_channels;
   const int tiles = ytiles * xtiles;
@@ -167,7 +167,7 @@ gridder_sep_kernel(const KernelArgs a, const int ytiles, const int xtiles, const
       const double gmax = (double)fabsf(ctx.w_offset) + (double)wmax * (double)kmax;
       const bool sep = gmax * r <= (double)SEP_PHASE_TOL && isfinite(gmax);
       s_red[12] = sep ? 1.f : 0.f;
-      if (tile == 0 && !sep) todo[s_local] = 1;
+      if (tile == 0 && !sep) todo[1 + atomicAdd(&todo[0], 1)] = s_local;   // work list of the per-pixel kernel
       for (int p = 0; p < NR_POL; p++) {          // E_p^2 = sum_v |vis_v[p]|^2
         float e2 = 0.f;
         for (int i = 0; i <= GS_W; i++) e2 += s_red[20 + i * 4 + p];
@@ -423,8 +423,9 @@ gridder_sep_kernel(const KernelArgs a, const int ytiles, const int xtiles, const
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (tid == 0 && nstages > 0 && s_red[40] + s_red[41] + s_red[42] + s_red[43] == 4.f &&
-      s_red[16] + s_red[17] + s_red[18] + s_red[19] > 0.f)
-    atomicAdd(&cancel[s_local], 1);
+      s_red[16] + s_red[17] + s_red[18] + s_red[19] > 0.f &&
+      atomicAdd(&cancel_tiles[s_local], 1) == tiles - 1)            // the last of the subgrid's tiles to say so
+    cancel[1 + atomicAdd(&cancel[0], 1)] = s_local;                  // work list of the FP32 kernel
   {
     const size_t plane = (size_t)N * N;
     const size_t at1 = ((size_t)ctx.aterm_index * a.nr_stations + ctx.station1) * plane;
@@ -458,13 +459,12 @@ bool gridder_sep_supports(int subgrid_size, int nr_channels) {
   return subgrid_size >= 4 && subgrid_size % 4 == 0 && subgrid_size <= 2048 && nr_channels >= 1 && nr_channels <= 4096;
 }
 
-// d_todo / d_cancel [nr_subgrids] (device, zeroed by the caller on the same stream): d_todo[s] = 1 where the subgrid's
-// dropped phase term exceeds SEP_PHASE_TOL (left to the per-pixel kernel launched behind this one), d_cancel[s] = the
-// number of the subgrid's tiles whose sums cancel (== *tiles_per_subgrid: redone by the FP32 kernel behind it)
-cudaError_t launch_gridder_sep(const KernelArgs &a, int *d_todo, int *d_cancel, int *tiles_per_subgrid, cudaStream_t stream) {
-  if (tiles_per_subgrid) *tiles_per_subgrid = ((a.subgrid_size + 31) / 32) * ((a.subgrid_size + 63) / 64);
+// Work lists for the kernels launched behind this one (device; counts and tile counters zeroed by the caller on the
+// same stream): d_todo = { n, subgrid[n] } whose dropped phase term exceeds SEP_PHASE_TOL (per-pixel kernel), d_cancel =
+// { n, subgrid[n] } all of whose tiles' sums cancel (FP32 kernel), d_cancel_tiles[nr_subgrids] = tiles counted so far
+cudaError_t launch_gridder_sep(const KernelArgs &a, int *d_todo, int *d_cancel, int *d_cancel_tiles, cudaStream_t stream) {
   if (a.nr_subgrids == 0) return cudaSuccess;
-  if (!gridder_sep_supports(a.subgrid_size, a.nr_channels) || !d_todo || !d_cancel) return cudaErrorInvalidValue;
+  if (!gridder_sep_supports(a.subgrid_size, a.nr_channels) || !d_todo || !d_cancel || !d_cancel_tiles) return cudaErrorInvalidValue;
   const int N = a.subgrid_size;
   const int ytiles = (N + 31) / 32, xtiles = (N + 63) / 64;
   const int xt_max = N < 64 ? N : 64;
@@ -477,7 +477,7 @@ cudaError_t launch_gridder_sep(const KernelArgs &a, int *d_todo, int *d_cancel, 
   auto k = wide ? gridder_sep_kernel<2> : gridder_sep_kernel<1>;
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  k<<<dim3((unsigned)a.nr_subgrids * ytiles * xtiles), dim3(GS_THREADS), smem, stream>>>(a, ytiles, xtiles, tmem_cols, d_todo, d_cancel);
+  k<<<dim3((unsigned)a.nr_subgrids * ytiles * xtiles), dim3(GS_THREADS), smem, stream>>>(a, ytiles, xtiles, tmem_cols, d_todo, d_cancel, d_cancel_tiles);
   return cudaGetLastError();
 }
 

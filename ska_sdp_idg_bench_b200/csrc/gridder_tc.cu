@@ -140,13 +140,9 @@ __device__ __forceinline__ void tc_produce_linear(unsigned char *A, const float 
 //        warps of the sub-partition cover that latency
 // WIDE:  the two A buffers hold the two channel blocks of one K = 32 stage (16 channels): the
 //        per-stage bookkeeping is amortised over 64 items instead of 32, single-buffered like SPLIT
-template <unsigned MASK16, bool SPLIT, bool WIDE = false>
-__global__ void __launch_bounds__(T2_THREADS, 3)
-gridder_tc_kernel(const KernelArgs a, const int slabs, const int tiles_per_cta, const int tmem_cols, const int recur,
-                  const int *__restrict__ todo) {
-  const int s_local = blockIdx.x / slabs;
-  if (todo && !todo[s_local]) return;    // gridder_sep.cu has gridded this subgrid
-  const int slab = blockIdx.x - s_local * slabs;
+template <unsigned MASK16, bool SPLIT, bool WIDE, bool LIST>
+__device__ __forceinline__ void gridder_tc_body(const KernelArgs &a, const int tiles_per_cta, const int tmem_cols, const int recur,
+                                                const int s_local, const int slab) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const int N = a.subgrid_size, C = a.nr_channels, npix = N * N;
   const int s = a.subgrid_offset + s_local;
@@ -185,7 +181,7 @@ gridder_tc_kernel(const KernelArgs a, const int slabs, const int tiles_per_cta, 
   }
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(tmem_cols));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    if (!LIST) asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);   // a list-mode CTA allocates again
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -464,6 +460,24 @@ gridder_tc_kernel(const KernelArgs a, const int slabs, const int tiles_per_cta, 
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols));
 }
 
+// LIST = false: CTA (s, slab) = blockIdx.x; LIST = true: a fixed number of CTAs loop over the subgrids of a.list
+// (what gridder_sep.cu left: the work is rare, the launch must be cheap when the list is empty)
+template <unsigned MASK16, bool SPLIT, bool WIDE, bool LIST>
+__global__ void __launch_bounds__(T2_THREADS, 3)
+gridder_tc_kernel(const KernelArgs a, const int slabs, const int tiles_per_cta, const int tmem_cols, const int recur) {
+  if (!LIST) {
+    const int s_local = blockIdx.x / slabs;
+    gridder_tc_body<MASK16, SPLIT, WIDE, false>(a, tiles_per_cta, tmem_cols, recur, s_local, blockIdx.x - s_local * slabs);
+  } else {
+    const int total = a.list[0] * slabs;
+    for (int item = blockIdx.x; item < total; item += gridDim.x) {
+      const int i = item / slabs;
+      gridder_tc_body<MASK16, SPLIT, WIDE, true>(a, tiles_per_cta, tmem_cols, recur, a.list[1 + i], item - i * slabs);
+      __syncthreads();
+    }
+  }
+}
+
 }  // namespace
 
 // FAST sincos only: the fp16 phasor operand is a FAST-class approximation.
@@ -471,7 +485,7 @@ gridder_tc_kernel(const KernelArgs a, const int slabs, const int tiles_per_cta, 
 //       MUFU (the measured optimum: DESIGN.md 4.5); 10 = fp16 hi + lo phasors (FP32-class accuracy), all by
 //       MUFU / rotation; 11 = as 3 with 16 channels (K = 32) per stage
 // recur: blocks of 8 equally spaced channels get their phasors by rotation from the first one
-cudaError_t launch_gridder_tc(const KernelArgs &a, int poly, bool recur, cudaStream_t stream, const int *todo) {
+cudaError_t launch_gridder_tc(const KernelArgs &a, int poly, bool recur, cudaStream_t stream) {
   if (a.nr_subgrids == 0) return cudaSuccess;
   const int npix = a.subgrid_size * a.subgrid_size;
   const int tiles_total = (npix + 127) / 128;
@@ -485,16 +499,26 @@ cudaError_t launch_gridder_tc(const KernelArgs &a, int poly, bool recur, cudaStr
   const size_t smem = (size_t)tiles_per_cta * T2_STAGES * T2_A_STAGE + T2_NB * T2_B_SLOT +
                       (T2_MAX_TILES * T2_STAGES + T2_NB + 3) * 8 + 8 + 48 + (size_t)ncb * (T2_CB + 2) * 4;
   if (smem > 200 * 1024) return cudaErrorInvalidValue;
-  void (*k)(const KernelArgs, int, int, int, int, const int *) = nullptr;
+  void (*k)(const KernelArgs, int, int, int, int) = nullptr;
+  const bool list = a.list != nullptr;
   switch (poly) {
-    case 3: k = gridder_tc_kernel<0x5252u, false>; break;   // 6 of 16 by polynomial: channels 1,4,6 | 9,12,14
-    case 10: k = gridder_tc_kernel<0x0000u, true>; break;   // fp16 hi + lo phasors
-    case 11: k = gridder_tc_kernel<0x5252u, false, true>; break;   // as 3 with K = 32 stages
+    case 3:    // 6 of 16 by polynomial: channels 1,4,6 | 9,12,14
+      k = list ? gridder_tc_kernel<0x5252u, false, false, true> : gridder_tc_kernel<0x5252u, false, false, false>;
+      break;
+    case 10:   // fp16 hi + lo phasors
+      if (list) return cudaErrorInvalidValue;
+      k = gridder_tc_kernel<0x0000u, true, false, false>;
+      break;
+    case 11:   // as 3 with K = 32 stages
+      k = list ? gridder_tc_kernel<0x5252u, false, true, true> : gridder_tc_kernel<0x5252u, false, true, false>;
+      break;
     default: return cudaErrorInvalidValue;
   }
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  k<<<dim3((unsigned)a.nr_subgrids * nslabs), dim3((producer_warps + 1) * 32), smem, stream>>>(a, nslabs, tiles_per_cta, tmem_cols, recur ? 1 : 0, todo);
+  const long long ctas = (long long)a.nr_subgrids * nslabs;
+  k<<<dim3((unsigned)(list && ctas > LIST_MODE_CTAS ? LIST_MODE_CTAS : ctas)), dim3((producer_warps + 1) * 32), smem, stream>>>(
+      a, nslabs, tiles_per_cta, tmem_cols, recur ? 1 : 0);
   return cudaGetLastError();
 }
 

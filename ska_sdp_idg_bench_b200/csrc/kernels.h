@@ -35,20 +35,19 @@ cudaError_t launch_subgrid_fft(long long nr_planes, int subgrid_size, int direct
 int resolve_gridder_variant(int subgrid_size, int nr_channels, int sincos_mode, int variant);
 int resolve_degridder_variant(int subgrid_size, int nr_channels, int sincos_mode, int variant);
 
+// Every per-pixel kernel below runs in LIST MODE when KernelArgs::list is set: a fixed number of CTAs loop over the
+// listed subgrids (what a row-column kernel left), so that the launch is cheap when the list is empty.
 // per-pixel tcgen05 / TMEM gridder (gridder_tc.cu); FAST sincos only
-// todo (device, may be null): per-subgrid flags of this launch; subgrids whose flag is 0 are skipped
-cudaError_t launch_gridder_tc(const KernelArgs &a, int poly, bool recur, cudaStream_t stream, const int *todo = nullptr);
-// FP32 gridder (gridder.cu) with the same per-subgrid gate
-// gate (device, may be null): the launch serves the subgrids with gate[s] == gate_want only
-cudaError_t launch_gridder_fp32(const KernelArgs &a, int sincos_mode, cudaStream_t stream, const int *gate = nullptr,
-                                int gate_want = 1);
-// row-column gridder (gridder_sep.cu): one GEMM per subgrid with the visibilities as K.  Writes
-// d_todo[nr_subgrids] = 1 where the subgrid is left to the per-pixel kernel launched behind it (its non-separable
-// phase term is too large); d_cancel[nr_subgrids] += 1 per tile whose pixel sums all cancel below the fp16 operand's
-// error model (== *tiles_per_subgrid: the FP32 kernel behind it redoes the subgrid).  Both zeroed by the caller.
+cudaError_t launch_gridder_tc(const KernelArgs &a, int poly, bool recur, cudaStream_t stream);
+// FP32 gridder (gridder.cu)
+cudaError_t launch_gridder_fp32(const KernelArgs &a, int sincos_mode, cudaStream_t stream);
+// row-column gridder (gridder_sep.cu): one GEMM per subgrid with the visibilities as K.  Appends to the work lists
+// d_todo = { n, subgrid[n] } (its non-separable phase term is too large: per-pixel kernel) and d_cancel = { n, subgrid[n] }
+// (every tile's pixel sums cancel below the fp16 operand's error model: FP32 kernel); d_cancel_tiles[nr_subgrids] counts
+// tiles.  Counts and counters zeroed by the caller on the same stream.
 bool gridder_sep_supports(int subgrid_size, int nr_channels);
-cudaError_t launch_gridder_sep(const KernelArgs &a, int *d_todo, int *d_cancel, int *tiles_per_subgrid, cudaStream_t stream);
-// row-column degridder (degridder_sep.cu); d_todo as for launch_gridder_sep (the per-pixel kernels read KernelArgs::todo)
+cudaError_t launch_gridder_sep(const KernelArgs &a, int *d_todo, int *d_cancel, int *d_cancel_tiles, cudaStream_t stream);
+// row-column degridder (degridder_sep.cu); d_todo as for launch_gridder_sep
 bool degridder_sep_supports(int subgrid_size, int nr_channels);
 cudaError_t launch_degridder_sep(const KernelArgs &a, int *d_todo, cudaStream_t stream);
 cudaError_t launch_degridder_tc(const KernelArgs &a, int poly, bool recur, cudaStream_t stream);

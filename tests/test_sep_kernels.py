@@ -25,6 +25,7 @@ SHAPES = [
     dict(subgrid_size=20, nr_channels=300, max_timesteps=2, nr_subgrids=2),
     dict(subgrid_size=32, nr_channels=24, max_timesteps=50, nr_subgrids=2),    # odd number of channel blocks
     dict(subgrid_size=128, nr_channels=8, max_timesteps=6, nr_subgrids=1),     # 4 x 2 tiles
+    dict(subgrid_size=16, nr_channels=3, max_timesteps=500, nr_subgrids=2),    # long subgrids: uvw beyond the staged 384 timesteps
 ]
 
 
@@ -84,6 +85,46 @@ def test_gridder_sep_declines_wide_fields():
     others = np.arange(p.nr_subgrids) != s
     assert np.array_equal(got[others], per_pixel[others])
     assert not np.array_equal(got[s], per_pixel[s])
+
+
+def test_list_mode_loops_over_more_subgrids_than_ctas():
+    """The kernels behind the row-column ones run in list mode: a fixed number of CTAs (592) loop over the subgrids the
+    row-column kernel declined.  declined subgrids make every CTA's loop body run more than once - barriers
+    re-initialised, TMEM re-allocated per subgrid - and the result must still be the per-pixel kernel's, bit for bit."""
+    o = oracle()
+    p = random_problem(205, subgrid_size=32, nr_channels=16, max_timesteps=3, nr_subgrids=1000, image_size=0.2, w_step=0.0)
+    ref_g, ref_d = o.gridder(p), o.degridder(p)
+    rows = covered_rows(p)
+    def declined(q):
+        """subgrids (and their visibility rows) that certainly fail the separability check: some |w| >= 20 m (the
+        few whose w all happen to be small stay with the row-column kernel)"""
+        sub = np.zeros(q.nr_subgrids, bool)
+        vis = np.zeros(q.total_timesteps, bool)
+        for s in range(q.nr_subgrids):
+            t0, nt = int(q.metadata[s]["time_offset"]), int(q.metadata[s]["nr_timesteps"])
+            if nt and np.abs(q.uvw[t0:t0 + nt, 2]).max() >= 20.0:
+                sub[s] = True
+                vis[t0:t0 + nt] = True
+        assert sub.sum() > 592
+        return sub, vis
+
+    sub, vis = declined(p)
+    got = run_gridder(p, FAST, SEP)
+    assert_close(got, ref_g, 1, FAST, "gridder, declined subgrids")
+    assert np.array_equal(got[sub], run_gridder(p, FAST, 24)[sub])
+    got = run_degridder(p, FAST, SEP)
+    assert_close(got[rows], ref_d[rows], 2, FAST, "degridder, declined subgrids")
+    assert np.array_equal(got[vis], run_degridder(p, FAST, 24)[vis])
+    # the FP32 kernels in list mode: a shape whose per-pixel fallback is FP32 (9 of 16 channels)
+    q = random_problem(206, subgrid_size=16, nr_channels=9, max_timesteps=3, nr_subgrids=1000, image_size=0.2, w_step=0.0)
+    sub, vis = declined(q)
+    assert np.array_equal(run_gridder(q, FAST, SEP)[sub], run_gridder(q, FAST, 10)[sub])
+    # 9 channels: the quad kernel (degridder_tc.cu) in list mode
+    assert np.array_equal(run_degridder(q, FAST, SEP)[vis], run_degridder(q, FAST, 22)[vis])
+    r = random_problem(207, subgrid_size=16, nr_channels=1, max_timesteps=3, nr_subgrids=1000, image_size=0.2, w_step=0.0)
+    sub, vis = declined(r)
+    # 1 channel: the FP32 degridder in list mode
+    assert np.array_equal(run_degridder(r, FAST, SEP)[vis], run_degridder(r, FAST, 4)[vis])
 
 
 def test_gridder_sep_fft_shift_and_empty():
