@@ -10,6 +10,9 @@ times of the first repetition, and the SM clock NVML reports before the first la
   v29        ring filled lazily          -> (A) + (B): repetitions 1 and 2 allocate, 3 does not
   v30        the row-column kernel (preallocated, event-guarded scratch)
     python tools/bench_split_probe.py            # driver: runs the cases, prints JSON lines
+
+The recorded run (profiles/r02_bench_split_probe.jsonl) is from commit 3d9a16f, the last one that still built
+variant 29; at HEAD that kernel is gone (superseded by the row-column gridder) and its cases report an error line.
 """
 import json
 import os
@@ -44,6 +47,11 @@ def case(variant: int, idle: float):
         idg.gridder(*scal, p["uvw"], p["wavenumbers"], p["visibilities"], p["spheroidal"], p["aterms"], p["metadata"],
                     p["subgrids"], sincos=idg.SINCOS_FAST, variant=variant)
 
+    try:
+        step()
+    except idg.IdgError as e:
+        print(json.dumps({"variant": variant, "error": str(e)}), flush=True)
+        return
     torch.cuda.synchronize()
     time.sleep(idle)
     out = {"variant": variant, "idle_s": idle, "sm_mhz_before": sm_clock(), "repetitions": []}
