@@ -25,7 +25,7 @@
 //     makes the A rows of its 4 polarisations (phasor by the three-term recurrence over equally spaced
 //     channels, else one sincos per channel; visibilities broadcast from a cp.async ring), lane = column x the
 //     B rows; fence.proxy.async, arrive on the stage's full barrier.  Stages go round-robin over the warps,
-//     two buffers per warp, so a warp waits only for its own stage of two rounds ago.
+//     two A buffers and one B buffer per warp, so a warp waits only for its own MMAs of one / two rounds ago.
 //   1 issuer warp: waits for the stages in order and issues their tcgen05.mma (one thread, so the MMAs
 //     that share the accumulator are ordered), committing each to the producer's empty barrier.
 //   epilogue: TMEM -> shared memory (a warp reads its lane quadrant = one polarisation), then per pixel
@@ -81,7 +81,7 @@ __device__ __forceinline__ void mbar_wait_sleep(const unsigned bar, const unsign
 
 // XPL: columns per lane (1: tiles of <= 32 columns, 2: of 33..64)
 template <int XPL>
-__global__ void __launch_bounds__(GS_THREADS, XPL == 1 ? 3 : 2)
+__global__ void __launch_bounds__(GS_THREADS, XPL == 1 ? 4 : 2)
 gridder_sep_kernel(const KernelArgs a, const int ytiles, const int xtiles, const int tmem_cols, int *__restrict__ todo,
                    int *__restrict__ cancel, int *__restrict__ cancel_tiles) {
   extern __shared__ __align__(1024) unsigned char smem[];
@@ -96,10 +96,13 @@ gridder_sep_kernel(const KernelArgs a, const int ytiles, const int xtiles, const
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
   const int ncb = (C + GS_CB - 1) / GS_CB;
   const int b_bytes = 4 * XT * 32;                        // B: 4 XT rows x 16 fp16
-  const int stage_bytes = GS_A_BYTES + 4 * 64 * 32 / (XPL == 1 ? 2 : 1);   // the kernel's largest tile
+  // per producer warp: two A buffers and ONE B buffer (of the kernel's largest tile).  A stage's A rows are most of its
+  // work, so by the time a warp turns to the B rows the MMA of its previous stage - the last reader of B - has long
+  // completed: B needs no second buffer, and 12 KB per producer let four CTAs share an SM
+  const int warp_bytes = 2 * GS_A_BYTES + 4 * 64 * 32 / (XPL == 1 ? 2 : 1);
 
-  unsigned char *sStage = smem;                                                        // [GS_W][2][stage_bytes]
-  unsigned char *sVis = sStage + GS_W * 2 * stage_bytes;                               // [GS_W][GS_VSLOTS][256]
+  unsigned char *sStage = smem;                                                        // [GS_W][A0 | A1 | B]
+  unsigned char *sVis = sStage + GS_W * warp_bytes;                                    // [GS_W][GS_VSLOTS][256]
   unsigned long long *full = reinterpret_cast<unsigned long long *>(sVis + GS_W * GS_VSLOTS * 256);   // [GS_W][2]
   unsigned long long *empty = full + GS_W * 2;                                         // [GS_W][2]
   unsigned long long *done = empty + GS_W * 2;
@@ -202,7 +205,7 @@ gridder_sep_kernel(const KernelArgs a, const int ytiles, const int xtiles, const
       n_x[i] = compute_n(l[i], 0.f);
       off_x[i] = __fmaf_rn(ctx.w_offset, n_x[i], __fmul_rn(ctx.u_offset, l[i]));
     }
-    unsigned char *my_stage = sStage + warp * 2 * stage_bytes;
+    unsigned char *my_stage = sStage + warp * warp_bytes;
     unsigned char *my_vis = sVis + warp * GS_VSLOTS * 256;
     const unsigned full_u = smem_u32(full + warp * 2), empty_u = smem_u32(empty + warp * 2);
 
@@ -291,7 +294,7 @@ gridder_sep_kernel(const KernelArgs a, const int ytiles, const int xtiles, const
       __syncwarp();
       if (j >= 2) mbar_wait_u(empty_u + buf * 8, ((j >> 1) - 1) & 1);
 
-      unsigned char *A = my_stage + buf * stage_bytes, *B = A + GS_A_BYTES;
+      unsigned char *A = my_stage + buf * GS_A_BYTES, *B = my_stage + 2 * GS_A_BYTES;
       {
         // ---- A rows (p, y): fp16 of scale * Y_c(y) * vis[c][p]
         const float4 *vs = reinterpret_cast<const float4 *>(my_vis + (j & (GS_VSLOTS - 1)) * 256);
@@ -316,6 +319,7 @@ gridder_sep_kernel(const KernelArgs a, const int ytiles, const int xtiles, const
             *reinterpret_cast<uint4 *>(A + kc * (128 * 16) + (p * 32 + lane) * 16) = make_uint4(pk[p][0], pk[p][1], pk[p][2], pk[p][3]);
         }
       }
+      if (j >= 1) mbar_wait_u(empty_u + (buf ^ 1) * 8, ((j - 1) >> 1) & 1);   // the previous stage's MMA has read B
 #pragma unroll
       for (int xi = 0; xi < XPL; xi++) {
         // ---- B rows of column x: (hi|lo, re|im) x XT; re row = (cos, -sin), im row = (sin, cos) per visibility
@@ -369,8 +373,8 @@ gridder_sep_kernel(const KernelArgs a, const int ytiles, const int xtiles, const
       mbar_wait_sleep(full_u + (pw * 2 + buf) * 8, (j >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       if (elect_one()) {
-        const unsigned a_addr = stage_u + (pw * 2 + buf) * stage_bytes;
-        umma_f16(tmem_base, smem_desc(a_addr, 128 * 16, 128), smem_desc(a_addr + GS_A_BYTES, 4 * XT * 16, 128), idesc,
+        const unsigned w_addr = stage_u + pw * warp_bytes;
+        umma_f16(tmem_base, smem_desc(w_addr + buf * GS_A_BYTES, 128 * 16, 128), smem_desc(w_addr + 2 * GS_A_BYTES, 4 * XT * 16, 128), idesc,
                  sidx > 0 ? 1u : 0u);
         umma_commit_u(empty_u + (pw * 2 + buf) * 8);
         if (sidx == nstages - 1) umma_commit_u(done_u);
@@ -472,8 +476,8 @@ cudaError_t launch_gridder_sep(const KernelArgs &a, int *d_todo, int *d_cancel, 
   int tmem_cols = 32;
   while (tmem_cols < 4 * xt_max) tmem_cols *= 2;
   const int ncb = (a.nr_channels + GS_CB - 1) / GS_CB;
-  const size_t stage_bytes = GS_A_BYTES + (wide ? 4 * 64 * 32 : 4 * 32 * 32);
-  const size_t smem = GS_W * 2 * stage_bytes + GS_W * GS_VSLOTS * 256 + (4 * GS_W + 1) * 8 + 8 + 192 + (size_t)ncb * (GS_CB + 2) * 4;
+  const size_t warp_bytes = 2 * GS_A_BYTES + (wide ? 4 * 64 * 32 : 4 * 32 * 32);
+  const size_t smem = GS_W * warp_bytes + GS_W * GS_VSLOTS * 256 + (4 * GS_W + 1) * 8 + 8 + 192 + (size_t)ncb * (GS_CB + 2) * 4;
   auto k = wide ? gridder_sep_kernel<2> : gridder_sep_kernel<1>;
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
