@@ -275,14 +275,16 @@ cudaError_t launch_degridder(const KernelArgs &a, int sincos_mode, int variant, 
     case 28:
       return fast && !(a.nr_channels & 7) ? launch_degridder_tc8(a, variant != 25, variant == 24, stream)
                                           : cudaErrorInvalidValue;
-    case 30: {   // degridder_sep.cu (row-column form); subgrids it declines go to the per-pixel kernel behind it
+    case 30:     // degridder_sep.cu (row-column form); subgrids it declines go to the per-pixel kernel behind it
+    case 31:     // 31: its one-subgrid-per-CTA kernel, 32: its pipelined persistent kernel (30 = 32 where the buffers fit)
+    case 32: {
       if (!fast || !degridder_sep_supports(a.subgrid_size, a.nr_channels)) return cudaErrorInvalidValue;
       ScratchLease lease;   // { n_todo, todo[S] }: the subgrids the row-column kernel leaves to the per-pixel kernel
       cudaError_t e = scratch_acquire((size_t)a.nr_subgrids + 1, stream, &lease);
       if (e != cudaSuccess) return e;
       nk = 2;
       e = cudaMemsetAsync(lease.ptr, 0, sizeof(int), stream);
-      if (e == cudaSuccess) e = launch_degridder_sep(a, lease.ptr, stream);
+      if (e == cudaSuccess) e = launch_degridder_sep(a, lease.ptr, stream, variant - 30);
       if (e == cudaSuccess) {
         KernelArgs b = a;
         b.list = lease.ptr;

@@ -363,18 +363,486 @@ degridder_sep_kernel(const KernelArgs a, const int tmem_cols, int *__restrict__ 
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols));
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// The same arithmetic as a warp-specialised, persistent pipeline: ONE CTA per SM that loops over subgrids, 21 warps.
+//   warps  0- 7  producers: the A rows (column phasors X, fp16 hi + lo) of tile i + 1 / i + 2 into one of two A buffers
+//   warps  8-15  consumers: the sum over the rows y of tile i out of one of two accumulators (all 512 TMEM columns)
+//   warp   16    issuer: the tile's 12 MMAs as soon as its A buffer is full and its accumulator has been drained
+//   warps 17-20  setup: the NEXT subgrid's separability check, B operand (P' in fp16 hi + lo, one of two B buffers),
+//                staged uvw and row geometry, while the others are in the tile loop of the current subgrid
+// so that the tensor pipe, the producers' dependency chains and the consumers' TMEM reads overlap inside one CTA
+// instead of across two (the kernel above: a tile's phases one after the other, 2 CTAs per SM), and the per-subgrid
+// prologue (32 KB of pixels + A-terms) is hidden behind the previous subgrid.  Hand-offs are mbarriers only:
+//   b_full[2]  (4 setup warps)   -> everyone     B buffer, meta, geometry, uvw of subgrid j are ready
+//   b_empty[2] (17 warps)        -> setup        producers, consumers and the issuer are done with subgrid j's buffers
+//   a_full[2]  (8 producers)     -> issuer
+//   mma_done[2] (tcgen05.commit) -> consumers (accumulator full) and producers (A buffer free)
+//   d_empty[2] (8 consumers)     -> issuer       accumulator drained
+//   part_full[2] (4 upper consumer warps) -> lower consumer warps (the two halves of the sum over the rows meet)
+// Tiles are counted over the whole run of a CTA (`it`), buffer = it & 1, phase = (it >> 1) & 1.  Results are bit-identical
+// to the kernel above (same MMAs in the same order, same split of the sum over the rows).
+constexpr int DP_WARPS = 21, DP_THREADS = DP_WARPS * 32;
+constexpr int DP_ISSUER = 16, DP_SETUP0 = 17, DP_SETUP_THREADS = 128;
+constexpr int DP_UVW_STAGED = 256;
+
+struct PipeMeta {        // per-subgrid scalars, written by the setup warps
+  int run;               // 1: the row-column tiles of this subgrid run here; 0: nothing to do (declined or no timesteps)
+  int nt;
+  long long time_offset;
+  float u_offset, w_offset, unscale;
+  int pad;
+};
+
+__device__ __forceinline__ void setup_bar() { asm volatile("bar.sync 1, %0;" ::"n"(DP_SETUP_THREADS) : "memory"); }
+
+// P' of pixel q (degridder_reference.cpp:38-74): sph . subgrid, A1 . A2^H
+__device__ __forceinline__ void pprime(const KernelArgs &a, const float2 *sub, const size_t at1, const size_t at2,
+                                       const int q, const int N, const size_t plane, float2 *px) {
+  const float sph = __ldg(&a.spheroidal[q]);
+  const int src = subgrid_slot(q, N, a.flags);
+#pragma unroll
+  for (int p = 0; p < NR_POL; p++) {
+    const float2 v = __ldg(&sub[p * plane + src]);
+    px[p] = make_float2(__fmul_rn(sph, v.x), __fmul_rn(sph, v.y));
+  }
+  float2 a1[4], a2[4];
+  load_jones(a.aterms, (at1 + q) * NR_POL, a1);
+  load_jones(a.aterms, (at2 + q) * NR_POL, a2);
+  apply_aterm_degridder(px, a1, a2);
+}
+
+__global__ void __launch_bounds__(DP_THREADS, 1)
+degridder_sep_pipe_kernel(const KernelArgs a, int *__restrict__ todo) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const int N = a.subgrid_size, C = a.nr_channels, npix = N * N;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  const int KC = N >> 2, KCp = (KC + 1) & ~1;
+  const int ncols = 8 * N;
+  const int b_ch = ncols * 16 + 16;
+  const int ncb = (C + 7) >> 3;
+  const int b_buf = 2 * KCp * b_ch, a_buf = 2 * KCp * DS_A_CH;
+
+  unsigned char *sB = smem;                                             // [2][hi|lo][KCp][b_ch]
+  unsigned char *sA = sB + 2 * b_buf;                                   // [2][hi|lo][KCp][DS_A_CH]
+  float4 *sGeo = reinterpret_cast<float4 *>(sA + 2 * a_buf);            // [2][N] (m_y, f(m_y^2), offset_y, 0)
+  float4 *sPart = sGeo + 2 * N;                                         // [2][128][2] partial sums of the upper warps
+  float *s_uvw = reinterpret_cast<float *>(sPart + 512);                // [2][DP_UVW_STAGED][3]
+  unsigned long long *bars = reinterpret_cast<unsigned long long *>(s_uvw + 2 * DP_UVW_STAGED * 3);   // [12]
+  PipeMeta *meta = reinterpret_cast<PipeMeta *>(bars + 12);             // [2]
+  unsigned *s_tmem = reinterpret_cast<unsigned *>(meta + 2);            // [2]
+  float *s_red = reinterpret_cast<float *>(s_tmem + 2);                 // [48]: [0, 21) kmax partials, [32, 48) setup partials
+  float *s_wn = s_red + 48;                                             // [ncb * 8]
+  float *s_dw = s_wn + ncb * 8;                                         // [ncb]
+  int *s_lin = reinterpret_cast<int *>(s_dw + ncb);                     // [ncb]
+  const unsigned bar_u = smem_u32(bars);
+  // barrier b of buffer i: bar_u + (2 * b + i) * 8
+  enum { A_FULL = 0, MMA_DONE = 1, D_EMPTY = 2, PART_FULL = 3, B_FULL = 4, B_EMPTY = 5 };
+  auto bar_at = [&](int b, int i) { return bar_u + (unsigned)(2 * b + i) * 8u; };
+  auto arrive_u = [](unsigned bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); };
+
+  // ---- once per CTA: channel layout, barriers, K padding, TMEM
+  {
+    float kmax = 0.f;
+    for (int c = tid; c < ncb * 8; c += DP_THREADS) {
+      const float k = c < C ? a.wavenumbers[c] : 0.f;
+      s_wn[c] = k;
+      kmax = fmaxf(kmax, fabsf(k));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) kmax = fmaxf(kmax, __shfl_xor_sync(0xffffffffu, kmax, o));
+    if (lane == 0) s_red[warp] = kmax;
+  }
+  if (tid == 0) {
+    for (int i = 0; i < 2; i++) {
+      mbar_init(&bars[2 * A_FULL + i], 8);
+      mbar_init(&bars[2 * MMA_DONE + i], 1);
+      mbar_init(&bars[2 * D_EMPTY + i], 8);
+      mbar_init(&bars[2 * PART_FULL + i], 4);
+      mbar_init(&bars[2 * B_FULL + i], 4);
+      mbar_init(&bars[2 * B_EMPTY + i], 17);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (KCp != KC) {                      // the K padding: zero in A and B (never written again)
+    for (int i = tid; i < 128 * 4; i += DP_THREADS)
+      for (int b = 0; b < 2; b++) {
+        *reinterpret_cast<unsigned *>(sA + b * a_buf + KC * DS_A_CH + i * 4) = 0u;
+        *reinterpret_cast<unsigned *>(sA + b * a_buf + (KCp + KC) * DS_A_CH + i * 4) = 0u;
+      }
+    for (int i = tid; i < ncols * 4; i += DP_THREADS)
+      for (int b = 0; b < 2; b++) {
+        *reinterpret_cast<unsigned *>(sB + b * b_buf + KC * b_ch + i * 4) = 0u;
+        *reinterpret_cast<unsigned *>(sB + b * b_buf + (KCp + KC) * b_ch + i * 4) = 0u;
+      }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == DP_ISSUER) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "n"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  for (int cb = tid; cb < ncb; cb += DP_THREADS) {     // s_wn is complete
+    float dw;
+    s_lin[cb] = linear_channels(s_wn, cb * 8, min(8, C - cb * 8), &dw) ? 1 : 0;
+    s_dw[cb] = dw;
+  }
+  __syncthreads();
+  const unsigned tmem_base = *s_tmem;
+  const int S = a.nr_subgrids;
+
+  if (warp < 8) {
+    // ================================================================================= producers: lane = column x
+    const float l = compute_l(min(lane, N - 1), N, a.image_size);
+    const float n_x = compute_n(l, 0.f);
+    const int a_off = (lane >> 2) * DS_A_CH + (lane & 3) * 4;
+    const int step_t = 16 / ncb, step_cb = 16 - step_t * ncb;
+    int it = 0;
+    for (int s_local = blockIdx.x, j = 0; s_local < S; s_local += gridDim.x, j++) {
+      const int bb = j & 1;
+      mbar_wait_t(bar_at(B_FULL, bb), (j >> 1) & 1);
+      const PipeMeta m = meta[bb];
+      if (m.run) {
+        const int nt = m.nt, nblk = nt * ncb, ntiles = (nblk + 15) >> 4;
+        const float off_x = __fmaf_rn(m.w_offset, n_x, __fmul_rn(m.u_offset, l));
+        const bool staged = nt <= DP_UVW_STAGED;
+        const float *uvw = staged ? s_uvw + bb * DP_UVW_STAGED * 3 : reinterpret_cast<const float *>(a.uvw) + (size_t)m.time_offset * 3;
+        auto uvw_at = [&](int i) { return staged ? uvw[i] : __ldg(&uvw[i]); };
+        int pt = (warp * 2) / ncb, pcb = warp * 2 - pt * ncb;
+        for (int tile = 0; tile < ntiles; tile++, it++) {
+          const int buf = it & 1;
+          if (it >= 2) mbar_wait_t(bar_at(MMA_DONE, buf), ((it >> 1) - 1) & 1);    // the MMAs of tile it - 2 have read the buffer
+          unsigned char *a_col = sA + buf * a_buf + a_off;
+#pragma unroll
+          for (int bi = 0; bi < 2; bi++) {
+            const int blk = tile * 16 + warp * 2 + bi;
+            unsigned hi[8], lo[8];
+            if (blk < nblk) {
+              int t = pt, cb = pcb + bi;
+              if (cb >= ncb) { cb -= ncb; t++; }
+              const float idx = __fmaf_rn(uvw_at(3 * t + 2), n_x, __fmul_rn(uvw_at(3 * t), l));
+              const float *wn8 = s_wn + cb * 8;
+              float2 ph[8];
+              if (s_lin[cb]) {
+                ph[0] = phasor<IDGB200_SINCOS_FAST>(__fmaf_rn(idx, wn8[0], -off_x));
+                const float2 d = phasor<IDGB200_SINCOS_FAST>(__fmul_rn(idx, s_dw[cb]));
+                ph[1] = ffma2(make_float2(ph[0].y, ph[0].x), make_float2(-d.y, d.y), __fmul2_rn(ph[0], make_float2(d.x, d.x)));
+                const float c2 = __fadd_rn(d.x, d.x);
+#pragma unroll
+                for (int i = 2; i < 8; i++) ph[i] = ffma2(ph[i - 1], make_float2(c2, c2), make_float2(-ph[i - 2].x, -ph[i - 2].y));
+              } else {
+#pragma unroll
+                for (int i = 0; i < 8; i++) ph[i] = phasor<IDGB200_SINCOS_FAST>(__fmaf_rn(idx, wn8[i], -off_x));
+              }
+#pragma unroll
+              for (int i = 0; i < 8; i++) {
+                hi[i] = pack_h2(ph[i].x, ph[i].y);
+                lo[i] = pack_h2(residual_h(ph[i].x, (unsigned short)(hi[i] & 0xffffu)), residual_h(ph[i].y, (unsigned short)(hi[i] >> 16)));
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 8; i++) hi[i] = lo[i] = 0u;
+            }
+            if (lane < N) {
+              unsigned char *row = a_col + ((warp * 2 + bi) * 8) * 16;
+#pragma unroll
+              for (int i = 0; i < 8; i++) {
+                *reinterpret_cast<unsigned *>(row + i * 16) = hi[i];
+                *reinterpret_cast<unsigned *>(row + i * 16 + KCp * DS_A_CH) = lo[i];
+              }
+            }
+          }
+          pt += step_t; pcb += step_cb;
+          if (pcb >= ncb) { pcb -= ncb; pt++; }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) arrive_u(bar_at(A_FULL, buf));
+        }
+      }
+      __syncwarp();
+      if (lane == 0) arrive_u(bar_at(B_EMPTY, bb));
+    }
+  } else if (warp < 16) {
+    // ========================================================= consumers: thread = visibility (TMEM lane = row of the tile)
+    const int q4 = warp & 3, upper = (warp >> 2) & 1;
+    const int ng = N >> 2, g_lo = upper ? (ng + 1) >> 1 : 0, g_hi = upper ? ng : (ng + 1) >> 1;
+    const int r_tile = q4 * 32 + lane;
+    int it = 0;
+    for (int s_local = blockIdx.x, j = 0; s_local < S; s_local += gridDim.x, j++) {
+      const int bb = j & 1;
+      mbar_wait_t(bar_at(B_FULL, bb), (j >> 1) & 1);
+      const PipeMeta m = meta[bb];
+      if (m.run) {
+        const int nt = m.nt, nblk = nt * ncb, ntiles = (nblk + 15) >> 4;
+        const float unscale = m.unscale;
+        const bool staged = nt <= DP_UVW_STAGED;
+        const float *uvw = staged ? s_uvw + bb * DP_UVW_STAGED * 3 : reinterpret_cast<const float *>(a.uvw) + (size_t)m.time_offset * 3;
+        auto uvw_at = [&](int i) { return staged ? uvw[i] : __ldg(&uvw[i]); };
+        const float4 *geo_b = sGeo + bb * N;
+        float2 *g_out = const_cast<float2 *>(a.visibilities) + (size_t)m.time_offset * C * NR_POL;
+        for (int tile = 0; tile < ntiles; tile++, it++) {
+          const int buf = it & 1;
+          const int blk = tile * 16 + (r_tile >> 3);
+          const bool in_range = blk < nblk;
+          const int t = in_range ? blk / ncb : 0, cb = in_range ? blk - t * ncb : 0;
+          const int c = cb * 8 + (r_tile & 7);
+          const bool valid = in_range && c < C;
+          const float k = s_wn[c];
+          const float vt = uvw_at(3 * t + 1), wt = uvw_at(3 * t + 2);
+          float2 acc[NR_POL];
+#pragma unroll
+          for (int p = 0; p < NR_POL; p++) acc[p] = make_float2(0.f, 0.f);
+          mbar_wait_t(bar_at(MMA_DONE, buf), (it >> 1) & 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          for (int g = g_lo; g < g_hi; g++) {
+            unsigned r[32];
+            const unsigned taddr = tmem_base + (unsigned)(buf * 256) + ((unsigned)(q4 * 32) << 16) + g * 32;
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+                "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                  "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                  "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                  "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                : "r"(taddr));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int yy = 0; yy < 4; yy++) {
+              const float4 geo = geo_b[g * 4 + yy];        // broadcast
+              const float idx = __fmaf_rn(wt, geo.y, __fmul_rn(vt, geo.x));
+              const float2 ph = phasor<IDGB200_SINCOS_FAST>(__fmaf_rn(idx, k, -geo.z));
+              const float2 phs = make_float2(-ph.y, ph.x);
+#pragma unroll
+              for (int p = 0; p < NR_POL; p++) {
+                const float qr = __uint_as_float(r[yy * 8 + 2 * p]), qi = __uint_as_float(r[yy * 8 + 2 * p + 1]);
+                acc[p] = ffma2(make_float2(qr, qr), ph, acc[p]);
+                acc[p] = ffma2(make_float2(qi, qi), phs, acc[p]);
+              }
+            }
+          }
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          float4 *part = sPart + buf * 256 + 2 * r_tile;
+          if (upper) {
+            part[0] = make_float4(acc[0].x, acc[0].y, acc[1].x, acc[1].y);
+            part[1] = make_float4(acc[2].x, acc[2].y, acc[3].x, acc[3].y);
+            __syncwarp();
+            if (lane == 0) {
+              arrive_u(bar_at(PART_FULL, buf));
+              arrive_u(bar_at(D_EMPTY, buf));
+            }
+          } else {
+            mbar_wait_t(bar_at(PART_FULL, buf), (it >> 1) & 1);
+            const float4 p0 = part[0], p1 = part[1];
+            __syncwarp();
+            if (lane == 0) arrive_u(bar_at(D_EMPTY, buf));     // accumulator drained AND the partial sums read
+            if (valid) {
+              float4 *o = reinterpret_cast<float4 *>(g_out + ((size_t)t * C + c) * NR_POL);
+              o[0] = make_float4((acc[0].x + p0.x) * unscale, (acc[0].y + p0.y) * unscale, (acc[1].x + p0.z) * unscale,
+                                 (acc[1].y + p0.w) * unscale);
+              o[1] = make_float4((acc[2].x + p1.x) * unscale, (acc[2].y + p1.y) * unscale, (acc[3].x + p1.z) * unscale,
+                                 (acc[3].y + p1.w) * unscale);
+            }
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) arrive_u(bar_at(B_EMPTY, bb));
+    }
+  } else if (warp == DP_ISSUER) {
+    // ================================================================================================== issuer
+    const unsigned idesc = (1u << 4) | (((unsigned)ncols >> 3) << 17) | ((128u >> 4) << 24);
+    const unsigned a_u = smem_u32(sA), b_u = smem_u32(sB);
+    int it = 0;
+    for (int s_local = blockIdx.x, j = 0; s_local < S; s_local += gridDim.x, j++) {
+      const int bb = j & 1;
+      mbar_wait_t(bar_at(B_FULL, bb), (j >> 1) & 1);
+      const PipeMeta m = meta[bb];
+      if (m.run) {
+        const int ntiles = (m.nt * ncb + 15) >> 4;
+        for (int tile = 0; tile < ntiles; tile++, it++) {
+          const int buf = it & 1;
+          mbar_wait_t(bar_at(A_FULL, buf), (it >> 1) & 1);
+          if (it >= 2) mbar_wait_t(bar_at(D_EMPTY, buf), ((it >> 1) - 1) & 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          if (elect_one()) {
+            const unsigned d_t = tmem_base + (unsigned)(buf * 256);
+            const unsigned a_b = a_u + buf * a_buf, b_b = b_u + bb * b_buf;
+            for (int ks = 0; ks < KCp / 2; ks++) {
+              const unsigned long long a_hi = smem_desc(a_b + 2 * ks * DS_A_CH, DS_A_CH, 128);
+              const unsigned long long a_lo = smem_desc(a_b + (KCp + 2 * ks) * DS_A_CH, DS_A_CH, 128);
+              const unsigned long long b_hi = smem_desc(b_b + 2 * ks * b_ch, b_ch, 128);
+              const unsigned long long b_lo = smem_desc(b_b + (KCp + 2 * ks) * b_ch, b_ch, 128);
+              umma_f16(d_t, a_hi, b_hi, idesc, ks > 0 ? 1u : 0u);
+              umma_f16(d_t, a_lo, b_hi, idesc, 1u);
+              umma_f16(d_t, a_hi, b_lo, idesc, 1u);
+            }
+            umma_commit_u(bar_at(MMA_DONE, buf));
+          }
+          __syncwarp();
+        }
+      }
+      __syncwarp();
+      if (lane == 0) arrive_u(bar_at(B_EMPTY, bb));
+    }
+  } else {
+    // =================================================================== setup: the next subgrid's check and B operand
+    const int ts = tid - DP_SETUP0 * 32, sw = warp - DP_SETUP0;
+    float kmax = 0.f;
+    for (int i = 0; i < DP_WARPS; i++) kmax = fmaxf(kmax, s_red[i]);
+    // the dropped phase term r at the corner pixel (gridder_sep.cu)
+    const double l0 = (0.5 - (N / 2)) * (double)a.image_size / (double)N;
+    const double s1 = l0 * l0;
+    const double fn = s1 / (1.0 + sqrt(1.0 - s1)), s2 = 2.0 * s1;
+    const double r_corner = s2 > 1.0 ? 1.0 : fabs(s2 / (1.0 + sqrt(1.0 - s2)) - 2.0 * fn);
+    const size_t plane = (size_t)npix;
+    for (int s_local = blockIdx.x, j = 0; s_local < S; s_local += gridDim.x, j++) {
+      const int bb = j & 1;
+      if (j >= 2) mbar_wait_t(bar_at(B_EMPTY, bb), ((j >> 1) - 1) & 1);
+      const int s = a.subgrid_offset + s_local;
+      const SubgridCtx ctx = load_ctx(a, s);
+      const int nt = ctx.nr_timesteps;
+      const float *g_uvw = reinterpret_cast<const float *>(a.uvw) + (size_t)ctx.time_offset * 3;
+      float wmax = 0.f;
+      if (nt <= DP_UVW_STAGED) {
+        float *dst = s_uvw + bb * DP_UVW_STAGED * 3;
+        for (int i = ts; i < nt * 3; i += DP_SETUP_THREADS) {
+          const float x = __ldg(&g_uvw[i]);
+          dst[i] = x;
+          if (i % 3 == 2) wmax = fmaxf(wmax, fabsf(x));
+        }
+      } else {
+        for (int t = ts; t < nt; t += DP_SETUP_THREADS) wmax = fmaxf(wmax, fabsf(__ldg(&g_uvw[3 * t + 2])));
+      }
+      const size_t at1 = ((size_t)ctx.aterm_index * a.nr_stations + ctx.station1) * plane;
+      const size_t at2 = ((size_t)ctx.aterm_index * a.nr_stations + ctx.station2) * plane;
+      const float2 *sub = a.subgrids + (size_t)s * NR_POL * plane;
+      float amax = 0.f;
+      if (nt > 0) {
+#pragma unroll 2
+        for (int q = ts; q < npix; q += DP_SETUP_THREADS) {
+          float2 px[NR_POL];
+          pprime(a, sub, at1, at2, q, N, plane, px);
+#pragma unroll
+          for (int p = 0; p < NR_POL; p++) amax = fmaxf(amax, fmaxf(fabsf(px[p].x), fabsf(px[p].y)));
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        wmax = fmaxf(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
+        amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+      }
+      float *red = s_red + 32 + bb * 8;          // [wmax of the 4 warps | amax of the 4 warps], one set per buffer
+      if (lane == 0) {
+        red[sw] = wmax;
+        red[4 + sw] = amax;
+      }
+      setup_bar();
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        wmax = fmaxf(wmax, red[i]);
+        amax = fmaxf(amax, red[4 + i]);
+      }
+      const double gmax = (double)fabsf(ctx.w_offset) + (double)wmax * (double)kmax;
+      const bool sep = gmax * r_corner <= (double)SEP_PHASE_TOL && isfinite(gmax);
+      if (!sep && ts == 0) todo[1 + atomicAdd(&todo[0], 1)] = s_local;   // work list of the per-pixel kernel
+      const bool run = sep && nt > 0;
+      const unsigned eb = (__float_as_uint(amax) >> 23) & 0xffu;
+      const bool ok = eb >= 14u && eb <= 253u;
+      const float scale = ok ? __uint_as_float((267u - eb) << 23) : 1.f;           // 2^(13 - E)
+      if (run) {
+        unsigned char *sBb = sB + bb * b_buf;
+#pragma unroll 2
+        for (int q = ts; q < npix; q += DP_SETUP_THREADS) {
+          float2 px[NR_POL];
+          pprime(a, sub, at1, at2, q, N, plane, px);
+          const int y = q / N, x = q - y * N;
+          unsigned char *col = sBb + (x >> 2) * b_ch + (x & 3) * 4 + (y * 8) * 16;
+#pragma unroll
+          for (int p = 0; p < NR_POL; p++) {
+            const float re = px[p].x * scale, im = px[p].y * scale;
+            const unsigned h_im = pack_h2(im, re);
+            const unsigned h_re = pack_h2(re, -im);
+            const float r_im = residual_h(im, (unsigned short)(h_im & 0xffffu));
+            const float r_re = residual_h(re, (unsigned short)(h_im >> 16));
+            unsigned char *row = col + (2 * p) * 16;
+            *reinterpret_cast<unsigned *>(row) = h_re;
+            *reinterpret_cast<unsigned *>(row + 16) = h_im;
+            *reinterpret_cast<unsigned *>(row + KCp * b_ch) = pack_h2(r_re, -r_im);
+            *reinterpret_cast<unsigned *>(row + KCp * b_ch + 16) = pack_h2(r_im, r_re);
+          }
+        }
+        if (ts < N) {
+          const float mm = compute_l(ts, N, a.image_size);
+          const float n_y = compute_n(mm, 0.f);
+          sGeo[bb * N + ts] = make_float4(mm, n_y, __fmaf_rn(ctx.w_offset, n_y, __fmul_rn(ctx.v_offset, mm)), 0.f);
+        }
+      }
+      if (ts == 0) {
+        PipeMeta m;
+        m.run = run ? 1 : 0;
+        m.nt = nt;
+        m.time_offset = ctx.time_offset;
+        m.u_offset = ctx.u_offset;
+        m.w_offset = ctx.w_offset;
+        m.unscale = ok ? __uint_as_float((eb - 13u) << 23) : 1.f;                  // 2^(E - 13)
+        m.pad = 0;
+        meta[bb] = m;
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) arrive_u(bar_at(B_FULL, bb));
+    }
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == DP_ISSUER)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
+}
+
 }  // namespace
 
 bool degridder_sep_supports(int subgrid_size, int nr_channels) {
   return subgrid_size >= 4 && subgrid_size % 4 == 0 && subgrid_size <= 32 && nr_channels >= 1 && nr_channels <= 4096;
 }
 
+static size_t pipe_smem_bytes(int N, int C) {
+  const int KC = N / 4, KCp = (KC + 1) & ~1, ncols = 8 * N, ncb = (C + 7) / 8;
+  return (size_t)2 * 2 * KCp * (ncols * 16 + 16) + (size_t)2 * 2 * KCp * DS_A_CH + (size_t)2 * N * 16 + 512 * 16 +
+         (size_t)2 * DP_UVW_STAGED * 12 + 12 * 8 + 2 * sizeof(PipeMeta) + 8 + 48 * 4 + (size_t)ncb * 10 * 4;
+}
+
 // d_todo = { n, subgrid[n] } (device; n zeroed by the caller on the same stream): the subgrids left to the per-pixel
-// kernel launched behind this one
-cudaError_t launch_degridder_sep(const KernelArgs &a, int *d_todo, cudaStream_t stream) {
+// kernel launched behind this one.  mode: 0 = the pipelined persistent kernel where its buffers fit (they do up to ~2000
+// channels), 1 = the one-subgrid-per-CTA kernel, 2 = the pipelined kernel or an error
+cudaError_t launch_degridder_sep(const KernelArgs &a, int *d_todo, cudaStream_t stream, int mode) {
   if (a.nr_subgrids == 0) return cudaSuccess;
   if (!degridder_sep_supports(a.subgrid_size, a.nr_channels) || !d_todo) return cudaErrorInvalidValue;
   const int N = a.subgrid_size, KC = N / 4, KCp = (KC + 1) & ~1, ncols = 8 * N, ncb = (a.nr_channels + 7) / 8;
+  const size_t smem_pipe = pipe_smem_bytes(N, a.nr_channels);
+  const bool pipe_fits = smem_pipe <= 227 * 1024;
+  if (mode == 2 && !pipe_fits) return cudaErrorInvalidValue;
+  if (mode != 1 && pipe_fits) {
+    static int sms[64] = {};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+    if (!sms[dev]) {
+      int n = 0;
+      e = cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+      if (e != cudaSuccess) return e;
+      sms[dev] = n;
+    }
+    e = cudaFuncSetAttribute(degridder_sep_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pipe);
+    if (e != cudaSuccess) return e;
+    const int ctas = a.nr_subgrids < sms[dev] ? a.nr_subgrids : sms[dev];
+    degridder_sep_pipe_kernel<<<dim3((unsigned)ctas), dim3(DP_THREADS), smem_pipe, stream>>>(a, d_todo);
+    return cudaGetLastError();
+  }
   int tmem_cols = 32;
   while (tmem_cols < ncols) tmem_cols *= 2;
   const size_t smem = (size_t)2 * KCp * (ncols * 16 + 16) + (size_t)2 * KCp * DS_A_CH + (size_t)N * 16 + 256 * 16 + DS_UVW_STAGED * 12 + 8 + 8 + 64 +

@@ -49,7 +49,8 @@ bool gridder_sep_supports(int subgrid_size, int nr_channels);
 cudaError_t launch_gridder_sep(const KernelArgs &a, int *d_todo, int *d_cancel, int *d_cancel_tiles, cudaStream_t stream);
 // row-column degridder (degridder_sep.cu); d_todo as for launch_gridder_sep
 bool degridder_sep_supports(int subgrid_size, int nr_channels);
-cudaError_t launch_degridder_sep(const KernelArgs &a, int *d_todo, cudaStream_t stream);
+// mode: 0 = pipelined persistent kernel where its buffers fit, 1 = one subgrid per CTA, 2 = pipelined or an error
+cudaError_t launch_degridder_sep(const KernelArgs &a, int *d_todo, cudaStream_t stream, int mode = 0);
 cudaError_t launch_degridder_tc(const KernelArgs &a, int poly, bool recur, cudaStream_t stream);
 // two M-tiles per warp, groups of 8 channels (degridder_tc8.cu); nr_channels % 8 == 0
 cudaError_t launch_degridder_tc8(const KernelArgs &a, bool recur, bool fold, cudaStream_t stream);

@@ -55,6 +55,25 @@ __device__ __forceinline__ void mbar_wait_u(unsigned bar, unsigned parity) {
     if (spin > (1 << 22)) __trap();
   }
 }
+// The same with a wall-clock bound instead of a spin count (a suspended try_wait may last up to the hint, so a spin
+// count bounds nothing): used by the persistent pipelines, whose roles wait on each other for whole subgrids.
+__device__ __forceinline__ void mbar_wait_t(unsigned bar, unsigned parity) {
+  unsigned done;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+               : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+  if (done) return;
+  unsigned long long t0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  while (!done) {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(bar), "r"(parity), "r"(MBAR_SUSPEND_HINT) : "memory");
+    if (!done) {
+      unsigned long long t1;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      if (t1 - t0 > 4000000000ull) __trap();   // 4 s: a lost arrival must fail loudly, not hang the GPU
+    }
+  }
+}
 __device__ __forceinline__ void umma_commit_u(unsigned bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }

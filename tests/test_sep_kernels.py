@@ -250,3 +250,46 @@ def test_degridder_sep_config1():
     e_cpu = np.abs(ref - ref64).max() / np.abs(ref64).max()
     print(f"degridder sep config 1: max rel {mx}, rel rms {rms}; vs f64 {e_gpu:.2e} (cpu {e_cpu:.2e})")
     assert e_gpu <= 2 * e_cpu + 2e-5
+
+
+# ---------------------------------------------------------- degridder: the pipelined persistent kernel (variant 32)
+PIPE, CLASSIC = 32, 31
+
+
+@pytest.mark.parametrize("shape", [s for s in SHAPES if s["subgrid_size"] <= 32])
+def test_degridder_pipe_equals_one_subgrid_per_cta(shape):
+    """degridder_sep.cu holds two kernels with the same arithmetic: one subgrid per CTA (31) and the warp-specialised
+    persistent pipeline (32, what 30 selects where its buffers fit).  Same MMAs in the same order, same split of the sum
+    over the rows: bit-identical visibilities."""
+    p = random_problem(221, **shape)
+    assert np.array_equal(run_degridder(p, FAST, PIPE), run_degridder(p, FAST, CLASSIC))
+    assert np.array_equal(run_degridder(with_linear_channels(p), FAST, PIPE), run_degridder(p, FAST, CLASSIC))
+
+
+def test_degridder_pipe_many_ragged_subgrids():
+    """More subgrids than SMs: every CTA of the persistent kernel walks through several subgrids with different numbers of
+    timesteps (0 included), some of them declined (wide field, large w) and left to the per-pixel kernel behind it, so
+    that both B buffers, both meta slots and every barrier phase are reused many times."""
+    o = oracle()
+    p = random_problem(222, subgrid_size=32, nr_channels=16, max_timesteps=70, nr_subgrids=900)
+    assert (p.metadata["nr_timesteps"] == 0).any()
+    ref = o.degridder(p)
+    rows = covered_rows(p)
+    got = run_degridder(p, FAST, PIPE)
+    assert_close(got[rows], ref[rows], 2, FAST, "degridder pipe, 900 ragged subgrids")
+    assert np.array_equal(got, run_degridder(p, FAST, CLASSIC))
+    assert not got[~rows].any()
+    # the same with a wide field: most subgrids are declined, a few (small |w|) stay
+    q = random_problem(223, subgrid_size=24, nr_channels=8, max_timesteps=9, nr_subgrids=700, image_size=0.2, w_step=0.0)
+    assert np.array_equal(run_degridder(q, FAST, PIPE), run_degridder(q, FAST, CLASSIC))
+    rows = covered_rows(q)
+    assert_close(run_degridder(q, FAST, PIPE)[rows], o.degridder(q)[rows], 2, FAST, "degridder pipe, wide field")
+
+
+def test_degridder_pipe_refused_where_buffers_do_not_fit():
+    """4000 channels: s_wn / s_dw / s_lin no longer fit beside the pipeline's buffers; 32 refuses, 30 takes the
+    one-subgrid-per-CTA kernel."""
+    p = random_problem(224, subgrid_size=32, nr_channels=4000, max_timesteps=2, nr_subgrids=2)
+    with pytest.raises(idg.IdgError):
+        run_degridder(p, FAST, PIPE)
+    assert np.array_equal(run_degridder(p, FAST, SEP), run_degridder(p, FAST, CLASSIC))
