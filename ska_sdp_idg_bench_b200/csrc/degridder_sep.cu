@@ -50,6 +50,16 @@ __device__ __forceinline__ float residual_h(const float x, const unsigned short 
   return r;
 }
 
+// 16 consecutive accumulator columns of the thread's TMEM lane.  Two of these, not one .x32: tools/tmem_ld.cu measures
+// 143 clocks per 32x32b.x32 load and at most 120 B/clock/SM however many warps issue them, against 39 clocks and 410
+// B/clock/SM for .x16 - with .x32 the 128 KB accumulator of a tile took longer to read (~1600 clocks) than to compute.
+__device__ __forceinline__ void tmem_ld16(const unsigned taddr, unsigned *r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                 "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+               : "r"(taddr));
+}
+
 // All 8 warps wait for the tile's MMAs (~1 us); a try_wait's own suspension is short (ncu: ~10 polls per warp and
 // tile, 13 % of the kernel's instructions), so they sleep between polls and leave the issue slots to the other CTA
 __device__ __forceinline__ void mbar_wait_sleep(unsigned long long *bar_ptr, const unsigned parity) {
@@ -314,35 +324,33 @@ degridder_sep_kernel(const KernelArgs a, const int tmem_cols, int *__restrict__ 
       const bool valid = in_range && c < C;
       const float k = s_wn[cb * 8 + (r_tile & 7)];
       const float vt = uvw_at(3 * t + 1), wt = uvw_at(3 * t + 2);
-      float2 acc[NR_POL];
+      // acc = sum Q ph with Q = qr + i qi, ph = (c, s): two packed accumulators per polarisation, ar += qr (c, s) and
+      // ai += qi (c, s), combined once per tile (acc = (ar.x - ai.y, ar.y + ai.x)): no (-s, c) operand to assemble
+      float2 ar[NR_POL], ai[NR_POL];
 #pragma unroll
-      for (int p = 0; p < NR_POL; p++) acc[p] = make_float2(0.f, 0.f);
+      for (int p = 0; p < NR_POL; p++) ar[p] = ai[p] = make_float2(0.f, 0.f);
       for (int g = g_lo; g < g_hi; g++) {
         unsigned r[32];
         const unsigned taddr = tmem_base + ((unsigned)(q4 * 32) << 16) + g * 32;
-        asm volatile(
-            "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
-            "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-              "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-              "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-              "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-            : "r"(taddr));
+        tmem_ld16(taddr, r);
+        tmem_ld16(taddr + 16, r + 16);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
         for (int yy = 0; yy < 4; yy++) {
           const float4 geo = sGeo[g * 4 + yy];        // broadcast
           const float idx = __fmaf_rn(wt, geo.y, __fmul_rn(vt, geo.x));
           const float2 ph = phasor<IDGB200_SINCOS_FAST>(__fmaf_rn(idx, k, -geo.z));
-          const float2 phs = make_float2(-ph.y, ph.x);
 #pragma unroll
-          for (int p = 0; p < NR_POL; p++) {      // acc += Q * ph: (qr, qr) * (c, s) + (qi, qi) * (-s, c)
+          for (int p = 0; p < NR_POL; p++) {
             const float qr = __uint_as_float(r[yy * 8 + 2 * p]), qi = __uint_as_float(r[yy * 8 + 2 * p + 1]);
-            acc[p] = ffma2(make_float2(qr, qr), ph, acc[p]);
-            acc[p] = ffma2(make_float2(qi, qi), phs, acc[p]);
+            ar[p] = ffma2(make_float2(qr, qr), ph, ar[p]);
+            ai[p] = ffma2(make_float2(qi, qi), ph, ai[p]);
           }
         }
       }
+      float2 acc[NR_POL];
+#pragma unroll
+      for (int p = 0; p < NR_POL; p++) acc[p] = make_float2(ar[p].x - ai[p].y, ar[p].y + ai[p].x);
       if (upper) {
         sPart[2 * r_tile] = make_float4(acc[0].x, acc[0].y, acc[1].x, acc[1].y);
         sPart[2 * r_tile + 1] = make_float4(acc[2].x, acc[2].y, acc[3].x, acc[3].y);
@@ -365,26 +373,71 @@ degridder_sep_kernel(const KernelArgs a, const int tmem_cols, int *__restrict__ 
 
 
 // ---------------------------------------------------------------------------------------------------------------------
-// The same arithmetic as a warp-specialised, persistent pipeline: ONE CTA per SM that loops over subgrids, 21 warps.
+// The same arithmetic as a warp-specialised, persistent pipeline: ONE CTA per SM that loops over subgrids, 28 warps.
 //   warps  0- 7  producers: the A rows (column phasors X, fp16 hi + lo) of tile i + 1 / i + 2 into one of two A buffers
-//   warps  8-15  consumers: the sum over the rows y of tile i out of one of two accumulators (all 512 TMEM columns)
-//   warp   16    issuer: the tile's 12 MMAs as soon as its A buffer is full and its accumulator has been drained
-//   warps 17-20  setup: the NEXT subgrid's separability check, B operand (P' in fp16 hi + lo, one of two B buffers),
+//   warps  8-23  consumers: the sum over the rows y of tile i out of one of two accumulators (all 512 TMEM columns);
+//                two groups of 8 warps, one per accumulator; in a group two warps per TMEM lane quadrant, half of the
+//                rows each
+//   warp   24    issuer: the tile's 12 MMAs as soon as its A buffer is full and its accumulator has been drained
+//   warps 25-27  setup: the NEXT subgrid's separability check, B operand (P' in fp16 hi + lo, one of two B buffers),
 //                staged uvw and row geometry, while the others are in the tile loop of the current subgrid
 // so that the tensor pipe, the producers' dependency chains and the consumers' TMEM reads overlap inside one CTA
 // instead of across two (the kernel above: a tile's phases one after the other, 2 CTAs per SM), and the per-subgrid
 // prologue (32 KB of pixels + A-terms) is hidden behind the previous subgrid.  Hand-offs are mbarriers only:
-//   b_full[2]  (4 setup warps)   -> everyone     B buffer, meta, geometry, uvw of subgrid j are ready
-//   b_empty[2] (17 warps)        -> setup        producers, consumers and the issuer are done with subgrid j's buffers
+//   b_full[2]  (3 setup warps)   -> everyone     B buffer, meta, geometry, uvw of subgrid j are ready
+//   b_empty[2] (25 warps)        -> setup        producers, consumers and the issuer are done with subgrid j's buffers
 //   a_full[2]  (8 producers)     -> issuer
 //   mma_done[2] (tcgen05.commit) -> consumers (accumulator full) and producers (A buffer free)
-//   d_empty[2] (8 consumers)     -> issuer       accumulator drained
-//   part_full[2] (4 upper consumer warps) -> lower consumer warps (the two halves of the sum over the rows meet)
+//   d_empty[2] (8 consumers of the accumulator's group) -> issuer       accumulator drained
+//   part_full[2][4] (upper consumer warp of a quadrant) -> its lower warp (the two halves of the sum over the rows meet)
+//   part_empty[2][4] (lower warp of a quadrant) -> its upper warp (the partial sums of tile it - 2 have been read)
 // Tiles are counted over the whole run of a CTA (`it`), buffer = it & 1, phase = (it >> 1) & 1.  Results are bit-identical
 // to the kernel above (same MMAs in the same order, same split of the sum over the rows).
-constexpr int DP_WARPS = 21, DP_THREADS = DP_WARPS * 32;
-constexpr int DP_ISSUER = 16, DP_SETUP0 = 17, DP_SETUP_THREADS = 128;
+// Consumer groups of 8 warps (2 per TMEM lane quadrant, half of the rows y each).  With 2 groups, group b takes the tiles
+// of accumulator b, so that a group has two tile periods for its tile: a consumer warp's chain through a tile (wake-up,
+// TMEM loads, 16 row phasors, partial sums through shared memory, store) is ~2000 clocks however few instructions it is
+// (tools/pipe_trace.py), longer than the tile's MMAs (1536)
+#ifndef DP_CGROUPS
+#define DP_CGROUPS 1     // measured: 4.41 ms with one group, 4.45 ms with two (the dispatch ports are what is short, not warps)
+#endif
+constexpr int DP_CONSUMERS = 8 * DP_CGROUPS;
+constexpr int DP_WARPS = 8 + DP_CONSUMERS + 1 + 3, DP_THREADS = DP_WARPS * 32;   // 28 warps of 72 registers (or 20 of 96)
+constexpr int DP_ISSUER = 8 + DP_CONSUMERS, DP_SETUP0 = DP_ISSUER + 1, DP_SETUP_WARPS = DP_WARPS - DP_SETUP0, DP_SETUP_THREADS = DP_SETUP_WARPS * 32;
 constexpr int DP_UVW_STAGED = 256;
+
+// wait flavours of the pipeline's per-tile hand-offs (A/B knobs, tools/build_ab.sh): 0 = try_wait with suspend hint and
+// wall-clock bound, 1 = bare try_wait loop, 2 / 3 / 4 = test_wait + nanosleep(32 / 128 / 256)
+#ifndef DP_WAIT_CONS
+#define DP_WAIT_CONS 1
+#endif
+#ifndef DP_WAIT_PROD
+#define DP_WAIT_PROD 3
+#endif
+#ifndef DP_WAIT_ISSUE
+#define DP_WAIT_ISSUE 1
+#endif
+#ifndef DP_CONS_PREFETCH     // 1: a group's row phasors are made ahead of its TMEM load's wait (the first group's before the MMA wait);
+#define DP_CONS_PREFETCH 0   //    measured slower (4.61 vs 4.43 ms): the extra live registers cost more than the overlap buys
+#endif
+// DP_TRACE builds (tools/build_ab.sh + tools/pipe_trace.py, never shipped): CTA 0 records clock64() at the hand-offs of
+// the tiles of its subgrids DP_TRACE_J0 .. DP_TRACE_J0 + 3 (steady state), one row per event
+#ifdef DP_TRACE
+constexpr int DP_TRACE_J0 = 20, DP_TRACE_TILES = 64, DP_TRACE_EVENTS = 56;
+__device__ long long dp_trace_buf[DP_TRACE_EVENTS * DP_TRACE_TILES];
+#define DP_MARK(ev, j, tile, cond)                                                                             \
+  do {                                                                                                         \
+    if (blockIdx.x == 0 && (cond) && (j) >= DP_TRACE_J0 && (j) < DP_TRACE_J0 + 4 && (tile) < 16)               \
+      dp_trace_buf[(ev) * DP_TRACE_TILES + ((j) - DP_TRACE_J0) * 16 + (tile)] = clock64();                     \
+  } while (0)
+#else
+#define DP_MARK(ev, j, tile, cond) do { } while (0)
+#endif
+template <int FLAVOUR>
+__device__ __forceinline__ void dp_wait(const unsigned bar, const unsigned parity) {
+  if (FLAVOUR == 0) mbar_wait_t(bar, parity);
+  else if (FLAVOUR == 1) mbar_wait_spin(bar, parity);
+  else mbar_wait_backoff(bar, parity, FLAVOUR == 2 ? 32 : FLAVOUR == 3 ? 128 : 256);
+}
 
 struct PipeMeta {        // per-subgrid scalars, written by the setup warps
   int run;               // 1: the row-column tiles of this subgrid run here; 0: nothing to do (declined or no timesteps)
@@ -427,18 +480,18 @@ degridder_sep_pipe_kernel(const KernelArgs a, int *__restrict__ todo) {
   unsigned char *sB = smem;                                             // [2][hi|lo][KCp][b_ch]
   unsigned char *sA = sB + 2 * b_buf;                                   // [2][hi|lo][KCp][DS_A_CH]
   float4 *sGeo = reinterpret_cast<float4 *>(sA + 2 * a_buf);            // [2][N] (m_y, f(m_y^2), offset_y, 0)
-  float4 *sPart = sGeo + 2 * N;                                         // [2][128][2] partial sums of the upper warps
+  float4 *sPart = sGeo + 2 * N;                                         // [2][128][2] partial sums of the upper consumer warps, per accumulator
   float *s_uvw = reinterpret_cast<float *>(sPart + 512);                // [2][DP_UVW_STAGED][3]
-  unsigned long long *bars = reinterpret_cast<unsigned long long *>(s_uvw + 2 * DP_UVW_STAGED * 3);   // [12]
-  PipeMeta *meta = reinterpret_cast<PipeMeta *>(bars + 12);             // [2]
+  unsigned long long *bars = reinterpret_cast<unsigned long long *>(s_uvw + 2 * DP_UVW_STAGED * 3);   // [26]
+  PipeMeta *meta = reinterpret_cast<PipeMeta *>(bars + 26);             // [2]
   unsigned *s_tmem = reinterpret_cast<unsigned *>(meta + 2);            // [2]
-  float *s_red = reinterpret_cast<float *>(s_tmem + 2);                 // [48]: [0, 21) kmax partials, [32, 48) setup partials
+  float *s_red = reinterpret_cast<float *>(s_tmem + 2);                 // [48]: [0, 28) kmax partials, [32, 48) setup partials
   float *s_wn = s_red + 48;                                             // [ncb * 8]
   float *s_dw = s_wn + ncb * 8;                                         // [ncb]
   int *s_lin = reinterpret_cast<int *>(s_dw + ncb);                     // [ncb]
   const unsigned bar_u = smem_u32(bars);
   // barrier b of buffer i: bar_u + (2 * b + i) * 8
-  enum { A_FULL = 0, MMA_DONE = 1, D_EMPTY = 2, PART_FULL = 3, B_FULL = 4, B_EMPTY = 5 };
+  enum { A_FULL = 0, MMA_DONE = 1, D_EMPTY = 2, B_FULL = 3, B_EMPTY = 4, PART_FULL = 5, PART_EMPTY = 9 };   // the last two: per accumulator and quadrant
   auto bar_at = [&](int b, int i) { return bar_u + (unsigned)(2 * b + i) * 8u; };
   auto arrive_u = [](unsigned bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); };
 
@@ -459,9 +512,12 @@ degridder_sep_pipe_kernel(const KernelArgs a, int *__restrict__ todo) {
       mbar_init(&bars[2 * A_FULL + i], 8);
       mbar_init(&bars[2 * MMA_DONE + i], 1);
       mbar_init(&bars[2 * D_EMPTY + i], 8);
-      mbar_init(&bars[2 * PART_FULL + i], 4);
-      mbar_init(&bars[2 * B_FULL + i], 4);
-      mbar_init(&bars[2 * B_EMPTY + i], 17);
+      mbar_init(&bars[2 * B_FULL + i], DP_SETUP_WARPS);
+      mbar_init(&bars[2 * B_EMPTY + i], 8 + DP_CONSUMERS + 1);
+    }
+    for (int q = 0; q < 8; q++) {
+      mbar_init(&bars[2 * PART_FULL + q], 1);
+      mbar_init(&bars[2 * PART_EMPTY + q], 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -514,10 +570,12 @@ degridder_sep_pipe_kernel(const KernelArgs a, int *__restrict__ todo) {
         int pt = (warp * 2) / ncb, pcb = warp * 2 - pt * ncb;
         for (int tile = 0; tile < ntiles; tile++, it++) {
           const int buf = it & 1;
-          if (it >= 2) mbar_wait_t(bar_at(MMA_DONE, buf), ((it >> 1) - 1) & 1);    // the MMAs of tile it - 2 have read the buffer
+          if (it >= 2) dp_wait<DP_WAIT_PROD>(bar_at(MMA_DONE, buf), ((it >> 1) - 1) & 1);   // the MMAs of tile it - 2 have read the buffer
+          DP_MARK(2 * warp, j, tile, lane == 0);
           unsigned char *a_col = sA + buf * a_buf + a_off;
 #pragma unroll
           for (int bi = 0; bi < 2; bi++) {
+            if ((IDGB200_ABLATE & 8) && !ablate_never()) continue;      // ablation: no A rows
             const int blk = tile * 16 + warp * 2 + bi;
             unsigned hi[8], lo[8];
             if (blk < nblk) {
@@ -560,15 +618,18 @@ degridder_sep_pipe_kernel(const KernelArgs a, int *__restrict__ todo) {
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           __syncwarp();
           if (lane == 0) arrive_u(bar_at(A_FULL, buf));
+          DP_MARK(2 * warp + 1, j, tile, lane == 0);
         }
       }
       __syncwarp();
       if (lane == 0) arrive_u(bar_at(B_EMPTY, bb));
     }
-  } else if (warp < 16) {
+  } else if (warp < DP_ISSUER) {
     // ========================================================= consumers: thread = visibility (TMEM lane = row of the tile)
-    const int q4 = warp & 3, upper = (warp >> 2) & 1;
-    const int ng = N >> 2, g_lo = upper ? (ng + 1) >> 1 : 0, g_hi = upper ? ng : (ng + 1) >> 1;
+    // group cg takes the tiles of accumulator cg (every tile with one group); in a group, quadrant q4's two warps (h = 0, 1)
+    // each sum half of the row groups, and warp 1 hands its sums to warp 0 through sPart
+    const int q4 = warp & 3, h = ((warp - 8) >> 2) & 1, cg = (warp - 8) >> 3;
+    const int ng = N >> 2, g_lo = h ? (ng + 1) >> 1 : 0, g_hi = h ? ng : (ng + 1) >> 1;
     const int r_tile = q4 * 32 + lane;
     int it = 0;
     for (int s_local = blockIdx.x, j = 0; s_local < S; s_local += gridDim.x, j++) {
@@ -585,6 +646,8 @@ degridder_sep_pipe_kernel(const KernelArgs a, int *__restrict__ todo) {
         float2 *g_out = const_cast<float2 *>(a.visibilities) + (size_t)m.time_offset * C * NR_POL;
         for (int tile = 0; tile < ntiles; tile++, it++) {
           const int buf = it & 1;
+          if (DP_CGROUPS == 2 && buf != cg) continue;
+          const unsigned part_full = bar_at(PART_FULL, 0) + 8u * (buf * 4 + q4), part_empty = bar_at(PART_EMPTY, 0) + 8u * (buf * 4 + q4);
           const int blk = tile * 16 + (r_tile >> 3);
           const bool in_range = blk < nblk;
           const int t = in_range ? blk / ncb : 0, cb = in_range ? blk - t * ncb : 0;
@@ -592,60 +655,85 @@ degridder_sep_pipe_kernel(const KernelArgs a, int *__restrict__ todo) {
           const bool valid = in_range && c < C;
           const float k = s_wn[c];
           const float vt = uvw_at(3 * t + 1), wt = uvw_at(3 * t + 2);
-          float2 acc[NR_POL];
+          // acc = sum Q ph with Q = qr + i qi, ph = (c, s): two packed accumulators per polarisation, ar += qr (c, s) and
+          // ai += qi (c, s), combined once per tile (acc = (ar.x - ai.y, ar.y + ai.x)): no (-s, c) operand to assemble
+          float2 ar[NR_POL], ai[NR_POL];
 #pragma unroll
-          for (int p = 0; p < NR_POL; p++) acc[p] = make_float2(0.f, 0.f);
-          mbar_wait_t(bar_at(MMA_DONE, buf), (it >> 1) & 1);
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          for (int g = g_lo; g < g_hi; g++) {
-            unsigned r[32];
-            const unsigned taddr = tmem_base + (unsigned)(buf * 256) + ((unsigned)(q4 * 32) << 16) + g * 32;
-            asm volatile(
-                "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
-                "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-                  "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-                  "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-                  "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-                : "r"(taddr));
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          for (int p = 0; p < NR_POL; p++) ar[p] = ai[p] = make_float2(0.f, 0.f);
+          // the row phasors Y_v(y) of a group of 4 rows do not depend on the MMAs: the first group's are made before the
+          // wait, the next group's behind the TMEM load of the current one
+          auto make_ph = [&](const int g, float2 *ph) {
 #pragma unroll
             for (int yy = 0; yy < 4; yy++) {
               const float4 geo = geo_b[g * 4 + yy];        // broadcast
               const float idx = __fmaf_rn(wt, geo.y, __fmul_rn(vt, geo.x));
-              const float2 ph = phasor<IDGB200_SINCOS_FAST>(__fmaf_rn(idx, k, -geo.z));
-              const float2 phs = make_float2(-ph.y, ph.x);
+              ph[yy] = phasor<IDGB200_SINCOS_FAST>(__fmaf_rn(idx, k, -geo.z));
+            }
+          };
+          float2 ph[4];
+          if (DP_CONS_PREFETCH && g_lo < g_hi) make_ph(g_lo, ph);
+          dp_wait<DP_WAIT_CONS>(bar_at(MMA_DONE, buf), (it >> 1) & 1);
+          DP_MARK(16 + 2 * (warp - 8), j, tile, lane == 0);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          for (int g = g_lo; g < g_hi; g++) {
+            if ((IDGB200_ABLATE & 4) && !ablate_never()) continue;      // ablation: no sum over the rows
+            unsigned r[32];
+            const unsigned taddr = tmem_base + (unsigned)(buf * 256) + ((unsigned)(q4 * 32) << 16) + g * 32;
+            tmem_ld16(taddr, r);
+            tmem_ld16(taddr + 16, r + 16);
+            float2 phn[4];
+            if (DP_CONS_PREFETCH) {
+              if (g + 1 < g_hi) make_ph(g + 1, phn);
+            } else {
+              make_ph(g, ph);
+            }
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int yy = 0; yy < 4; yy++) {
 #pragma unroll
               for (int p = 0; p < NR_POL; p++) {
                 const float qr = __uint_as_float(r[yy * 8 + 2 * p]), qi = __uint_as_float(r[yy * 8 + 2 * p + 1]);
-                acc[p] = ffma2(make_float2(qr, qr), ph, acc[p]);
-                acc[p] = ffma2(make_float2(qi, qi), phs, acc[p]);
+                ar[p] = ffma2(make_float2(qr, qr), ph[yy], ar[p]);
+                ai[p] = ffma2(make_float2(qi, qi), ph[yy], ai[p]);
               }
             }
+            if (DP_CONS_PREFETCH) {
+#pragma unroll
+              for (int yy = 0; yy < 4; yy++) ph[yy] = phn[yy];
+            }
           }
+          // the accumulator has been read (its values are in registers): the issuer may overwrite it
           asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-          float4 *part = sPart + buf * 256 + 2 * r_tile;
-          if (upper) {
+          __syncwarp();
+          if (lane == 0) arrive_u(bar_at(D_EMPTY, buf));
+          DP_MARK(17 + 2 * (warp - 8), j, tile, lane == 0);
+          float2 acc[NR_POL];
+#pragma unroll
+          for (int p = 0; p < NR_POL; p++) acc[p] = make_float2(ar[p].x - ai[p].y, ar[p].y + ai[p].x);
+          if (h > 0) {
+            if (it >= 2) dp_wait<DP_WAIT_CONS>(part_empty, ((it >> 1) - 1) & 1);    // warp 0 has read tile it - 2's
+            float4 *part = sPart + buf * 256 + 2 * r_tile;
             part[0] = make_float4(acc[0].x, acc[0].y, acc[1].x, acc[1].y);
             part[1] = make_float4(acc[2].x, acc[2].y, acc[3].x, acc[3].y);
             __syncwarp();
-            if (lane == 0) {
-              arrive_u(bar_at(PART_FULL, buf));
-              arrive_u(bar_at(D_EMPTY, buf));
-            }
+            if (lane == 0) arrive_u(part_full);
           } else {
-            mbar_wait_t(bar_at(PART_FULL, buf), (it >> 1) & 1);
+            dp_wait<DP_WAIT_CONS>(part_full, (it >> 1) & 1);
+            const float4 *part = sPart + buf * 256 + 2 * r_tile;
             const float4 p0 = part[0], p1 = part[1];
+            acc[0] = make_float2(acc[0].x + p0.x, acc[0].y + p0.y);
+            acc[1] = make_float2(acc[1].x + p0.z, acc[1].y + p0.w);
+            acc[2] = make_float2(acc[2].x + p1.x, acc[2].y + p1.y);
+            acc[3] = make_float2(acc[3].x + p1.z, acc[3].y + p1.w);
             __syncwarp();
-            if (lane == 0) arrive_u(bar_at(D_EMPTY, buf));     // accumulator drained AND the partial sums read
+            if (lane == 0) arrive_u(part_empty);
             if (valid) {
               float4 *o = reinterpret_cast<float4 *>(g_out + ((size_t)t * C + c) * NR_POL);
-              o[0] = make_float4((acc[0].x + p0.x) * unscale, (acc[0].y + p0.y) * unscale, (acc[1].x + p0.z) * unscale,
-                                 (acc[1].y + p0.w) * unscale);
-              o[1] = make_float4((acc[2].x + p1.x) * unscale, (acc[2].y + p1.y) * unscale, (acc[3].x + p1.z) * unscale,
-                                 (acc[3].y + p1.w) * unscale);
+              o[0] = make_float4(acc[0].x * unscale, acc[0].y * unscale, acc[1].x * unscale, acc[1].y * unscale);
+              o[1] = make_float4(acc[2].x * unscale, acc[2].y * unscale, acc[3].x * unscale, acc[3].y * unscale);
             }
           }
+          DP_MARK(h ? 53 : 52, j, tile, q4 == 0 && h < 2 && lane == 0);
         }
       }
       __syncwarp();
@@ -664,13 +752,15 @@ degridder_sep_pipe_kernel(const KernelArgs a, int *__restrict__ todo) {
         const int ntiles = (m.nt * ncb + 15) >> 4;
         for (int tile = 0; tile < ntiles; tile++, it++) {
           const int buf = it & 1;
-          mbar_wait_t(bar_at(A_FULL, buf), (it >> 1) & 1);
-          if (it >= 2) mbar_wait_t(bar_at(D_EMPTY, buf), ((it >> 1) - 1) & 1);
+          dp_wait<DP_WAIT_ISSUE>(bar_at(A_FULL, buf), (it >> 1) & 1);
+          if (it >= 2) dp_wait<DP_WAIT_ISSUE>(bar_at(D_EMPTY, buf), ((it >> 1) - 1) & 1);
+          DP_MARK(48, j, tile, lane == 0);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           if (elect_one()) {
             const unsigned d_t = tmem_base + (unsigned)(buf * 256);
             const unsigned a_b = a_u + buf * a_buf, b_b = b_u + bb * b_buf;
             for (int ks = 0; ks < KCp / 2; ks++) {
+              if ((IDGB200_ABLATE & 1) && !ablate_never()) continue;    // ablation: no MMAs
               const unsigned long long a_hi = smem_desc(a_b + 2 * ks * DS_A_CH, DS_A_CH, 128);
               const unsigned long long a_lo = smem_desc(a_b + (KCp + 2 * ks) * DS_A_CH, DS_A_CH, 128);
               const unsigned long long b_hi = smem_desc(b_b + 2 * ks * b_ch, b_ch, 128);
@@ -682,6 +772,7 @@ degridder_sep_pipe_kernel(const KernelArgs a, int *__restrict__ todo) {
             umma_commit_u(bar_at(MMA_DONE, buf));
           }
           __syncwarp();
+          DP_MARK(49, j, tile, lane == 0);
         }
       }
       __syncwarp();
@@ -700,7 +791,8 @@ degridder_sep_pipe_kernel(const KernelArgs a, int *__restrict__ todo) {
     const size_t plane = (size_t)npix;
     for (int s_local = blockIdx.x, j = 0; s_local < S; s_local += gridDim.x, j++) {
       const int bb = j & 1;
-      if (j >= 2) mbar_wait_t(bar_at(B_EMPTY, bb), ((j >> 1) - 1) & 1);
+      if (j >= 2) mbar_wait_backoff(bar_at(B_EMPTY, bb), ((j >> 1) - 1) & 1, 1000);
+      DP_MARK(50, j, 0, ts == 0);
       const int s = a.subgrid_offset + s_local;
       const SubgridCtx ctx = load_ctx(a, s);
       const int nt = ctx.nr_timesteps;
@@ -719,14 +811,58 @@ degridder_sep_pipe_kernel(const KernelArgs a, int *__restrict__ todo) {
       const size_t at1 = ((size_t)ctx.aterm_index * a.nr_stations + ctx.station1) * plane;
       const size_t at2 = ((size_t)ctx.aterm_index * a.nr_stations + ctx.station2) * plane;
       const float2 *sub = a.subgrids + (size_t)s * NR_POL * plane;
+      // pass 1: P' in fp32, parked in the words of the B buffer's lo half that the pixel's own lo parts will take
+      // (row n = y * 8 + 2 p + re|im of K chunk x / 4: eight words 16 bytes apart, only ever touched by the pixel's
+      // own thread).  The subgrid's pixels (DRAM) are brought there by cp.async, all of a thread's pixels in flight at
+      // once and none of them in registers; the A-terms (L2: the array is small) come through registers, one pixel ahead.
       float amax = 0.f;
-      if (nt > 0) {
-#pragma unroll 2
+      unsigned char *sBlo = sB + bb * b_buf + KCp * b_ch;
+      if (nt > 0 && !((IDGB200_ABLATE & 32) && !ablate_never())) {     // ablation: no P'
+        auto slot_of = [&](const int q) {
+          const int y = q / N, x = q - y * N;
+          return reinterpret_cast<float *>(sBlo + (x >> 2) * b_ch + (x & 3) * 4 + (y * 8) * 16);
+        };
         for (int q = ts; q < npix; q += DP_SETUP_THREADS) {
-          float2 px[NR_POL];
-          pprime(a, sub, at1, at2, q, N, plane, px);
+          const float *src = reinterpret_cast<const float *>(sub + subgrid_slot(q, N, a.flags));
+          float *slot = slot_of(q);
 #pragma unroll
-          for (int p = 0; p < NR_POL; p++) amax = fmaxf(amax, fmaxf(fabsf(px[p].x), fabsf(px[p].y)));
+          for (int p = 0; p < NR_POL; p++) {
+            cp_async4(slot + 8 * p, src + 2 * p * plane);
+            cp_async4(slot + 8 * p + 4, src + 2 * p * plane + 1);
+          }
+        }
+        cp_async_commit();
+        float2 a1[4], a2[4];
+        load_jones(a.aterms, (at1 + ts) * NR_POL, a1);
+        load_jones(a.aterms, (at2 + ts) * NR_POL, a2);
+        float sph = __ldg(&a.spheroidal[ts]);
+        asm volatile("cp.async.wait_all;" ::: "memory");     // this thread's pixels have landed (and the loads below stay below)
+        for (int q = ts; q < npix; q += DP_SETUP_THREADS) {
+          float2 b1[4], b2[4];
+          float sph_n = 0.f;
+          const int qn = q + DP_SETUP_THREADS;
+          if (qn < npix) {
+            load_jones(a.aterms, (at1 + qn) * NR_POL, b1);
+            load_jones(a.aterms, (at2 + qn) * NR_POL, b2);
+            sph_n = __ldg(&a.spheroidal[qn]);
+          }
+          float *slot = slot_of(q);
+          float2 px[NR_POL];
+#pragma unroll
+          for (int p = 0; p < NR_POL; p++) px[p] = make_float2(__fmul_rn(sph, slot[8 * p]), __fmul_rn(sph, slot[8 * p + 4]));
+          apply_aterm_degridder(px, a1, a2);
+#pragma unroll
+          for (int p = 0; p < NR_POL; p++) {
+            slot[8 * p] = px[p].x;
+            slot[8 * p + 4] = px[p].y;
+            amax = fmaxf(amax, fmaxf(fabsf(px[p].x), fabsf(px[p].y)));
+          }
+#pragma unroll
+          for (int i = 0; i < 4; i++) {
+            a1[i] = b1[i];
+            a2[i] = b2[i];
+          }
+          sph = sph_n;
         }
       }
 #pragma unroll
@@ -734,14 +870,14 @@ degridder_sep_pipe_kernel(const KernelArgs a, int *__restrict__ todo) {
         wmax = fmaxf(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
         amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
       }
-      float *red = s_red + 32 + bb * 8;          // [wmax of the 4 warps | amax of the 4 warps], one set per buffer
+      float *red = s_red + 32 + bb * 8;          // [wmax of the setup warps | amax of the setup warps], one set per buffer
       if (lane == 0) {
         red[sw] = wmax;
         red[4 + sw] = amax;
       }
-      setup_bar();
+      setup_bar();                               // also: every thread's fp32 P' is in the B buffer
 #pragma unroll
-      for (int i = 0; i < 4; i++) {
+      for (int i = 0; i < DP_SETUP_WARPS; i++) {
         wmax = fmaxf(wmax, red[i]);
         amax = fmaxf(amax, red[4 + i]);
       }
@@ -752,17 +888,19 @@ degridder_sep_pipe_kernel(const KernelArgs a, int *__restrict__ todo) {
       const unsigned eb = (__float_as_uint(amax) >> 23) & 0xffu;
       const bool ok = eb >= 14u && eb <= 253u;
       const float scale = ok ? __uint_as_float((267u - eb) << 23) : 1.f;           // 2^(13 - E)
-      if (run) {
+      if (run && !((IDGB200_ABLATE & 16) && !ablate_never())) {     // ablation: no B operand
         unsigned char *sBb = sB + bb * b_buf;
 #pragma unroll 2
         for (int q = ts; q < npix; q += DP_SETUP_THREADS) {
-          float2 px[NR_POL];
-          pprime(a, sub, at1, at2, q, N, plane, px);
           const int y = q / N, x = q - y * N;
           unsigned char *col = sBb + (x >> 2) * b_ch + (x & 3) * 4 + (y * 8) * 16;
+          const float *slot = reinterpret_cast<const float *>(col + KCp * b_ch);
+          float pv[8];
+#pragma unroll
+          for (int i = 0; i < 8; i++) pv[i] = slot[4 * i];
 #pragma unroll
           for (int p = 0; p < NR_POL; p++) {
-            const float re = px[p].x * scale, im = px[p].y * scale;
+            const float re = pv[2 * p] * scale, im = pv[2 * p + 1] * scale;
             const unsigned h_im = pack_h2(im, re);
             const unsigned h_re = pack_h2(re, -im);
             const float r_im = residual_h(im, (unsigned short)(h_im & 0xffffu));
@@ -794,6 +932,7 @@ degridder_sep_pipe_kernel(const KernelArgs a, int *__restrict__ todo) {
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncwarp();
       if (lane == 0) arrive_u(bar_at(B_FULL, bb));
+      DP_MARK(51, j, 0, ts == 0);
     }
   }
 
@@ -812,7 +951,7 @@ bool degridder_sep_supports(int subgrid_size, int nr_channels) {
 static size_t pipe_smem_bytes(int N, int C) {
   const int KC = N / 4, KCp = (KC + 1) & ~1, ncols = 8 * N, ncb = (C + 7) / 8;
   return (size_t)2 * 2 * KCp * (ncols * 16 + 16) + (size_t)2 * 2 * KCp * DS_A_CH + (size_t)2 * N * 16 + 512 * 16 +
-         (size_t)2 * DP_UVW_STAGED * 12 + 12 * 8 + 2 * sizeof(PipeMeta) + 8 + 48 * 4 + (size_t)ncb * 10 * 4;
+         (size_t)2 * DP_UVW_STAGED * 12 + 26 * 8 + 2 * sizeof(PipeMeta) + 8 + 48 * 4 + (size_t)ncb * 10 * 4;
 }
 
 // d_todo = { n, subgrid[n] } (device; n zeroed by the caller on the same stream): the subgrids left to the per-pixel
@@ -854,3 +993,9 @@ cudaError_t launch_degridder_sep(const KernelArgs &a, int *d_todo, cudaStream_t 
 }
 
 }  // namespace idgb200
+
+#ifdef DP_TRACE
+extern "C" int idgb200_dp_trace_read(long long *out) {
+  return (int)cudaMemcpyFromSymbol(out, idgb200::dp_trace_buf, sizeof(idgb200::dp_trace_buf));
+}
+#endif

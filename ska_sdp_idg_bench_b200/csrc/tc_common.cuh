@@ -74,6 +74,33 @@ __device__ __forceinline__ void mbar_wait_t(unsigned bar, unsigned parity) {
     }
   }
 }
+// Latency-critical waits of the persistent pipelines: nothing but the try_wait and its branch in the loop (the wall-clock
+// check above is six more instructions per poll, and a pipeline polls a few times per tile).  2^26 polls of >= ~50 clocks
+// bound a lost arrival to seconds.
+__device__ __forceinline__ void mbar_wait_spin(unsigned bar, unsigned parity) {
+  unsigned done;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+               : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+  for (unsigned spin = 0; !done; spin++) {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    if (spin > (1u << 26)) __trap();
+  }
+}
+// For waits that are known to be long (a role that runs ahead of the others): sleep between polls, so that the waiting
+// warp leaves the issue slots to the warps it is waiting for (ncu on the first pipelined degridder: a third of all
+// executed instructions were try_wait loops of warps with nothing to do).  Bounded like the others: 2^24 sleeps >= 4 s.
+__device__ __forceinline__ void mbar_wait_backoff(unsigned bar, unsigned parity, unsigned ns) {
+  unsigned done;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+               : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+  for (unsigned spin = 0; !done; spin++) {
+    __nanosleep(ns);
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    if (spin > (1u << 24)) __trap();
+  }
+}
 __device__ __forceinline__ void umma_commit_u(unsigned bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
