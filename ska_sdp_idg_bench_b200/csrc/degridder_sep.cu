@@ -1,5 +1,5 @@
 // IDG degridder in row-column form on tcgen05 + TMEM (variant 30, the default for FAST sincos and
-// subgrids of up to 32 x 32 pixels).
+// subgrids of up to 64 x 64 pixels).
 //
 // The transpose of gridder_sep.cu.  With the phase split into a column and a row part (see there; the
 // degridder's sign: degridder_reference.cpp:96-112),
@@ -75,16 +75,38 @@ __device__ __forceinline__ void mbar_wait_sleep(unsigned long long *bar_ptr, con
   }
 }
 
-__global__ void __launch_bounds__(DS_THREADS, 2)
+// P' of pixel q (degridder_reference.cpp:38-74): sph . subgrid, A1 . A2^H
+__device__ __forceinline__ void pprime(const KernelArgs &a, const float2 *sub, const size_t at1, const size_t at2,
+                                       const int q, const int N, const size_t plane, float2 *px) {
+  const float sph = __ldg(&a.spheroidal[q]);
+  const int src = subgrid_slot(q, N, a.flags);
+#pragma unroll
+  for (int p = 0; p < NR_POL; p++) {
+    const float2 v = __ldg(&sub[p * plane + src]);
+    px[p] = make_float2(__fmul_rn(sph, v.x), __fmul_rn(sph, v.y));
+  }
+  float2 a1[4], a2[4];
+  load_jones(a.aterms, (at1 + q) * NR_POL, a1);
+  load_jones(a.aterms, (at2 + q) * NR_POL, a2);
+  apply_aterm_degridder(px, a1, a2);
+}
+
+// XPL: columns x per lane of the A rows (1: subgrids of up to 32 x 32 pixels, 2 CTAs per SM; 2: up to 64 x 64, one CTA
+// per SM).  Subgrids of more than 32 rows are done in SLABS of 32 rows (8 x 32 = 256 accumulator columns each), one after
+// the other in the same CTA: B is rebuilt for the slab, the tiles run again (the A rows are made again: they are the
+// cheaper operand), and from the second slab on the partial visibilities are read back, added to and stored again by the
+// thread that wrote them - no atomics, the same bits every run.
+template <int XPL>
+__global__ void __launch_bounds__(DS_THREADS, XPL == 1 ? 2 : 1)
 degridder_sep_kernel(const KernelArgs a, const int tmem_cols, int *__restrict__ todo) {
   extern __shared__ __align__(1024) unsigned char smem[];
-  const int N = a.subgrid_size, C = a.nr_channels, npix = N * N;
+  const int N = a.subgrid_size, C = a.nr_channels;
   const int s_local = blockIdx.x, s = a.subgrid_offset + s_local;
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
   const int KC = N >> 2, KCp = (KC + 1) & ~1;      // 16-byte K chunks (4 columns x (cos, sin)); K steps of 2 chunks
-  const int ncols = 8 * N;                         // n = y * 8 + p * 2 + (re|im)
-  const int b_ch = ncols * 16 + 16;                // one K chunk of B, padded like DS_A_CH
+  const int nslab = (N + 31) >> 5, ny_max = min(N, 32);
+  const int b_ch = 8 * ny_max * 16 + 16;           // one K chunk of B (n = y * 8 + p * 2 + (re|im) of a slab), padded like DS_A_CH
   const int ncb = (C + 7) >> 3;
 
   unsigned char *sB = smem;                                             // [hi|lo][KCp][b_ch]
@@ -152,79 +174,16 @@ degridder_sep_kernel(const KernelArgs a, const int tmem_cols, int *__restrict__ 
   if (s_red[12] == 0.f) return;          // the per-pixel kernel behind this launch takes the subgrid
   if (nblk == 0) return;
 
-  // ---- B = P' (degridder_reference.cpp:38-74) in fp16 hi + lo; the fp32 pixels wait in the A buffer
-  {
-    const size_t plane = (size_t)npix;
-    const size_t at1 = ((size_t)ctx.aterm_index * a.nr_stations + ctx.station1) * plane;
-    const size_t at2 = ((size_t)ctx.aterm_index * a.nr_stations + ctx.station2) * plane;
-    const float2 *sub = a.subgrids + (size_t)s * NR_POL * plane;
-    float4 *sT = reinterpret_cast<float4 *>(sA);     // [npix][2]: 32 N^2 <= 2 KCp DS_A_CH for N <= 32
-    float amax = 0.f;
-    for (int q = tid; q < npix; q += DS_THREADS) {
-      const float sph = __ldg(&a.spheroidal[q]);
-      const int src = subgrid_slot(q, N, a.flags);
-      float2 px[NR_POL];
-#pragma unroll
-      for (int p = 0; p < NR_POL; p++) {
-        const float2 v = __ldg(&sub[p * plane + src]);
-        px[p] = make_float2(__fmul_rn(sph, v.x), __fmul_rn(sph, v.y));
-      }
-      float2 a1[4], a2[4];
-      load_jones(a.aterms, (at1 + q) * NR_POL, a1);
-      load_jones(a.aterms, (at2 + q) * NR_POL, a2);
-      apply_aterm_degridder(px, a1, a2);
-      sT[2 * q] = make_float4(px[0].x, px[0].y, px[1].x, px[1].y);
-      sT[2 * q + 1] = make_float4(px[2].x, px[2].y, px[3].x, px[3].y);
-#pragma unroll
-      for (int p = 0; p < NR_POL; p++) amax = fmaxf(amax, fmaxf(fabsf(px[p].x), fabsf(px[p].y)));
+  if (KCp != KC) {                       // the K padding: zero in A and B (never written again)
+    for (int i = tid; i < 128 * 4; i += DS_THREADS) {
+      *reinterpret_cast<unsigned *>(sA + KC * DS_A_CH + i * 4) = 0u;
+      *reinterpret_cast<unsigned *>(sA + (KCp + KC) * DS_A_CH + i * 4) = 0u;
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
-    if (lane == 0) s_red[warp] = amax;
-    __syncthreads();
-    if (tid == 0) {
-      for (int i = 1; i < 8; i++) amax = fmaxf(amax, s_red[i]);
-      const unsigned eb = (__float_as_uint(amax) >> 23) & 0xffu;
-      const bool ok = eb >= 14u && eb <= 253u;
-      s_red[10] = ok ? __uint_as_float((267u - eb) << 23) : 1.f;           // 2^(13 - E)
-      s_red[11] = ok ? __uint_as_float((eb - 13u) << 23) : 1.f;            // 2^(E - 13)
-    }
-    __syncthreads();
-    const float scale = s_red[10];
-    for (int q = tid; q < npix; q += DS_THREADS) {
-      const int y = q / N, x = q - y * N;
-      const float4 v01 = sT[2 * q], v23 = sT[2 * q + 1];
-      const float pv[8] = {v01.x, v01.y, v01.z, v01.w, v23.x, v23.y, v23.z, v23.w};
-      unsigned char *col = sB + (x >> 2) * b_ch + (x & 3) * 4 + (y * 8) * 16;
-#pragma unroll
-      for (int p = 0; p < NR_POL; p++) {
-        const float re = pv[2 * p] * scale, im = pv[2 * p + 1] * scale;
-        // row (y, p, re): (re, -im) against (cos, sin); row (y, p, im): (im, re)
-        const unsigned h_im = pack_h2(im, re);
-        const unsigned h_re = pack_h2(re, -im);
-        const float r_im = residual_h(im, (unsigned short)(h_im & 0xffffu));
-        const float r_re = residual_h(re, (unsigned short)(h_im >> 16));
-        unsigned char *row = col + (2 * p) * 16;
-        *reinterpret_cast<unsigned *>(row) = h_re;
-        *reinterpret_cast<unsigned *>(row + 16) = h_im;
-        *reinterpret_cast<unsigned *>(row + KCp * b_ch) = pack_h2(r_re, -r_im);
-        *reinterpret_cast<unsigned *>(row + KCp * b_ch + 16) = pack_h2(r_im, r_re);
-      }
-    }
-    __syncthreads();                    // the fp32 pixels have been read: the A buffer is free
-    if (KCp != KC) {                    // the K padding: zero in A (never written again) and in B
-      for (int i = tid; i < 128 * 4; i += DS_THREADS) {
-        *reinterpret_cast<unsigned *>(sA + KC * DS_A_CH + i * 4) = 0u;
-        *reinterpret_cast<unsigned *>(sA + (KCp + KC) * DS_A_CH + i * 4) = 0u;
-      }
-      for (int i = tid; i < ncols * 4; i += DS_THREADS) {
-        *reinterpret_cast<unsigned *>(sB + KC * b_ch + i * 4) = 0u;
-        *reinterpret_cast<unsigned *>(sB + (KCp + KC) * b_ch + i * 4) = 0u;
-      }
+    for (int i = tid; i < 8 * ny_max * 4; i += DS_THREADS) {
+      *reinterpret_cast<unsigned *>(sB + KC * b_ch + i * 4) = 0u;
+      *reinterpret_cast<unsigned *>(sB + (KCp + KC) * b_ch + i * 4) = 0u;
     }
   }
-  const float unscale = s_red[11];
-
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(tmem_cols));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
@@ -234,143 +193,224 @@ degridder_sep_kernel(const KernelArgs a, const int tmem_cols, int *__restrict__ 
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const unsigned tmem_base = *s_tmem;
 
-  // lane = column x of the A operand
-  const float l = compute_l(min(lane, N - 1), N, a.image_size);
-  const float n_x = compute_n(l, 0.f);
-  const float off_x = __fmaf_rn(ctx.w_offset, n_x, __fmul_rn(ctx.u_offset, l));
-  unsigned char *a_col = sA + (lane >> 2) * DS_A_CH + (lane & 3) * 4;
-  // instruction descriptor: D = F32, A = B = F16, K-major, N = 8 N, M = 128
-  const unsigned idesc = (1u << 4) | (((unsigned)ncols >> 3) << 17) | ((128u >> 4) << 24);
-  float2 *g_out = const_cast<float2 *>(a.visibilities) + (size_t)ctx.time_offset * C * NR_POL;
-  // the rows y of this warp in the sum over the rows: warps 0-3 the first groups of 4, warps 4-7 the rest
-  const int q4 = warp & 3, upper = warp >> 2;
-  const int ng = N >> 2, g_lo = upper ? (ng + 1) >> 1 : 0, g_hi = upper ? ng : (ng + 1) >> 1;
-
-  // (timestep, block) of the warp's first block of the tile, stepped by 16 blocks per tile
-  int pt = (warp * 2) / ncb, pcb = warp * 2 - pt * ncb;
-  const int step_t = 16 / ncb, step_cb = 16 - step_t * ncb;
-  for (int tile = 0; tile < ntiles; tile++) {
-    // ---- A rows of blocks 2 warp, 2 warp + 1 of the tile: X_v(x) for the block's 8 channels, hi + lo
+  // lane = column x (and x + 32) of the A operand
+  float l[XPL], n_x[XPL], off_x[XPL];
 #pragma unroll
-    for (int bi = 0; bi < 2; bi++) {   // both blocks unrolled: two independent chains in flight
-      const int blk = tile * 16 + warp * 2 + bi;
-      unsigned hi[8], lo[8];
-      if (blk < nblk) {
+  for (int xi = 0; xi < XPL; xi++) {
+    l[xi] = compute_l(min(lane + 32 * xi, N - 1), N, a.image_size);
+    n_x[xi] = compute_n(l[xi], 0.f);
+    off_x[xi] = __fmaf_rn(ctx.w_offset, n_x[xi], __fmul_rn(ctx.u_offset, l[xi]));
+  }
+  float2 *g_out = const_cast<float2 *>(a.visibilities) + (size_t)ctx.time_offset * C * NR_POL;
+  const int q4 = warp & 3, upper = warp >> 2;
+  const int step_t = 16 / ncb, step_cb = 16 - step_t * ncb;
+  const size_t plane = (size_t)N * N;
+  const size_t at1 = ((size_t)ctx.aterm_index * a.nr_stations + ctx.station1) * plane;
+  const size_t at2 = ((size_t)ctx.aterm_index * a.nr_stations + ctx.station2) * plane;
+  const float2 *sub = a.subgrids + (size_t)s * NR_POL * plane;
+  int it = 0;                                      // tiles so far: the parity of mma_done
+
+  for (int slab = 0; slab < nslab; slab++) {
+    const int y0 = slab * 32, ny = min(32, N - y0), npix = ny * N, ncols = 8 * ny;
+    // ---- B = P' (degridder_reference.cpp:38-74) of the slab's rows in fp16 hi + lo; the fp32 pixels wait in the A buffer
+    {
+      float4 *sT = reinterpret_cast<float4 *>(sA);     // [npix][2]: 32 ny N <= 2 KCp DS_A_CH
+      float amax = 0.f;
+      for (int q = tid; q < npix; q += DS_THREADS) {
+        const int qq = y0 * N + q;
+        float2 px[NR_POL];
+        pprime(a, sub, at1, at2, qq, N, plane, px);
+        sT[2 * q] = make_float4(px[0].x, px[0].y, px[1].x, px[1].y);
+        sT[2 * q + 1] = make_float4(px[2].x, px[2].y, px[3].x, px[3].y);
+#pragma unroll
+        for (int p = 0; p < NR_POL; p++) amax = fmaxf(amax, fmaxf(fabsf(px[p].x), fabsf(px[p].y)));
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+      if (lane == 0) s_red[warp] = amax;
+      __syncthreads();
+      if (tid == 0) {
+        for (int i = 1; i < 8; i++) amax = fmaxf(amax, s_red[i]);
+        const unsigned eb = (__float_as_uint(amax) >> 23) & 0xffu;
+        const bool ok = eb >= 14u && eb <= 253u;
+        s_red[10] = ok ? __uint_as_float((267u - eb) << 23) : 1.f;           // 2^(13 - E)
+        s_red[11] = ok ? __uint_as_float((eb - 13u) << 23) : 1.f;            // 2^(E - 13)
+      }
+      __syncthreads();
+      const float scale = s_red[10];
+      for (int q = tid; q < npix; q += DS_THREADS) {
+        const int y = q / N, x = q - y * N;
+        const float4 v01 = sT[2 * q], v23 = sT[2 * q + 1];
+        const float pv[8] = {v01.x, v01.y, v01.z, v01.w, v23.x, v23.y, v23.z, v23.w};
+        unsigned char *col = sB + (x >> 2) * b_ch + (x & 3) * 4 + (y * 8) * 16;
+#pragma unroll
+        for (int p = 0; p < NR_POL; p++) {
+          const float re = pv[2 * p] * scale, im = pv[2 * p + 1] * scale;
+          // row (y, p, re): (re, -im) against (cos, sin); row (y, p, im): (im, re)
+          const unsigned h_im = pack_h2(im, re);
+          const unsigned h_re = pack_h2(re, -im);
+          const float r_im = residual_h(im, (unsigned short)(h_im & 0xffffu));
+          const float r_re = residual_h(re, (unsigned short)(h_im >> 16));
+          unsigned char *row = col + (2 * p) * 16;
+          *reinterpret_cast<unsigned *>(row) = h_re;
+          *reinterpret_cast<unsigned *>(row + 16) = h_im;
+          *reinterpret_cast<unsigned *>(row + KCp * b_ch) = pack_h2(r_re, -r_im);
+          *reinterpret_cast<unsigned *>(row + KCp * b_ch + 16) = pack_h2(r_im, r_re);
+        }
+      }
+      __syncthreads();                    // the fp32 pixels have been read: the A buffer is free
+      if (KCp != KC && ny * N * 32 > KC * DS_A_CH) {   // the staging reached into A's K padding: zero it again
+        for (int i = tid; i < 128 * 4; i += DS_THREADS) {
+          *reinterpret_cast<unsigned *>(sA + KC * DS_A_CH + i * 4) = 0u;
+          *reinterpret_cast<unsigned *>(sA + (KCp + KC) * DS_A_CH + i * 4) = 0u;
+        }
+      }
+    }
+    const float unscale = s_red[11];
+    // instruction descriptor: D = F32, A = B = F16, K-major, N = 8 ny, M = 128
+    const unsigned idesc = (1u << 4) | (((unsigned)ncols >> 3) << 17) | ((128u >> 4) << 24);
+    // the rows y of this warp in the sum over the rows: warps 0-3 the first groups of 4, warps 4-7 the rest
+    const int ng = ny >> 2, g_lo = upper ? (ng + 1) >> 1 : 0, g_hi = upper ? ng : (ng + 1) >> 1;
+
+    // (timestep, block) of the warp's first block of the tile, stepped by 16 blocks per tile
+    int pt = (warp * 2) / ncb, pcb = warp * 2 - pt * ncb;
+    for (int tile = 0; tile < ntiles; tile++, it++) {
+      // ---- A rows of blocks 2 warp, 2 warp + 1 of the tile: X_v(x) for the block's 8 channels, hi + lo
+#pragma unroll
+      for (int bi = 0; bi < 2; bi++) {   // both blocks unrolled: two independent chains in flight
+        const int blk = tile * 16 + warp * 2 + bi;
         int t = pt, cb = pcb + bi;
         if (cb >= ncb) { cb -= ncb; t++; }
-        const float idx = __fmaf_rn(uvw_at(3 * t + 2), n_x, __fmul_rn(uvw_at(3 * t), l));
-        const float *wn8 = s_wn + cb * 8;
-        float2 ph[8];
-        if (s_lin[cb]) {   // first channel by sincos, second by one rotation, then the three-term recurrence
-          ph[0] = phasor<IDGB200_SINCOS_FAST>(__fmaf_rn(idx, wn8[0], -off_x));
-          const float2 d = phasor<IDGB200_SINCOS_FAST>(__fmul_rn(idx, s_dw[cb]));
-          ph[1] = ffma2(make_float2(ph[0].y, ph[0].x), make_float2(-d.y, d.y), __fmul2_rn(ph[0], make_float2(d.x, d.x)));
-          const float c2 = __fadd_rn(d.x, d.x);
+        const bool live = blk < nblk;
+        const float ut = live ? uvw_at(3 * t) : 0.f, wt = live ? uvw_at(3 * t + 2) : 0.f;
+        const float *wn8 = s_wn + (live ? cb : 0) * 8;
+        const bool lin = live && s_lin[cb];
+        const float dwc = live ? s_dw[cb] : 0.f;
 #pragma unroll
-          for (int i = 2; i < 8; i++) ph[i] = ffma2(ph[i - 1], make_float2(c2, c2), make_float2(-ph[i - 2].x, -ph[i - 2].y));
-        } else {
+        for (int xi = 0; xi < XPL; xi++) {
+          unsigned hi[8], lo[8];
+          if (live) {
+            const float idx = __fmaf_rn(wt, n_x[xi], __fmul_rn(ut, l[xi]));
+            float2 ph[8];
+            if (lin) {   // first channel by sincos, second by one rotation, then the three-term recurrence
+              ph[0] = phasor<IDGB200_SINCOS_FAST>(__fmaf_rn(idx, wn8[0], -off_x[xi]));
+              const float2 d = phasor<IDGB200_SINCOS_FAST>(__fmul_rn(idx, dwc));
+              ph[1] = ffma2(make_float2(ph[0].y, ph[0].x), make_float2(-d.y, d.y), __fmul2_rn(ph[0], make_float2(d.x, d.x)));
+              const float c2 = __fadd_rn(d.x, d.x);
 #pragma unroll
-          for (int i = 0; i < 8; i++) ph[i] = phasor<IDGB200_SINCOS_FAST>(__fmaf_rn(idx, wn8[i], -off_x));
-        }
+              for (int i = 2; i < 8; i++) ph[i] = ffma2(ph[i - 1], make_float2(c2, c2), make_float2(-ph[i - 2].x, -ph[i - 2].y));
+            } else {
 #pragma unroll
-        for (int i = 0; i < 8; i++) {
-          hi[i] = pack_h2(ph[i].x, ph[i].y);
-          lo[i] = pack_h2(residual_h(ph[i].x, (unsigned short)(hi[i] & 0xffffu)), residual_h(ph[i].y, (unsigned short)(hi[i] >> 16)));
-        }
-      } else {
+              for (int i = 0; i < 8; i++) ph[i] = phasor<IDGB200_SINCOS_FAST>(__fmaf_rn(idx, wn8[i], -off_x[xi]));
+            }
 #pragma unroll
-        for (int i = 0; i < 8; i++) hi[i] = lo[i] = 0u;
-      }
-      if (lane < N) {
-        unsigned char *row = a_col + ((warp * 2 + bi) * 8) * 16;
+            for (int i = 0; i < 8; i++) {
+              hi[i] = pack_h2(ph[i].x, ph[i].y);
+              lo[i] = pack_h2(residual_h(ph[i].x, (unsigned short)(hi[i] & 0xffffu)), residual_h(ph[i].y, (unsigned short)(hi[i] >> 16)));
+            }
+          } else {
 #pragma unroll
-        for (int i = 0; i < 8; i++) {
-          *reinterpret_cast<unsigned *>(row + i * 16) = hi[i];
-          *reinterpret_cast<unsigned *>(row + i * 16 + KCp * DS_A_CH) = lo[i];
-        }
-      }
-    }
-    pt += step_t; pcb += step_cb;
-    if (pcb >= ncb) { pcb -= ncb; pt++; }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    __syncthreads();
-    if (warp == 0) {
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      if (elect_one()) {
-        const unsigned a_u = smem_u32(sA), b_u = smem_u32(sB);
-        for (int ks = 0; ks < KCp / 2; ks++) {
-          const unsigned long long a_hi = smem_desc(a_u + 2 * ks * DS_A_CH, DS_A_CH, 128);
-          const unsigned long long a_lo = smem_desc(a_u + (KCp + 2 * ks) * DS_A_CH, DS_A_CH, 128);
-          const unsigned long long b_hi = smem_desc(b_u + 2 * ks * b_ch, b_ch, 128);
-          const unsigned long long b_lo = smem_desc(b_u + (KCp + 2 * ks) * b_ch, b_ch, 128);
-          umma_f16(tmem_base, a_hi, b_hi, idesc, ks > 0 ? 1u : 0u);
-          umma_f16(tmem_base, a_lo, b_hi, idesc, 1u);
-          umma_f16(tmem_base, a_hi, b_lo, idesc, 1u);
-        }
-        umma_commit(mma_done);
-      }
-      __syncwarp();
-    }
-    mbar_wait_sleep(mma_done, tile & 1);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-
-    // ---- the sum over the rows y: thread = row 32 q4 + lane of the tile, warps q4 and q4 + 4 half of the rows each
-    {
-      const int r_tile = q4 * 32 + lane;
-      const int blk = tile * 16 + (r_tile >> 3);
-      const bool in_range = blk < nblk;
-      const int t = in_range ? blk / ncb : 0, cb = in_range ? blk - t * ncb : 0;
-      const int c = cb * 8 + (r_tile & 7);
-      const bool valid = in_range && c < C;
-      const float k = s_wn[cb * 8 + (r_tile & 7)];
-      const float vt = uvw_at(3 * t + 1), wt = uvw_at(3 * t + 2);
-      // acc = sum Q ph with Q = qr + i qi, ph = (c, s): two packed accumulators per polarisation, ar += qr (c, s) and
-      // ai += qi (c, s), combined once per tile (acc = (ar.x - ai.y, ar.y + ai.x)): no (-s, c) operand to assemble
-      float2 ar[NR_POL], ai[NR_POL];
+            for (int i = 0; i < 8; i++) hi[i] = lo[i] = 0u;
+          }
+          const int x = lane + 32 * xi;
+          if (x < N) {
+            unsigned char *row = sA + (x >> 2) * DS_A_CH + (x & 3) * 4 + ((warp * 2 + bi) * 8) * 16;
 #pragma unroll
-      for (int p = 0; p < NR_POL; p++) ar[p] = ai[p] = make_float2(0.f, 0.f);
-      for (int g = g_lo; g < g_hi; g++) {
-        unsigned r[32];
-        const unsigned taddr = tmem_base + ((unsigned)(q4 * 32) << 16) + g * 32;
-        tmem_ld16(taddr, r);
-        tmem_ld16(taddr + 16, r + 16);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-        for (int yy = 0; yy < 4; yy++) {
-          const float4 geo = sGeo[g * 4 + yy];        // broadcast
-          const float idx = __fmaf_rn(wt, geo.y, __fmul_rn(vt, geo.x));
-          const float2 ph = phasor<IDGB200_SINCOS_FAST>(__fmaf_rn(idx, k, -geo.z));
-#pragma unroll
-          for (int p = 0; p < NR_POL; p++) {
-            const float qr = __uint_as_float(r[yy * 8 + 2 * p]), qi = __uint_as_float(r[yy * 8 + 2 * p + 1]);
-            ar[p] = ffma2(make_float2(qr, qr), ph, ar[p]);
-            ai[p] = ffma2(make_float2(qi, qi), ph, ai[p]);
+            for (int i = 0; i < 8; i++) {
+              *reinterpret_cast<unsigned *>(row + i * 16) = hi[i];
+              *reinterpret_cast<unsigned *>(row + i * 16 + KCp * DS_A_CH) = lo[i];
+            }
           }
         }
       }
-      float2 acc[NR_POL];
-#pragma unroll
-      for (int p = 0; p < NR_POL; p++) acc[p] = make_float2(ar[p].x - ai[p].y, ar[p].y + ai[p].x);
-      if (upper) {
-        sPart[2 * r_tile] = make_float4(acc[0].x, acc[0].y, acc[1].x, acc[1].y);
-        sPart[2 * r_tile + 1] = make_float4(acc[2].x, acc[2].y, acc[3].x, acc[3].y);
+      pt += step_t; pcb += step_cb;
+      if (pcb >= ncb) { pcb -= ncb; pt++; }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncthreads();
+      if (warp == 0) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (elect_one()) {
+          const unsigned a_u = smem_u32(sA), b_u = smem_u32(sB);
+          for (int ks = 0; ks < KCp / 2; ks++) {
+            const unsigned long long a_hi = smem_desc(a_u + 2 * ks * DS_A_CH, DS_A_CH, 128);
+            const unsigned long long a_lo = smem_desc(a_u + (KCp + 2 * ks) * DS_A_CH, DS_A_CH, 128);
+            const unsigned long long b_hi = smem_desc(b_u + 2 * ks * b_ch, b_ch, 128);
+            const unsigned long long b_lo = smem_desc(b_u + (KCp + 2 * ks) * b_ch, b_ch, 128);
+            umma_f16(tmem_base, a_hi, b_hi, idesc, ks > 0 ? 1u : 0u);
+            umma_f16(tmem_base, a_lo, b_hi, idesc, 1u);
+            umma_f16(tmem_base, a_hi, b_lo, idesc, 1u);
+          }
+          umma_commit(mma_done);
+        }
+        __syncwarp();
       }
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      __syncthreads();                  // accumulator and A buffer are free for the next tile; the upper halves are in
-      if (!upper && valid) {
-        const float4 p0 = sPart[2 * r_tile], p1 = sPart[2 * r_tile + 1];
-        float4 *o = reinterpret_cast<float4 *>(g_out + ((size_t)t * C + c) * NR_POL);
-        o[0] = make_float4((acc[0].x + p0.x) * unscale, (acc[0].y + p0.y) * unscale, (acc[1].x + p0.z) * unscale,
-                           (acc[1].y + p0.w) * unscale);
-        o[1] = make_float4((acc[2].x + p1.x) * unscale, (acc[2].y + p1.y) * unscale, (acc[3].x + p1.z) * unscale,
-                           (acc[3].y + p1.w) * unscale);
+      mbar_wait_sleep(mma_done, it & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+      // ---- the sum over the rows y: thread = row 32 q4 + lane of the tile, warps q4 and q4 + 4 half of the rows each
+      {
+        const int r_tile = q4 * 32 + lane;
+        const int blk = tile * 16 + (r_tile >> 3);
+        const bool in_range = blk < nblk;
+        const int t = in_range ? blk / ncb : 0, cb = in_range ? blk - t * ncb : 0;
+        const int c = cb * 8 + (r_tile & 7);
+        const bool valid = in_range && c < C;
+        const float k = s_wn[cb * 8 + (r_tile & 7)];
+        const float vt = uvw_at(3 * t + 1), wt = uvw_at(3 * t + 2);
+        // acc = sum Q ph with Q = qr + i qi, ph = (c, s): two packed accumulators per polarisation, ar += qr (c, s) and
+        // ai += qi (c, s), combined once per tile (acc = (ar.x - ai.y, ar.y + ai.x)): no (-s, c) operand to assemble
+        float2 ar[NR_POL], ai[NR_POL];
+#pragma unroll
+        for (int p = 0; p < NR_POL; p++) ar[p] = ai[p] = make_float2(0.f, 0.f);
+        for (int g = g_lo; g < g_hi; g++) {
+          unsigned r[32];
+          const unsigned taddr = tmem_base + ((unsigned)(q4 * 32) << 16) + g * 32;
+          tmem_ld16(taddr, r);
+          tmem_ld16(taddr + 16, r + 16);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int yy = 0; yy < 4; yy++) {
+            const float4 geo = sGeo[y0 + g * 4 + yy];        // broadcast
+            const float idx = __fmaf_rn(wt, geo.y, __fmul_rn(vt, geo.x));
+            const float2 ph = phasor<IDGB200_SINCOS_FAST>(__fmaf_rn(idx, k, -geo.z));
+#pragma unroll
+            for (int p = 0; p < NR_POL; p++) {
+              const float qr = __uint_as_float(r[yy * 8 + 2 * p]), qi = __uint_as_float(r[yy * 8 + 2 * p + 1]);
+              ar[p] = ffma2(make_float2(qr, qr), ph, ar[p]);
+              ai[p] = ffma2(make_float2(qi, qi), ph, ai[p]);
+            }
+          }
+        }
+        float2 acc[NR_POL];
+#pragma unroll
+        for (int p = 0; p < NR_POL; p++) acc[p] = make_float2(ar[p].x - ai[p].y, ar[p].y + ai[p].x);
+        if (upper) {
+          sPart[2 * r_tile] = make_float4(acc[0].x, acc[0].y, acc[1].x, acc[1].y);
+          sPart[2 * r_tile + 1] = make_float4(acc[2].x, acc[2].y, acc[3].x, acc[3].y);
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();                  // accumulator and A buffer are free for the next tile; the upper halves are in
+        if (!upper && valid) {
+          const float4 p0 = sPart[2 * r_tile], p1 = sPart[2 * r_tile + 1];
+          float4 *o = reinterpret_cast<float4 *>(g_out + ((size_t)t * C + c) * NR_POL);
+          float4 o0 = make_float4((acc[0].x + p0.x) * unscale, (acc[0].y + p0.y) * unscale, (acc[1].x + p0.z) * unscale,
+                                  (acc[1].y + p0.w) * unscale);
+          float4 o1 = make_float4((acc[2].x + p1.x) * unscale, (acc[2].y + p1.y) * unscale, (acc[3].x + p1.z) * unscale,
+                                  (acc[3].y + p1.w) * unscale);
+          if (slab > 0) {                 // the earlier slabs' partial visibility: written by this very thread
+            const float4 e0 = o[0], e1 = o[1];
+            o0 = make_float4(e0.x + o0.x, e0.y + o0.y, e0.z + o0.z, e0.w + o0.w);
+            o1 = make_float4(e1.x + o1.x, e1.y + o1.y, e1.z + o1.z, e1.w + o1.w);
+          }
+          o[0] = o0;
+          o[1] = o1;
+        }
       }
     }
   }
   if (warp == 0)
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols));
 }
-
 
 // ---------------------------------------------------------------------------------------------------------------------
 // The same arithmetic as a warp-specialised, persistent pipeline: ONE CTA per SM that loops over subgrids, 28 warps.
@@ -448,22 +488,6 @@ struct PipeMeta {        // per-subgrid scalars, written by the setup warps
 };
 
 __device__ __forceinline__ void setup_bar() { asm volatile("bar.sync 1, %0;" ::"n"(DP_SETUP_THREADS) : "memory"); }
-
-// P' of pixel q (degridder_reference.cpp:38-74): sph . subgrid, A1 . A2^H
-__device__ __forceinline__ void pprime(const KernelArgs &a, const float2 *sub, const size_t at1, const size_t at2,
-                                       const int q, const int N, const size_t plane, float2 *px) {
-  const float sph = __ldg(&a.spheroidal[q]);
-  const int src = subgrid_slot(q, N, a.flags);
-#pragma unroll
-  for (int p = 0; p < NR_POL; p++) {
-    const float2 v = __ldg(&sub[p * plane + src]);
-    px[p] = make_float2(__fmul_rn(sph, v.x), __fmul_rn(sph, v.y));
-  }
-  float2 a1[4], a2[4];
-  load_jones(a.aterms, (at1 + q) * NR_POL, a1);
-  load_jones(a.aterms, (at2 + q) * NR_POL, a2);
-  apply_aterm_degridder(px, a1, a2);
-}
 
 __global__ void __launch_bounds__(DP_THREADS, 1)
 degridder_sep_pipe_kernel(const KernelArgs a, int *__restrict__ todo) {
@@ -945,7 +969,7 @@ degridder_sep_pipe_kernel(const KernelArgs a, int *__restrict__ todo) {
 }  // namespace
 
 bool degridder_sep_supports(int subgrid_size, int nr_channels) {
-  return subgrid_size >= 4 && subgrid_size % 4 == 0 && subgrid_size <= 32 && nr_channels >= 1 && nr_channels <= 4096;
+  return subgrid_size >= 4 && subgrid_size % 4 == 0 && subgrid_size <= 64 && nr_channels >= 1 && nr_channels <= 4096;
 }
 
 static size_t pipe_smem_bytes(int N, int C) {
@@ -960,9 +984,9 @@ static size_t pipe_smem_bytes(int N, int C) {
 cudaError_t launch_degridder_sep(const KernelArgs &a, int *d_todo, cudaStream_t stream, int mode) {
   if (a.nr_subgrids == 0) return cudaSuccess;
   if (!degridder_sep_supports(a.subgrid_size, a.nr_channels) || !d_todo) return cudaErrorInvalidValue;
-  const int N = a.subgrid_size, KC = N / 4, KCp = (KC + 1) & ~1, ncols = 8 * N, ncb = (a.nr_channels + 7) / 8;
+  const int N = a.subgrid_size, KC = N / 4, KCp = (KC + 1) & ~1, ncols = 8 * (N < 32 ? N : 32), ncb = (a.nr_channels + 7) / 8;
   const size_t smem_pipe = pipe_smem_bytes(N, a.nr_channels);
-  const bool pipe_fits = smem_pipe <= 227 * 1024;
+  const bool pipe_fits = N <= 32 && smem_pipe <= 227 * 1024;
   if (mode == 2 && !pipe_fits) return cudaErrorInvalidValue;
   if (mode != 1 && pipe_fits) {
     static int sms[64] = {};
@@ -986,9 +1010,11 @@ cudaError_t launch_degridder_sep(const KernelArgs &a, int *d_todo, cudaStream_t 
   while (tmem_cols < ncols) tmem_cols *= 2;
   const size_t smem = (size_t)2 * KCp * (ncols * 16 + 16) + (size_t)2 * KCp * DS_A_CH + (size_t)N * 16 + 256 * 16 + DS_UVW_STAGED * 12 + 8 + 8 + 64 +
                       (size_t)ncb * 10 * 4;
-  cudaError_t e = cudaFuncSetAttribute(degridder_sep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (smem > 227 * 1024) return cudaErrorInvalidValue;
+  auto kernel = N > 32 ? degridder_sep_kernel<2> : degridder_sep_kernel<1>;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  degridder_sep_kernel<<<dim3((unsigned)a.nr_subgrids), dim3(DS_THREADS), smem, stream>>>(a, tmem_cols, d_todo);
+  kernel<<<dim3((unsigned)a.nr_subgrids), dim3(DS_THREADS), smem, stream>>>(a, tmem_cols, d_todo);
   return cudaGetLastError();
 }
 

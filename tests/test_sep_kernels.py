@@ -192,7 +192,7 @@ def test_degridder_sep_vs_oracle(shape, linear):
         with_linear_channels(p)
     ref = o.degridder(p)
     rows = covered_rows(p)
-    if p.subgrid_size > 32:   # the row-column degridder takes subgrids of up to 32 x 32 pixels
+    if p.subgrid_size > 64:   # the row-column degridder takes subgrids of up to 64 x 64 pixels
         with pytest.raises(idg.IdgError):
             run_degridder(p, FAST, SEP)
         assert idg.resolve_variant(p.subgrid_size, p.nr_channels, FAST, 0, gridder=False) != SEP
