@@ -33,7 +33,6 @@ namespace idgb200 {
 
 namespace {
 
-constexpr int DS_THREADS = 256;
 constexpr int DS_A_CH = 128 * 16 + 16;           // one 16-byte K chunk of 128 rows, padded: the 8 chunks a warp's
                                                  // 4-byte stores touch fall into different banks
 constexpr float SEP_PHASE_TOL = 1e-4f;           // largest dropped phase |gamma| r (rad), as in gridder_sep.cu
@@ -95,10 +94,14 @@ __device__ __forceinline__ void pprime(const KernelArgs &a, const float2 *sub, c
 // per SM).  Subgrids of more than 32 rows are done in SLABS of 32 rows (8 x 32 = 256 accumulator columns each), one after
 // the other in the same CTA: B is rebuilt for the slab, the tiles run again (the A rows are made again: they are the
 // cheaper operand), and from the second slab on the partial visibilities are read back, added to and stored again by the
-// thread that wrote them - no atomics, the same bits every run.
+// thread that wrote them - no atomics, the same bits every run.  With one CTA per SM there is room for 16 warps: one
+// block of A rows per warp, four warps per TMEM lane quadrant in the sum over the rows.
 template <int XPL>
-__global__ void __launch_bounds__(DS_THREADS, XPL == 1 ? 2 : 1)
+__global__ void __launch_bounds__(XPL == 1 ? 256 : 512, XPL == 1 ? 2 : 1)
 degridder_sep_kernel(const KernelArgs a, const int tmem_cols, int *__restrict__ todo) {
+  constexpr int NW = XPL == 1 ? 8 : 16, DS_THREADS = NW * 32;   // warps
+  constexpr int NP = NW / 4;                                    // warps per TMEM lane quadrant = parts of the sum over the rows
+  constexpr int BPW = 16 / NW;                                  // blocks of A rows per warp and tile
   extern __shared__ __align__(1024) unsigned char smem[];
   const int N = a.subgrid_size, C = a.nr_channels;
   const int s_local = blockIdx.x, s = a.subgrid_offset + s_local;
@@ -112,12 +115,12 @@ degridder_sep_kernel(const KernelArgs a, const int tmem_cols, int *__restrict__ 
   unsigned char *sB = smem;                                             // [hi|lo][KCp][b_ch]
   unsigned char *sA = sB + 2 * KCp * b_ch;                              // [hi|lo][KCp][DS_A_CH]
   float4 *sGeo = reinterpret_cast<float4 *>(sA + 2 * KCp * DS_A_CH);    // [N] (m_y, f(m_y^2), offset_y, 0)
-  float4 *sPart = sGeo + N;                                             // [128][2] partial sums of the upper warps
-  float *s_uvw = reinterpret_cast<float *>(sPart + 256);                // [DS_UVW_STAGED][3]
+  float4 *sPart = sGeo + N;                                             // [NP - 1][128][2] partial sums of a quadrant's warps 1 .. NP - 1
+  float *s_uvw = reinterpret_cast<float *>(sPart + (NP - 1) * 256);                // [DS_UVW_STAGED][3]
   unsigned long long *mma_done = reinterpret_cast<unsigned long long *>(s_uvw + DS_UVW_STAGED * 3);
   unsigned *s_tmem = reinterpret_cast<unsigned *>(mma_done + 1);
-  float *s_red = reinterpret_cast<float *>(s_tmem + 2);                 // [16]
-  float *s_wn = s_red + 16;                                             // [ncb * 8]
+  float *s_red = reinterpret_cast<float *>(s_tmem + 2);                 // [24]: [0, 16) per warp, [16, 19) scale, unscale, verdict
+  float *s_wn = s_red + 24;                                             // [ncb * 8]
   float *s_dw = s_wn + ncb * 8;                                         // [ncb]
   int *s_lin = reinterpret_cast<int *>(s_dw + ncb);                     // [ncb]
 
@@ -157,7 +160,7 @@ degridder_sep_kernel(const KernelArgs a, const int tmem_cols, int *__restrict__ 
     }
     __syncthreads();
     if (tid == 0) {
-      for (int i = 1; i < 8; i++) wmax = fmaxf(wmax, s_red[i]);
+      for (int i = 1; i < NW; i++) wmax = fmaxf(wmax, s_red[i]);
       float kmax = 0.f;
       for (int c = 0; c < C; c++) kmax = fmaxf(kmax, fabsf(s_wn[c]));
       const double l0 = (0.5 - (N / 2)) * (double)a.image_size / (double)N;
@@ -166,12 +169,12 @@ degridder_sep_kernel(const KernelArgs a, const int tmem_cols, int *__restrict__ 
       const double r = s2 > 1.0 ? 1.0 : fabs(s2 / (1.0 + sqrt(1.0 - s2)) - 2.0 * fn);
       const double gmax = (double)fabsf(ctx.w_offset) + (double)wmax * (double)kmax;
       const bool sep = gmax * r <= (double)SEP_PHASE_TOL && isfinite(gmax);
-      s_red[12] = sep ? 1.f : 0.f;
+      s_red[18] = sep ? 1.f : 0.f;
       if (!sep) todo[1 + atomicAdd(&todo[0], 1)] = s_local;   // work list of the per-pixel kernel
     }
     __syncthreads();
   }
-  if (s_red[12] == 0.f) return;          // the per-pixel kernel behind this launch takes the subgrid
+  if (s_red[18] == 0.f) return;          // the per-pixel kernel behind this launch takes the subgrid
   if (nblk == 0) return;
 
   if (KCp != KC) {                       // the K padding: zero in A and B (never written again)
@@ -202,7 +205,7 @@ degridder_sep_kernel(const KernelArgs a, const int tmem_cols, int *__restrict__ 
     off_x[xi] = __fmaf_rn(ctx.w_offset, n_x[xi], __fmul_rn(ctx.u_offset, l[xi]));
   }
   float2 *g_out = const_cast<float2 *>(a.visibilities) + (size_t)ctx.time_offset * C * NR_POL;
-  const int q4 = warp & 3, upper = warp >> 2;
+  const int q4 = warp & 3, part = warp >> 2;
   const int step_t = 16 / ncb, step_cb = 16 - step_t * ncb;
   const size_t plane = (size_t)N * N;
   const size_t at1 = ((size_t)ctx.aterm_index * a.nr_stations + ctx.station1) * plane;
@@ -230,14 +233,14 @@ degridder_sep_kernel(const KernelArgs a, const int tmem_cols, int *__restrict__ 
       if (lane == 0) s_red[warp] = amax;
       __syncthreads();
       if (tid == 0) {
-        for (int i = 1; i < 8; i++) amax = fmaxf(amax, s_red[i]);
+        for (int i = 1; i < NW; i++) amax = fmaxf(amax, s_red[i]);
         const unsigned eb = (__float_as_uint(amax) >> 23) & 0xffu;
         const bool ok = eb >= 14u && eb <= 253u;
-        s_red[10] = ok ? __uint_as_float((267u - eb) << 23) : 1.f;           // 2^(13 - E)
-        s_red[11] = ok ? __uint_as_float((eb - 13u) << 23) : 1.f;            // 2^(E - 13)
+        s_red[16] = ok ? __uint_as_float((267u - eb) << 23) : 1.f;           // 2^(13 - E)
+        s_red[17] = ok ? __uint_as_float((eb - 13u) << 23) : 1.f;            // 2^(E - 13)
       }
       __syncthreads();
-      const float scale = s_red[10];
+      const float scale = s_red[16];
       for (int q = tid; q < npix; q += DS_THREADS) {
         const int y = q / N, x = q - y * N;
         const float4 v01 = sT[2 * q], v23 = sT[2 * q + 1];
@@ -266,19 +269,20 @@ degridder_sep_kernel(const KernelArgs a, const int tmem_cols, int *__restrict__ 
         }
       }
     }
-    const float unscale = s_red[11];
+    const float unscale = s_red[17];
     // instruction descriptor: D = F32, A = B = F16, K-major, N = 8 ny, M = 128
     const unsigned idesc = (1u << 4) | (((unsigned)ncols >> 3) << 17) | ((128u >> 4) << 24);
-    // the rows y of this warp in the sum over the rows: warps 0-3 the first groups of 4, warps 4-7 the rest
-    const int ng = ny >> 2, g_lo = upper ? (ng + 1) >> 1 : 0, g_hi = upper ? ng : (ng + 1) >> 1;
+    // the rows y of this warp in the sum over the rows: a quadrant's NP warps each take a share of the groups of 4
+    const int ng = ny >> 2;
+    const int g_lo = NP == 2 ? (part ? (ng + 1) >> 1 : 0) : (part * ng) / NP, g_hi = NP == 2 ? (part ? ng : (ng + 1) >> 1) : ((part + 1) * ng) / NP;
 
     // (timestep, block) of the warp's first block of the tile, stepped by 16 blocks per tile
-    int pt = (warp * 2) / ncb, pcb = warp * 2 - pt * ncb;
+    int pt = (warp * BPW) / ncb, pcb = warp * BPW - pt * ncb;
     for (int tile = 0; tile < ntiles; tile++, it++) {
-      // ---- A rows of blocks 2 warp, 2 warp + 1 of the tile: X_v(x) for the block's 8 channels, hi + lo
+      // ---- A rows of this warp's BPW blocks of the tile: X_v(x) for the block's 8 channels, hi + lo
 #pragma unroll
-      for (int bi = 0; bi < 2; bi++) {   // both blocks unrolled: two independent chains in flight
-        const int blk = tile * 16 + warp * 2 + bi;
+      for (int bi = 0; bi < BPW; bi++) {   // unrolled: independent chains in flight
+        const int blk = tile * 16 + warp * BPW + bi;
         int t = pt, cb = pcb + bi;
         if (cb >= ncb) { cb -= ncb; t++; }
         const bool live = blk < nblk;
@@ -314,7 +318,7 @@ degridder_sep_kernel(const KernelArgs a, const int tmem_cols, int *__restrict__ 
           }
           const int x = lane + 32 * xi;
           if (x < N) {
-            unsigned char *row = sA + (x >> 2) * DS_A_CH + (x & 3) * 4 + ((warp * 2 + bi) * 8) * 16;
+            unsigned char *row = sA + (x >> 2) * DS_A_CH + (x & 3) * 4 + ((warp * BPW + bi) * 8) * 16;
 #pragma unroll
             for (int i = 0; i < 8; i++) {
               *reinterpret_cast<unsigned *>(row + i * 16) = hi[i];
@@ -384,19 +388,24 @@ degridder_sep_kernel(const KernelArgs a, const int tmem_cols, int *__restrict__ 
         float2 acc[NR_POL];
 #pragma unroll
         for (int p = 0; p < NR_POL; p++) acc[p] = make_float2(ar[p].x - ai[p].y, ar[p].y + ai[p].x);
-        if (upper) {
-          sPart[2 * r_tile] = make_float4(acc[0].x, acc[0].y, acc[1].x, acc[1].y);
-          sPart[2 * r_tile + 1] = make_float4(acc[2].x, acc[2].y, acc[3].x, acc[3].y);
+        if (part) {
+          sPart[(part - 1) * 256 + 2 * r_tile] = make_float4(acc[0].x, acc[0].y, acc[1].x, acc[1].y);
+          sPart[(part - 1) * 256 + 2 * r_tile + 1] = make_float4(acc[2].x, acc[2].y, acc[3].x, acc[3].y);
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();                  // accumulator and A buffer are free for the next tile; the upper halves are in
-        if (!upper && valid) {
-          const float4 p0 = sPart[2 * r_tile], p1 = sPart[2 * r_tile + 1];
+        if (!part && valid) {
+#pragma unroll
+          for (int hh = 0; hh < NP - 1; hh++) {     // the other parts' sums, in order
+            const float4 p0 = sPart[hh * 256 + 2 * r_tile], p1 = sPart[hh * 256 + 2 * r_tile + 1];
+            acc[0] = make_float2(acc[0].x + p0.x, acc[0].y + p0.y);
+            acc[1] = make_float2(acc[1].x + p0.z, acc[1].y + p0.w);
+            acc[2] = make_float2(acc[2].x + p1.x, acc[2].y + p1.y);
+            acc[3] = make_float2(acc[3].x + p1.z, acc[3].y + p1.w);
+          }
           float4 *o = reinterpret_cast<float4 *>(g_out + ((size_t)t * C + c) * NR_POL);
-          float4 o0 = make_float4((acc[0].x + p0.x) * unscale, (acc[0].y + p0.y) * unscale, (acc[1].x + p0.z) * unscale,
-                                  (acc[1].y + p0.w) * unscale);
-          float4 o1 = make_float4((acc[2].x + p1.x) * unscale, (acc[2].y + p1.y) * unscale, (acc[3].x + p1.z) * unscale,
-                                  (acc[3].y + p1.w) * unscale);
+          float4 o0 = make_float4(acc[0].x * unscale, acc[0].y * unscale, acc[1].x * unscale, acc[1].y * unscale);
+          float4 o1 = make_float4(acc[2].x * unscale, acc[2].y * unscale, acc[3].x * unscale, acc[3].y * unscale);
           if (slab > 0) {                 // the earlier slabs' partial visibility: written by this very thread
             const float4 e0 = o[0], e1 = o[1];
             o0 = make_float4(e0.x + o0.x, e0.y + o0.y, e0.z + o0.z, e0.w + o0.w);
@@ -1008,13 +1017,14 @@ cudaError_t launch_degridder_sep(const KernelArgs &a, int *d_todo, cudaStream_t 
   }
   int tmem_cols = 32;
   while (tmem_cols < ncols) tmem_cols *= 2;
-  const size_t smem = (size_t)2 * KCp * (ncols * 16 + 16) + (size_t)2 * KCp * DS_A_CH + (size_t)N * 16 + 256 * 16 + DS_UVW_STAGED * 12 + 8 + 8 + 64 +
-                      (size_t)ncb * 10 * 4;
+  const int threads = N > 32 ? 512 : 256;
+  const size_t smem = (size_t)2 * KCp * (ncols * 16 + 16) + (size_t)2 * KCp * DS_A_CH + (size_t)N * 16 + (size_t)(threads / 128 - 1) * 256 * 16 +
+                      DS_UVW_STAGED * 12 + 8 + 8 + 96 + (size_t)ncb * 10 * 4;
   if (smem > 227 * 1024) return cudaErrorInvalidValue;
   auto kernel = N > 32 ? degridder_sep_kernel<2> : degridder_sep_kernel<1>;
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  kernel<<<dim3((unsigned)a.nr_subgrids), dim3(DS_THREADS), smem, stream>>>(a, tmem_cols, d_todo);
+  kernel<<<dim3((unsigned)a.nr_subgrids), dim3(threads), smem, stream>>>(a, tmem_cols, d_todo);
   return cudaGetLastError();
 }
 
