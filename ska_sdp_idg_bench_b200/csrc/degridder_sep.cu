@@ -677,13 +677,18 @@ degridder_sep_pipe_kernel(const KernelArgs a, int *__restrict__ todo) {
         auto uvw_at = [&](int i) { return staged ? uvw[i] : __ldg(&uvw[i]); };
         const float4 *geo_b = sGeo + bb * N;
         float2 *g_out = const_cast<float2 *>(a.visibilities) + (size_t)m.time_offset * C * NR_POL;
+        // (timestep, block) of this thread's row of the tile, stepped by 16 blocks per tile like the producers'
+        const int c_step_t = 16 / ncb, c_step_cb = 16 - c_step_t * ncb;
+        int ct = (r_tile >> 3) / ncb, ccb = (r_tile >> 3) - ct * ncb;
         for (int tile = 0; tile < ntiles; tile++, it++) {
           const int buf = it & 1;
-          if (DP_CGROUPS == 2 && buf != cg) continue;
-          const unsigned part_full = bar_at(PART_FULL, 0) + 8u * (buf * 4 + q4), part_empty = bar_at(PART_EMPTY, 0) + 8u * (buf * 4 + q4);
           const int blk = tile * 16 + (r_tile >> 3);
           const bool in_range = blk < nblk;
-          const int t = in_range ? blk / ncb : 0, cb = in_range ? blk - t * ncb : 0;
+          const int t = in_range ? ct : 0, cb = in_range ? ccb : 0;
+          ct += c_step_t; ccb += c_step_cb;
+          if (ccb >= ncb) { ccb -= ncb; ct++; }
+          if (DP_CGROUPS == 2 && buf != cg) continue;
+          const unsigned part_full = bar_at(PART_FULL, 0) + 8u * (buf * 4 + q4), part_empty = bar_at(PART_EMPTY, 0) + 8u * (buf * 4 + q4);
           const int c = cb * 8 + (r_tile & 7);
           const bool valid = in_range && c < C;
           const float k = s_wn[c];
