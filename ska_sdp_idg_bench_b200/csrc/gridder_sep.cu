@@ -52,6 +52,9 @@ constexpr float SEP_PHASE_TOL = 1e-4f;           // largest dropped phase |gamma
 // pixel sums ALL stay below GS_CANCEL E_p in every polarisation is counted in cancel[subgrid], and a subgrid all of
 // whose tiles are is redone by the FP32 kernel launched behind this one.  Unflagged: max error <~ 7.5e-4 / GS_CANCEL.
 constexpr float GS_CANCEL = 1.0f;
+#ifndef GS_ISSUER_SLEEP_NS
+#define GS_ISSUER_SLEEP_NS 300
+#endif
 
 __device__ __forceinline__ unsigned pack_h2(const float lo, const float hi) {
   const __half2 h = __floats2half2_rn(lo, hi);
@@ -367,20 +370,40 @@ gridder_sep_kernel(const KernelArgs a, const int ytiles, const int xtiles, const
     const unsigned idesc = (1u << 4) | (((unsigned)(4 * XT) >> 3) << 17) | ((128u >> 4) << 24);
     const unsigned full_u = smem_u32(full), empty_u = smem_u32(empty), done_u = smem_u32(done);
     const unsigned stage_u = smem_u32(sStage);
-    int pw = 0, j = 0;                         // producer warp and its stage count for flat stage sidx
-    for (int sidx = 0; sidx < nstages; sidx++) {
-      const int buf = j & 1;
-      mbar_wait_sleep(full_u + (pw * 2 + buf) * 8, (j >> 1) & 1);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      if (elect_one()) {
-        const unsigned w_addr = stage_u + pw * warp_bytes;
-        umma_f16(tmem_base, smem_desc(w_addr + buf * GS_A_BYTES, 128 * 16, 128), smem_desc(w_addr + 2 * GS_A_BYTES, 4 * XT * 16, 128), idesc,
-                 sidx > 0 ? 1u : 0u);
-        umma_commit_u(empty_u + (pw * 2 + buf) * 8);
-        if (sidx == nstages - 1) umma_commit_u(done_u);
+    // flat stage sidx = j GS_W + pw (producer warp pw's j-th stage, buffer j & 1).  Unrolled over the 2 GS_W (pw, buffer)
+    // combinations so that barrier addresses and operand descriptors are loop invariants (they were ~20 uniform
+    // instructions per stage), and the warp sleeps longer between polls: a producer needs ~3000 clocks for a stage and has
+    // two stage buffers, so an MMA that starts a few hundred clocks late delays nobody (was: 9 polls of 6 instructions
+    // per stage, a tenth of the kernel's instructions)
+    for (int base = 0; base < nstages; base += 2 * GS_W) {
+      const unsigned parity = (unsigned)(base / (2 * GS_W)) & 1u;
+#pragma unroll
+      for (int u = 0; u < 2 * GS_W; u++) {
+        const int sidx = base + u;
+        if (sidx >= nstages) break;
+        const int pw = u % GS_W, buf = u / GS_W;
+        {
+          const unsigned bar = full_u + (pw * 2 + buf) * 8;
+          unsigned ok;
+          asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                       : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+          for (int spin = 0; !ok; spin++) {
+            __nanosleep(GS_ISSUER_SLEEP_NS);
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                         : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+            if (spin > (1 << 22)) __trap();   // a lost arrival must fail loudly, not hang the GPU
+          }
+        }
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (elect_one()) {
+          const unsigned w_addr = stage_u + pw * warp_bytes;
+          umma_f16(tmem_base, smem_desc(w_addr + buf * GS_A_BYTES, 128 * 16, 128), smem_desc(w_addr + 2 * GS_A_BYTES, 4 * XT * 16, 128), idesc,
+                   sidx > 0 ? 1u : 0u);
+          umma_commit_u(empty_u + (pw * 2 + buf) * 8);
+          if (sidx == nstages - 1) umma_commit_u(done_u);
+        }
+        __syncwarp();
       }
-      __syncwarp();
-      if (++pw == GS_W) { pw = 0; j++; }
     }
     (void)b_bytes;
   }

@@ -78,6 +78,9 @@ def main():
             r.update(kernel=kind, variant=v, resolved=idg.resolve_variant(N, C, idg.SINCOS_FAST, v, gridder=kind == "gridder"),
                      mvis_per_s=mvis / (r["median_ms"] * 1e-3), w_sigma=a.w_sigma, subgrids=S, channels=C, subgrid=N)
             torch.cuda.synchronize()
+            # bit-level fingerprint of the whole output: equal across builds <=> the same bits
+            bits = torch.view_as_real(out).contiguous().view(torch.int32).to(torch.int64)
+            r["fingerprint"] = int((bits * (torch.arange(bits.numel(), device=bits.device).view(bits.shape) % 1000003 + 1)).sum().item() & 0xFFFFFFFFFFFF)
             o = out[: 64].clone() if kind == "gridder" else out[: 64 * 128].clone()
             if kind in ref:   # agreement with the first variant listed (different kernels, same answer)
                 d = (o - ref[kind]).abs().max().item() / ref[kind].abs().max().item()
