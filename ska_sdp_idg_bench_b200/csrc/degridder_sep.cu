@@ -422,35 +422,31 @@ degridder_sep_kernel(const KernelArgs a, const int tmem_cols, int *__restrict__ 
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// The same arithmetic as a warp-specialised, persistent pipeline: ONE CTA per SM that loops over subgrids, 28 warps.
+// The same arithmetic as a warp-specialised, persistent pipeline: ONE CTA per SM that loops over subgrids, 20 warps.
 //   warps  0- 7  producers: the A rows (column phasors X, fp16 hi + lo) of tile i + 1 / i + 2 into one of two A buffers
-//   warps  8-23  consumers: the sum over the rows y of tile i out of one of two accumulators (all 512 TMEM columns);
-//                two groups of 8 warps, one per accumulator; in a group two warps per TMEM lane quadrant, half of the
-//                rows each
-//   warp   24    issuer: the tile's 12 MMAs as soon as its A buffer is full and its accumulator has been drained
-//   warps 25-27  setup: the NEXT subgrid's separability check, B operand (P' in fp16 hi + lo, one of two B buffers),
+//   warps  8-15  consumers: the sum over the rows y of tile i out of one of two accumulators (all 512 TMEM columns);
+//                two warps per TMEM lane quadrant, half of the rows each
+//   warp   16    issuer: the tile's 12 MMAs as soon as its A buffer is full and its accumulator has been drained
+//   warps 17-19  setup: the NEXT subgrid's separability check, B operand (P' in fp16 hi + lo, one of two B buffers),
 //                staged uvw and row geometry, while the others are in the tile loop of the current subgrid
 // so that the tensor pipe, the producers' dependency chains and the consumers' TMEM reads overlap inside one CTA
 // instead of across two (the kernel above: a tile's phases one after the other, 2 CTAs per SM), and the per-subgrid
 // prologue (32 KB of pixels + A-terms) is hidden behind the previous subgrid.  Hand-offs are mbarriers only:
 //   b_full[2]  (3 setup warps)   -> everyone     B buffer, meta, geometry, uvw of subgrid j are ready
-//   b_empty[2] (25 warps)        -> setup        producers, consumers and the issuer are done with subgrid j's buffers
+//   b_empty[2] (17 warps)        -> setup        producers, consumers and the issuer are done with subgrid j's buffers
 //   a_full[2]  (8 producers)     -> issuer
 //   mma_done[2] (tcgen05.commit) -> consumers (accumulator full) and producers (A buffer free)
-//   d_empty[2] (8 consumers of the accumulator's group) -> issuer       accumulator drained
+//   d_empty[2] (8 consumers)     -> issuer       accumulator drained
 //   part_full[2][4] (upper consumer warp of a quadrant) -> its lower warp (the two halves of the sum over the rows meet)
 //   part_empty[2][4] (lower warp of a quadrant) -> its upper warp (the partial sums of tile it - 2 have been read)
 // Tiles are counted over the whole run of a CTA (`it`), buffer = it & 1, phase = (it >> 1) & 1.  Results are bit-identical
 // to the kernel above (same MMAs in the same order, same split of the sum over the rows).
-// Consumer groups of 8 warps (2 per TMEM lane quadrant, half of the rows y each).  With 2 groups, group b takes the tiles
-// of accumulator b, so that a group has two tile periods for its tile: a consumer warp's chain through a tile (wake-up,
-// TMEM loads, 16 row phasors, partial sums through shared memory, store) is ~2000 clocks however few instructions it is
-// (tools/pipe_trace.py), longer than the tile's MMAs (1536)
-#ifndef DP_CGROUPS
-#define DP_CGROUPS 1     // measured: 4.41 ms with one group, 4.45 ms with two (the dispatch ports are what is short, not warps)
-#endif
-constexpr int DP_CONSUMERS = 8 * DP_CGROUPS;
-constexpr int DP_WARPS = 8 + DP_CONSUMERS + 1 + 3, DP_THREADS = DP_WARPS * 32;   // 28 warps of 72 registers (or 20 of 96)
+// 8 consumer warps: 2 per TMEM lane quadrant, half of the rows y each.  Tried and dropped: 16 consumer warps,
+// either four per quadrant on one tile or two groups of 8 alternating accumulators (4.74 / 4.45 against 4.41 ms: the
+// dispatch ports are what is short, not warps), and making a group's row phasors ahead of its TMEM load's wait (4.61
+// against 4.43 ms: the extra live registers cost more than the overlap buys).
+constexpr int DP_CONSUMERS = 8;
+constexpr int DP_WARPS = 8 + DP_CONSUMERS + 1 + 3, DP_THREADS = DP_WARPS * 32;   // 20 warps of 96 registers
 constexpr int DP_ISSUER = 8 + DP_CONSUMERS, DP_SETUP0 = DP_ISSUER + 1, DP_SETUP_WARPS = DP_WARPS - DP_SETUP0, DP_SETUP_THREADS = DP_SETUP_WARPS * 32;
 constexpr int DP_UVW_STAGED = 256;
 
@@ -464,9 +460,6 @@ constexpr int DP_UVW_STAGED = 256;
 #endif
 #ifndef DP_WAIT_ISSUE
 #define DP_WAIT_ISSUE 1
-#endif
-#ifndef DP_CONS_PREFETCH     // 1: a group's row phasors are made ahead of its TMEM load's wait (the first group's before the MMA wait);
-#define DP_CONS_PREFETCH 0   //    measured slower (4.61 vs 4.43 ms): the extra live registers cost more than the overlap buys
 #endif
 // DP_TRACE builds (tools/build_ab.sh + tools/pipe_trace.py, never shipped): CTA 0 records clock64() at the hand-offs of
 // the tiles of its subgrids DP_TRACE_J0 .. DP_TRACE_J0 + 3 (steady state), one row per event
@@ -659,9 +652,8 @@ degridder_sep_pipe_kernel(const KernelArgs a, int *__restrict__ todo) {
     }
   } else if (warp < DP_ISSUER) {
     // ========================================================= consumers: thread = visibility (TMEM lane = row of the tile)
-    // group cg takes the tiles of accumulator cg (every tile with one group); in a group, quadrant q4's two warps (h = 0, 1)
-    // each sum half of the row groups, and warp 1 hands its sums to warp 0 through sPart
-    const int q4 = warp & 3, h = ((warp - 8) >> 2) & 1, cg = (warp - 8) >> 3;
+    // quadrant q4's two warps (h = 0, 1) each sum half of the row groups, and warp 1 hands its sums to warp 0 through sPart
+    const int q4 = warp & 3, h = (warp - 8) >> 2;
     const int ng = N >> 2, g_lo = h ? (ng + 1) >> 1 : 0, g_hi = h ? ng : (ng + 1) >> 1;
     const int r_tile = q4 * 32 + lane;
     int it = 0;
@@ -687,7 +679,6 @@ degridder_sep_pipe_kernel(const KernelArgs a, int *__restrict__ todo) {
           const int t = in_range ? ct : 0, cb = in_range ? ccb : 0;
           ct += c_step_t; ccb += c_step_cb;
           if (ccb >= ncb) { ccb -= ncb; ct++; }
-          if (DP_CGROUPS == 2 && buf != cg) continue;
           const unsigned part_full = bar_at(PART_FULL, 0) + 8u * (buf * 4 + q4), part_empty = bar_at(PART_EMPTY, 0) + 8u * (buf * 4 + q4);
           const int c = cb * 8 + (r_tile & 7);
           const bool valid = in_range && c < C;
@@ -698,8 +689,7 @@ degridder_sep_pipe_kernel(const KernelArgs a, int *__restrict__ todo) {
           float2 ar[NR_POL], ai[NR_POL];
 #pragma unroll
           for (int p = 0; p < NR_POL; p++) ar[p] = ai[p] = make_float2(0.f, 0.f);
-          // the row phasors Y_v(y) of a group of 4 rows do not depend on the MMAs: the first group's are made before the
-          // wait, the next group's behind the TMEM load of the current one
+          // the row phasors Y_v(y) of a group of 4 rows
           auto make_ph = [&](const int g, float2 *ph) {
 #pragma unroll
             for (int yy = 0; yy < 4; yy++) {
@@ -708,8 +698,6 @@ degridder_sep_pipe_kernel(const KernelArgs a, int *__restrict__ todo) {
               ph[yy] = phasor<IDGB200_SINCOS_FAST>(__fmaf_rn(idx, k, -geo.z));
             }
           };
-          float2 ph[4];
-          if (DP_CONS_PREFETCH && g_lo < g_hi) make_ph(g_lo, ph);
           dp_wait<DP_WAIT_CONS>(bar_at(MMA_DONE, buf), (it >> 1) & 1);
           DP_MARK(16 + 2 * (warp - 8), j, tile, lane == 0);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -719,12 +707,8 @@ degridder_sep_pipe_kernel(const KernelArgs a, int *__restrict__ todo) {
             const unsigned taddr = tmem_base + (unsigned)(buf * 256) + ((unsigned)(q4 * 32) << 16) + g * 32;
             tmem_ld16(taddr, r);
             tmem_ld16(taddr + 16, r + 16);
-            float2 phn[4];
-            if (DP_CONS_PREFETCH) {
-              if (g + 1 < g_hi) make_ph(g + 1, phn);
-            } else {
-              make_ph(g, ph);
-            }
+            float2 ph[4];
+            make_ph(g, ph);              // independent of the loads: overlaps their latency
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
             for (int yy = 0; yy < 4; yy++) {
@@ -734,10 +718,6 @@ degridder_sep_pipe_kernel(const KernelArgs a, int *__restrict__ todo) {
                 ar[p] = ffma2(make_float2(qr, qr), ph[yy], ar[p]);
                 ai[p] = ffma2(make_float2(qi, qi), ph[yy], ai[p]);
               }
-            }
-            if (DP_CONS_PREFETCH) {
-#pragma unroll
-              for (int yy = 0; yy < 4; yy++) ph[yy] = phn[yy];
             }
           }
           // the accumulator has been read (its values are in registers): the issuer may overwrite it
