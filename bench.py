@@ -689,7 +689,8 @@ def run_ours(args) -> None:
                                           "(A = fp16(Y vis), B = fp16 hi + lo column phasors), per-subgrid separability check on the "
                                           "device, per-pixel kernel behind it" if g_variant == 30 else f"variant {g_variant}",
                            degridder_kernel="degridder_sep.cu: row-column form, tcgen05 GEMM over the columns (fp16 hi + lo both "
-                                            "operands), the sum over the rows on the CUDA cores out of TMEM" if d_variant == 30
+                                            "operands), the sum over the rows on the CUDA cores out of TMEM; persistent warp-specialised pipeline, one CTA "
+                                            "per SM (producers / issuer / consumers / next-subgrid setup)" if d_variant == 30
                                             else f"variant {d_variant}"),
             "tflops": top["tflops"], "step_ms": top["step_ms"], "timed_steps": top["timed_steps"], "rounds": top["rounds"],
             "timed_region_s": top["timed_region_s"], "warmup_steps": top["warmup_steps"],
