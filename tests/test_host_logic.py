@@ -213,8 +213,9 @@ def test_default_variant_selection():
     assert idg.resolve_variant(32, 16, idg.SINCOS_FAST, variant=24) == 24
     assert idg.resolve_variant(32, 16, idg.SINCOS_FAST, gridder=False) == 30
     assert idg.resolve_variant(8, 16, idg.SINCOS_FAST, gridder=False) == 30
-    assert idg.resolve_variant(64, 16, idg.SINCOS_FAST, gridder=False) == 24   # beyond 32 x 32: two tiles per warp
-    assert idg.resolve_variant(64, 12, idg.SINCOS_FAST, gridder=False) == 22   # quads of 4 channels
+    assert idg.resolve_variant(64, 16, idg.SINCOS_FAST, gridder=False) == 30   # up to 64 x 64: slabs of 32 rows
+    assert idg.resolve_variant(72, 16, idg.SINCOS_FAST, gridder=False) == 24   # beyond 64 x 64: two tiles per warp
+    assert idg.resolve_variant(72, 12, idg.SINCOS_FAST, gridder=False) == 22   # quads of 4 channels
     assert idg.resolve_variant(18, 1, idg.SINCOS_FAST, gridder=False) == 4     # 1 of 4 channels
     assert idg.resolve_variant(32, 16, idg.SINCOS_ACCURATE, gridder=False) == 4
 
