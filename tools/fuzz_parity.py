@@ -24,6 +24,8 @@ for case in range(n_cases):
     C = int(rng.choice([4, 8, 12, 16, 24, 32, 33, 64]))
     T = int(rng.integers(1, 70))
     S = int(rng.integers(1, 6))
+    if N <= 32 and rng.integers(0, 4) == 0:      # more subgrids than SMs: the persistent degridder's CTAs walk through several
+        S, T = int(rng.integers(150, 500)), min(T, 24)
     linear = bool(rng.integers(0, 2))
     planar = bool(rng.integers(0, 2))     # w = 0 everywhere: the pixel-pair folded paths
     p = random_problem(int(rng.integers(1 << 30)), subgrid_size=N, nr_channels=C, max_timesteps=T, nr_subgrids=S,
