@@ -17,12 +17,15 @@
 // sincos per (visibility, row y), four complex multiply-adds, then one coalesced 32-byte store per visibility:
 // every visibility of the subgrid's time range is written exactly once.
 //
-// CTA = one subgrid, 8 warps, 2 CTAs per SM (256 TMEM columns each).  The rows of the GEMM are enumerated in
-// blocks of 8 channels (row = (timestep * blocks + block) * 8 + channel, channels padded to blocks), 16 blocks
-// per tile: warp w makes the A rows of blocks 2 w, 2 w + 1 (lane = column x; the 8 phasors of a block unrolled),
-// one thread issues the tile's MMAs, and when they have completed warps q and q + 4 (the two warps that may read
-// TMEM lane quadrant q) each sum half of the rows y for their 32 visibilities; the halves meet in shared memory.
-// While one CTA waits for its MMAs the other one computes.
+// Two kernels with this arithmetic (bit-identical results):
+//   degridder_sep_kernel       CTA = one subgrid, a tile's phases one after the other (A rows, MMAs, sum over the rows);
+//                              up to 32 x 32 pixels 8 warps and 2 CTAs per SM; above, slabs of 32 rows and 16 warps
+//   degridder_sep_pipe_kernel  one persistent CTA per SM, warp-specialised (producers / issuer / consumers / setup of the
+//                              next subgrid), two A buffers, two accumulators, two B buffers: the default up to 32 x 32
+// The rows of the GEMM are enumerated in blocks of 8 channels (row = (timestep * blocks + block) * 8 + channel, channels
+// padded to blocks), 16 blocks per tile of 128 visibilities; a warp makes the A rows of whole blocks (lane = column x; the
+// 8 phasors of a block unrolled), one thread issues the tile's MMAs, and the two (four) warps that may read TMEM lane
+// quadrant q each sum their share of the rows y for its 32 visibilities; the shares meet in shared memory.
 #include <cuda_fp16.h>
 
 #include "common.cuh"
