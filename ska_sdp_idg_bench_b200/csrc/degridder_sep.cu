@@ -594,8 +594,8 @@ degridder_sep_pipe_kernel(const KernelArgs a, int *__restrict__ todo) {
         const int nt = m.nt, nblk = nt * ncb, ntiles = (nblk + 15) >> 4;
         const float off_x = __fmaf_rn(m.w_offset, n_x, __fmul_rn(m.u_offset, l));
         const bool staged = nt <= DP_UVW_STAGED;
-        const float *uvw = staged ? s_uvw + bb * DP_UVW_STAGED * 3 : reinterpret_cast<const float *>(a.uvw) + (size_t)m.time_offset * 3;
-        auto uvw_at = [&](int i) { return staged ? uvw[i] : __ldg(&uvw[i]); };
+        const float *uvw_s = s_uvw + bb * DP_UVW_STAGED * 3, *uvw_g = reinterpret_cast<const float *>(a.uvw) + (size_t)m.time_offset * 3;
+        auto uvw_at = [&](int i) { return staged ? uvw_s[i] : __ldg(&uvw_g[i]); };
         int pt = (warp * 2) / ncb, pcb = warp * 2 - pt * ncb;
         for (int tile = 0; tile < ntiles; tile++, it++) {
           const int buf = it & 1;
@@ -606,7 +606,7 @@ degridder_sep_pipe_kernel(const KernelArgs a, int *__restrict__ todo) {
           for (int bi = 0; bi < 2; bi++) {
             if ((IDGB200_ABLATE & 8) && !ablate_never()) continue;      // ablation: no A rows
             const int blk = tile * 16 + warp * 2 + bi;
-            unsigned hi[8], lo[8];
+            unsigned char *row = a_col + ((warp * 2 + bi) * 8) * 16;
             if (blk < nblk) {
               int t = pt, cb = pcb + bi;
               if (cb >= ncb) { cb -= ncb; t++; }
@@ -624,21 +624,20 @@ degridder_sep_pipe_kernel(const KernelArgs a, int *__restrict__ todo) {
 #pragma unroll
                 for (int i = 0; i < 8; i++) ph[i] = phasor<IDGB200_SINCOS_FAST>(__fmaf_rn(idx, wn8[i], -off_x));
               }
+              if (lane < N) {
 #pragma unroll
-              for (int i = 0; i < 8; i++) {
-                hi[i] = pack_h2(ph[i].x, ph[i].y);
-                lo[i] = pack_h2(residual_h(ph[i].x, (unsigned short)(hi[i] & 0xffffu)), residual_h(ph[i].y, (unsigned short)(hi[i] >> 16)));
+                for (int i = 0; i < 8; i++) {
+                  const unsigned hi = pack_h2(ph[i].x, ph[i].y);
+                  *reinterpret_cast<unsigned *>(row + i * 16) = hi;
+                  *reinterpret_cast<unsigned *>(row + i * 16 + KCp * DS_A_CH) =
+                      pack_h2(residual_h(ph[i].x, (unsigned short)(hi & 0xffffu)), residual_h(ph[i].y, (unsigned short)(hi >> 16)));
+                }
               }
-            } else {
-#pragma unroll
-              for (int i = 0; i < 8; i++) hi[i] = lo[i] = 0u;
-            }
-            if (lane < N) {
-              unsigned char *row = a_col + ((warp * 2 + bi) * 8) * 16;
+            } else if (lane < N) {     // rows beyond the subgrid's last block (the last tile only): zeros
 #pragma unroll
               for (int i = 0; i < 8; i++) {
-                *reinterpret_cast<unsigned *>(row + i * 16) = hi[i];
-                *reinterpret_cast<unsigned *>(row + i * 16 + KCp * DS_A_CH) = lo[i];
+                *reinterpret_cast<unsigned *>(row + i * 16) = 0u;
+                *reinterpret_cast<unsigned *>(row + i * 16 + KCp * DS_A_CH) = 0u;
               }
             }
           }
@@ -668,8 +667,8 @@ degridder_sep_pipe_kernel(const KernelArgs a, int *__restrict__ todo) {
         const int nt = m.nt, nblk = nt * ncb, ntiles = (nblk + 15) >> 4;
         const float unscale = m.unscale;
         const bool staged = nt <= DP_UVW_STAGED;
-        const float *uvw = staged ? s_uvw + bb * DP_UVW_STAGED * 3 : reinterpret_cast<const float *>(a.uvw) + (size_t)m.time_offset * 3;
-        auto uvw_at = [&](int i) { return staged ? uvw[i] : __ldg(&uvw[i]); };
+        const float *uvw_s = s_uvw + bb * DP_UVW_STAGED * 3, *uvw_g = reinterpret_cast<const float *>(a.uvw) + (size_t)m.time_offset * 3;
+        auto uvw_at = [&](int i) { return staged ? uvw_s[i] : __ldg(&uvw_g[i]); };
         const float4 *geo_b = sGeo + bb * N;
         float2 *g_out = const_cast<float2 *>(a.visibilities) + (size_t)m.time_offset * C * NR_POL;
         // (timestep, block) of this thread's row of the tile, stepped by 16 blocks per tile like the producers'
