@@ -103,6 +103,28 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
+    def mark(self) -> int:
+        """index of the next sample: brackets a timed region"""
+        return len(self.lines)
+
+    def between(self, i0: int, i1: int):
+        """SM clock (median / min / max) and board power (median) of the under-load samples taken between two marks
+        (None without samples): the clock one kernel's region ran at - the power cap bites the tensor-core kernels
+        harder than the FP32 ones"""
+        sm, pw = [], []
+        for ln in self.lines[i0:max(i1, i0 + 1) + 1]:      # + the sample in flight when the region ended
+            f = [x.strip() for x in ln.split(",")]
+            try:
+                sm.append(float(f[1])); pw.append(float(f[3]))
+            except (ValueError, IndexError):
+                continue
+        if not sm:
+            return None
+        keep = [i for i, x in enumerate(sm) if x >= 0.5 * max(sm)]
+        hi = [sm[i] for i in keep]
+        return {"sm_mhz": statistics.median(hi), "sm_mhz_min": min(hi), "sm_mhz_max": max(hi),
+                "power_w": statistics.median(pw[i] for i in keep), "samples": len(hi)}
+
     def stop(self) -> dict:
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -387,6 +409,8 @@ def run_ours(args) -> None:
     def all_max(x: float) -> float:
         return reduce_max_time(x, dev)
 
+    sampler = None      # the clock sampler of the device-resident timings (set below; timed() brackets its region in it)
+
     def timed(step, steps, warmup, min_seconds=None, max_rounds=64, adaptive=True):
         """Warm-up: at least `warmup` steps, then on until two consecutive steps agree to 2 % (allocations,
         module loading and clock ramps stay out of the timed region).  Timed: rounds of EXACTLY `steps` steps,
@@ -411,6 +435,7 @@ def run_ours(args) -> None:
         rounds = int(all_max(float(rounds)))
         n = rounds * steps
         barrier()
+        c0 = sampler.mark() if sampler is not None else 0
         l0 = idg.launch_count()
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(n + 1)]
         ev[0].record()
@@ -418,9 +443,10 @@ def run_ours(args) -> None:
             step()
             ev[i + 1].record()
         barrier()
+        c1 = sampler.mark() if sampler is not None else 0
         per = sorted(ev[i].elapsed_time(ev[i + 1]) for i in range(n))
         sec = ev[0].elapsed_time(ev[n]) * 1e-3
-        return {"sec_per_step": all_max(sec) / n, "rounds": rounds, "timed_steps": n, "timed_region_s": sec,
+        return {"sec_per_step": all_max(sec) / n, "rounds": rounds, "timed_steps": n, "timed_region_s": sec, "clock_marks": (c0, c1),
                 "warmup_steps": n_warm, "launches_per_step": (idg.launch_count() - l0) / n,
                 "step_ms": {"min": per[0], "median": per[n // 2], "max": per[-1]}}
 
@@ -654,8 +680,13 @@ def run_ours(args) -> None:
             else:
                 r.update({"bound": "fp32" if variant in (10, 4) else "issue", "achieved": tf, "peak": p_fp32,
                           "unit": "TFLOP/s (reference flop model)", "frac": tf / p_fp32})
-            if clocks.get("sm_mhz"):
-                r["frac_at_measured_clock"] = r["frac"] * f_max / clocks["sm_mhz"]
+            ck = sampler.between(*t["clock_marks"]) if rank == 0 and "clock_marks" in t else None
+            mhz = (ck or {}).get("sm_mhz") or clocks.get("sm_mhz")
+            if mhz:     # the clock THIS kernel's region ran at (falls back to the whole run's median)
+                r["sm_mhz"] = mhz
+                if ck:
+                    r["clocks_in_region"] = ck
+                r["frac_at_measured_clock"] = r["frac"] * f_max / mhz
             return r
 
         def entry(t, kind, variant, what=None):

@@ -27,6 +27,7 @@
 // 8 phasors of a block unrolled), one thread issues the tile's MMAs, and the two (four) warps that may read TMEM lane
 // quadrant q each sum their share of the rows y for its 32 visibilities; the shares meet in shared memory.
 #include <cuda_fp16.h>
+#include <cuda_fp8.h>
 
 #include "common.cuh"
 #include "kernels.h"
@@ -50,6 +51,63 @@ __device__ __forceinline__ float residual_h(const float x, const unsigned short 
   float r;
   asm("fma.rn.f32.f16 %0, %1, %2, %3;" : "=f"(r) : "h"(h), "h"(minus_one), "f"(x));
   return r;
+}
+
+// The second word of an operand element.  DS_FP8_LO = 0: the fp16 rounding residuals (lo), and three fp16 products per K
+// step (hi hi, lo hi, hi lo).  DS_FP8_LO = 1 (default): the two cross products only have to be good to a few bits - they
+// are 2^-11 of the result - so they run as ONE kind::f8f6f4 MMA over four e4m3 values per element,
+//   A word = (lo8_c, lo8_s, hi8_c, hi8_s)   against   B word = (hi8_c, hi8_s, lo8_c, lo8_s)
+// with hi8 = e4m3(fp16 hi), lo8 = e4m3(x - fp16 hi): K = 32 e4m3 take the bytes and the clocks of K = 16 fp16, so a tile
+// is 8 MMAs instead of 12 (the kernel sits at the board's power cap and the tensor pipe is its largest consumer).  The
+// operands are scaled so that both parts sit in e4m3's range: A by 2^8 (|X| <= 1 -> hi8 <= 256 < 448, lo8 <= 2^-4 against
+// a subnormal step of 2^-9), B to [2^7, 2^8); an operand then keeps ~2^-17 of its largest value instead of fp16's 2^-12
+// (tools/sep_prototype.py --fp8: config 1 rel-RMS 1.5e-4 against 1.3e-4 for three fp16 products and 7.1e-4 for one).
+#ifndef DS_FP8_LO
+#define DS_FP8_LO 1
+#endif
+constexpr float DS_A_SCALE = DS_FP8_LO ? 256.f : 1.f;
+constexpr unsigned DS_B_EXP = DS_FP8_LO ? 7u : 13u;               // B is scaled to [2^DS_B_EXP, 2^(DS_B_EXP + 1))
+constexpr unsigned DS_UNSCALE_EXP = DS_FP8_LO ? 15u : 13u;        // log2 of the product of the two scalings
+constexpr float DS_UNSCALE_RAW = DS_FP8_LO ? 1.f / 256.f : 1.f;   // where B is not scaled (all-zero or non-finite pixels)
+
+__device__ __forceinline__ unsigned e4m3x2(const float lo, const float hi) {
+  return (unsigned)__nv_cvt_float2_to_fp8x2(make_float2(lo, hi), __NV_SATFINITE, __NV_E4M3);
+}
+__device__ __forceinline__ unsigned e4m3x2_h2(const unsigned h2) {
+  __half2_raw r;
+  r.x = (unsigned short)(h2 & 0xffffu);
+  r.y = (unsigned short)(h2 >> 16);
+  return (unsigned)__nv_cvt_halfraw2_to_fp8x2(r, __NV_SATFINITE, __NV_E4M3);
+}
+// A: second word of (first, second) = the K pair (cos, sin) of a column, given its fp16 word
+__device__ __forceinline__ unsigned second_word_a(const float first, const float second, const unsigned hi) {
+  const float r0 = residual_h(first, (unsigned short)(hi & 0xffffu)), r1 = residual_h(second, (unsigned short)(hi >> 16));
+#if DS_FP8_LO
+  return e4m3x2(r0, r1) | (e4m3x2_h2(hi) << 16);
+#else
+  return pack_h2(r0, r1);
+#endif
+}
+// B: second word given the fp16 word and the residuals of its two halves
+__device__ __forceinline__ unsigned second_word_b(const float r0, const float r1, const unsigned hi) {
+#if DS_FP8_LO
+  return e4m3x2_h2(hi) | (e4m3x2(r0, r1) << 16);
+#else
+  return pack_h2(r0, r1);
+#endif
+}
+// the cross products of one K step (2 chunks): lo hi + hi lo
+__device__ __forceinline__ void umma_cross(const unsigned d, const unsigned long long a_hi, const unsigned long long a_lo,
+                                           const unsigned long long b_hi, const unsigned long long b_lo, const unsigned idesc) {
+#if DS_FP8_LO
+  // the same instruction descriptor: format code 0 is F16 for kind::f16 and E4M3 for kind::f8f6f4
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, 1, 0;\n\t"
+               "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}"
+               ::"r"(d), "l"(a_lo), "l"(b_lo), "r"(idesc) : "memory");
+#else
+  umma_f16(d, a_lo, b_hi, idesc, 1u);
+  umma_f16(d, a_hi, b_lo, idesc, 1u);
+#endif
 }
 
 // 16 consecutive accumulator columns of the thread's TMEM lane.  Two of these, not one .x32: tools/tmem_ld.cu measures
@@ -238,9 +296,9 @@ degridder_sep_kernel(const KernelArgs a, const int tmem_cols, int *__restrict__ 
       if (tid == 0) {
         for (int i = 1; i < NW; i++) amax = fmaxf(amax, s_red[i]);
         const unsigned eb = (__float_as_uint(amax) >> 23) & 0xffu;
-        const bool ok = eb >= 14u && eb <= 253u;
-        s_red[16] = ok ? __uint_as_float((267u - eb) << 23) : 1.f;           // 2^(13 - E)
-        s_red[17] = ok ? __uint_as_float((eb - 13u) << 23) : 1.f;            // 2^(E - 13)
+        const bool ok = eb >= 16u && eb <= 253u;
+        s_red[16] = ok ? __uint_as_float((254u + DS_B_EXP - eb) << 23) : 1.f;           // 2^(DS_B_EXP - E)
+        s_red[17] = ok ? __uint_as_float((eb - DS_UNSCALE_EXP) << 23) : DS_UNSCALE_RAW;  // 2^(E - DS_UNSCALE_EXP)
       }
       __syncthreads();
       const float scale = s_red[16];
@@ -260,8 +318,8 @@ degridder_sep_kernel(const KernelArgs a, const int tmem_cols, int *__restrict__ 
           unsigned char *row = col + (2 * p) * 16;
           *reinterpret_cast<unsigned *>(row) = h_re;
           *reinterpret_cast<unsigned *>(row + 16) = h_im;
-          *reinterpret_cast<unsigned *>(row + KCp * b_ch) = pack_h2(r_re, -r_im);
-          *reinterpret_cast<unsigned *>(row + KCp * b_ch + 16) = pack_h2(r_im, r_re);
+          *reinterpret_cast<unsigned *>(row + KCp * b_ch) = second_word_b(r_re, -r_im, h_re);
+          *reinterpret_cast<unsigned *>(row + KCp * b_ch + 16) = second_word_b(r_im, r_re, h_im);
         }
       }
       __syncthreads();                    // the fp32 pixels have been read: the A buffer is free
@@ -301,6 +359,7 @@ degridder_sep_kernel(const KernelArgs a, const int tmem_cols, int *__restrict__ 
             float2 ph[8];
             if (lin) {   // first channel by sincos, second by one rotation, then the three-term recurrence
               ph[0] = phasor<IDGB200_SINCOS_FAST>(__fmaf_rn(idx, wn8[0], -off_x[xi]));
+              if (DS_FP8_LO) ph[0] = __fmul2_rn(ph[0], make_float2(DS_A_SCALE, DS_A_SCALE));
               const float2 d = phasor<IDGB200_SINCOS_FAST>(__fmul_rn(idx, dwc));
               ph[1] = ffma2(make_float2(ph[0].y, ph[0].x), make_float2(-d.y, d.y), __fmul2_rn(ph[0], make_float2(d.x, d.x)));
               const float c2 = __fadd_rn(d.x, d.x);
@@ -308,12 +367,15 @@ degridder_sep_kernel(const KernelArgs a, const int tmem_cols, int *__restrict__ 
               for (int i = 2; i < 8; i++) ph[i] = ffma2(ph[i - 1], make_float2(c2, c2), make_float2(-ph[i - 2].x, -ph[i - 2].y));
             } else {
 #pragma unroll
-              for (int i = 0; i < 8; i++) ph[i] = phasor<IDGB200_SINCOS_FAST>(__fmaf_rn(idx, wn8[i], -off_x[xi]));
+              for (int i = 0; i < 8; i++) {
+                ph[i] = phasor<IDGB200_SINCOS_FAST>(__fmaf_rn(idx, wn8[i], -off_x[xi]));
+                if (DS_FP8_LO) ph[i] = __fmul2_rn(ph[i], make_float2(DS_A_SCALE, DS_A_SCALE));
+              }
             }
 #pragma unroll
             for (int i = 0; i < 8; i++) {
               hi[i] = pack_h2(ph[i].x, ph[i].y);
-              lo[i] = pack_h2(residual_h(ph[i].x, (unsigned short)(hi[i] & 0xffffu)), residual_h(ph[i].y, (unsigned short)(hi[i] >> 16)));
+              lo[i] = second_word_a(ph[i].x, ph[i].y, hi[i]);
             }
           } else {
 #pragma unroll
@@ -344,8 +406,7 @@ degridder_sep_kernel(const KernelArgs a, const int tmem_cols, int *__restrict__ 
             const unsigned long long b_hi = smem_desc(b_u + 2 * ks * b_ch, b_ch, 128);
             const unsigned long long b_lo = smem_desc(b_u + (KCp + 2 * ks) * b_ch, b_ch, 128);
             umma_f16(tmem_base, a_hi, b_hi, idesc, ks > 0 ? 1u : 0u);
-            umma_f16(tmem_base, a_lo, b_hi, idesc, 1u);
-            umma_f16(tmem_base, a_hi, b_lo, idesc, 1u);
+            umma_cross(tmem_base, a_hi, a_lo, b_hi, b_lo, idesc);
           }
           umma_commit(mma_done);
         }
@@ -615,6 +676,7 @@ degridder_sep_pipe_kernel(const KernelArgs a, int *__restrict__ todo) {
               float2 ph[8];
               if (s_lin[cb]) {
                 ph[0] = phasor<IDGB200_SINCOS_FAST>(__fmaf_rn(idx, wn8[0], -off_x));
+                if (DS_FP8_LO) ph[0] = __fmul2_rn(ph[0], make_float2(DS_A_SCALE, DS_A_SCALE));
                 const float2 d = phasor<IDGB200_SINCOS_FAST>(__fmul_rn(idx, s_dw[cb]));
                 ph[1] = ffma2(make_float2(ph[0].y, ph[0].x), make_float2(-d.y, d.y), __fmul2_rn(ph[0], make_float2(d.x, d.x)));
                 const float c2 = __fadd_rn(d.x, d.x);
@@ -622,15 +684,17 @@ degridder_sep_pipe_kernel(const KernelArgs a, int *__restrict__ todo) {
                 for (int i = 2; i < 8; i++) ph[i] = ffma2(ph[i - 1], make_float2(c2, c2), make_float2(-ph[i - 2].x, -ph[i - 2].y));
               } else {
 #pragma unroll
-                for (int i = 0; i < 8; i++) ph[i] = phasor<IDGB200_SINCOS_FAST>(__fmaf_rn(idx, wn8[i], -off_x));
+                for (int i = 0; i < 8; i++) {
+                  ph[i] = phasor<IDGB200_SINCOS_FAST>(__fmaf_rn(idx, wn8[i], -off_x));
+                  if (DS_FP8_LO) ph[i] = __fmul2_rn(ph[i], make_float2(DS_A_SCALE, DS_A_SCALE));
+                }
               }
               if (lane < N) {
 #pragma unroll
                 for (int i = 0; i < 8; i++) {
                   const unsigned hi = pack_h2(ph[i].x, ph[i].y);
                   *reinterpret_cast<unsigned *>(row + i * 16) = hi;
-                  *reinterpret_cast<unsigned *>(row + i * 16 + KCp * DS_A_CH) =
-                      pack_h2(residual_h(ph[i].x, (unsigned short)(hi & 0xffffu)), residual_h(ph[i].y, (unsigned short)(hi >> 16)));
+                  *reinterpret_cast<unsigned *>(row + i * 16 + KCp * DS_A_CH) = second_word_a(ph[i].x, ph[i].y, hi);
                 }
               }
             } else if (lane < N) {     // rows beyond the subgrid's last block (the last tile only): zeros
@@ -786,8 +850,7 @@ degridder_sep_pipe_kernel(const KernelArgs a, int *__restrict__ todo) {
               const unsigned long long b_hi = smem_desc(b_b + 2 * ks * b_ch, b_ch, 128);
               const unsigned long long b_lo = smem_desc(b_b + (KCp + 2 * ks) * b_ch, b_ch, 128);
               umma_f16(d_t, a_hi, b_hi, idesc, ks > 0 ? 1u : 0u);
-              umma_f16(d_t, a_lo, b_hi, idesc, 1u);
-              umma_f16(d_t, a_hi, b_lo, idesc, 1u);
+              umma_cross(d_t, a_hi, a_lo, b_hi, b_lo, idesc);
             }
             umma_commit_u(bar_at(MMA_DONE, buf));
           }
@@ -906,8 +969,8 @@ degridder_sep_pipe_kernel(const KernelArgs a, int *__restrict__ todo) {
       if (!sep && ts == 0) todo[1 + atomicAdd(&todo[0], 1)] = s_local;   // work list of the per-pixel kernel
       const bool run = sep && nt > 0;
       const unsigned eb = (__float_as_uint(amax) >> 23) & 0xffu;
-      const bool ok = eb >= 14u && eb <= 253u;
-      const float scale = ok ? __uint_as_float((267u - eb) << 23) : 1.f;           // 2^(13 - E)
+      const bool ok = eb >= 16u && eb <= 253u;
+      const float scale = ok ? __uint_as_float((254u + DS_B_EXP - eb) << 23) : 1.f;   // 2^(DS_B_EXP - E)
       if (run && !((IDGB200_ABLATE & 16) && !ablate_never())) {     // ablation: no B operand
         unsigned char *sBb = sB + bb * b_buf;
 #pragma unroll 2
@@ -928,8 +991,8 @@ degridder_sep_pipe_kernel(const KernelArgs a, int *__restrict__ todo) {
             unsigned char *row = col + (2 * p) * 16;
             *reinterpret_cast<unsigned *>(row) = h_re;
             *reinterpret_cast<unsigned *>(row + 16) = h_im;
-            *reinterpret_cast<unsigned *>(row + KCp * b_ch) = pack_h2(r_re, -r_im);
-            *reinterpret_cast<unsigned *>(row + KCp * b_ch + 16) = pack_h2(r_im, r_re);
+            *reinterpret_cast<unsigned *>(row + KCp * b_ch) = second_word_b(r_re, -r_im, h_re);
+            *reinterpret_cast<unsigned *>(row + KCp * b_ch + 16) = second_word_b(r_im, r_re, h_im);
           }
         }
         if (ts < N) {
@@ -945,7 +1008,7 @@ degridder_sep_pipe_kernel(const KernelArgs a, int *__restrict__ todo) {
         m.time_offset = ctx.time_offset;
         m.u_offset = ctx.u_offset;
         m.w_offset = ctx.w_offset;
-        m.unscale = ok ? __uint_as_float((eb - 13u) << 23) : 1.f;                  // 2^(E - 13)
+        m.unscale = ok ? __uint_as_float((eb - DS_UNSCALE_EXP) << 23) : DS_UNSCALE_RAW;   // 2^(E - DS_UNSCALE_EXP)
         m.pad = 0;
         meta[bb] = m;
       }
