@@ -1,6 +1,6 @@
 """CPU prototype of the row-column (separable) formulation of the IDG gridder / degridder
 (csrc/gridder_sep.cu, degridder_sep.cu).  Test infrastructure: numpy, float64
-containers with the kernels' fp32 phase arithmetic and fp16 operand roundings emulated.
+containers with the kernels' fp32 phase arithmetic and fp16 / e4m3 operand roundings emulated.
 
     phase(y, x, v) = phase_y(y, v) + phase_x(x, v) + gamma_v * r(y, x)
     phase_x = (u_off l_x + w_off nx_x) - (u l_x + w nx_x) k_c ,  nx_x = f(l_x^2),  f(s) = s / (1 + sqrt(1 - s))
@@ -71,6 +71,19 @@ def scaled16(z, split):
     return hi / sc
 
 
+def e4m3(v):
+    """round to e4m3 (4 significant bits, normal from 2^-6, subnormal step 2^-9, saturating at 448), half to even"""
+    v = np.asarray(v, np.float64)
+    a = np.abs(v)
+    e = np.maximum(np.floor(np.log2(np.where(a > 0, a, 1.0))), -6.0)
+    step = 2.0 ** (e - 3)
+    return np.sign(v) * np.minimum(np.round(a / step) * step, 448.0)
+
+
+def c8(z):
+    return e4m3(z.real) + 1j * e4m3(z.imag)
+
+
 def aterm_g(p, s, pix):
     m = p.metadata[s]
     a1 = p.aterms[m["aterm_index"], m["station1"]].astype(np.complex128).reshape(p.subgrid_size, p.subgrid_size, 2, 2)
@@ -105,14 +118,29 @@ def gridder_sep(p, emulate=True):
 
 
 def degridder_sep(p, emulate=True):
+    """emulate: False = exact operands, "f16x3" = fp16 hi + lo on both operands and three products (hi hi, lo hi, hi lo:
+    round 2's first form), "f16x1" = one fp16 product, True / "fp8" = what degridder_sep.cu does: hi hi in fp16 and the two
+    cross products as one e4m3 MMA, A scaled by 2^8 and B to [2^7, 2^8) so that both parts sit in e4m3's range"""
     out = np.zeros((p.total_timesteps, p.nr_channels, 4), np.complex128)
     for s in range(p.nr_subgrids):
         X, Y, t0, nt = half_phasors(p, s, -1)
         P = aterm_d(p, s)                                                # [y][x][pol]
-        if emulate:
-            P = scaled16(P.astype(np.complex64).astype(np.complex128), split=True)
-            X = r16(X) + r16(X - r16(X))
-        Q = np.einsum("tcx,yxp->tcyp", X, P)                             # tensor core, fp32 accumulate
+        if emulate in (True, "fp8"):
+            P = P.astype(np.complex64).astype(np.complex128)
+            a = np.abs(np.concatenate([P.real.ravel(), P.imag.ravel()])).max() if P.size else 0.0
+            sc = 2.0 ** (7 - np.floor(np.log2(a))) if a > 0 else 1.0
+            B, A = P * sc, X * 256.0
+            Bh, Ah = r16(B), r16(A)
+            Q = (np.einsum("tcx,yxp->tcyp", Ah, Bh) + np.einsum("tcx,yxp->tcyp", c8(A - Ah), c8(Bh)) +
+                 np.einsum("tcx,yxp->tcyp", c8(Ah), c8(B - Bh))) / (sc * 256.0)
+        else:
+            if emulate == "f16x3":
+                P = scaled16(P.astype(np.complex64).astype(np.complex128), split=True)
+                X = r16(X) + r16(X - r16(X))
+            elif emulate == "f16x1":
+                P = scaled16(P.astype(np.complex64).astype(np.complex128), split=False)
+                X = r16(X)
+            Q = np.einsum("tcx,yxp->tcyp", X, P)                         # tensor core, fp32 accumulate
         if emulate:
             Q = Q.astype(np.complex64).astype(np.complex128)
         out[t0:t0 + nt] = np.einsum("tcy,tcyp->tcp", Y, Q)
@@ -138,16 +166,16 @@ def main():
     for name, p in cases:
         g32, g64 = o.gridder(p), o.gridder_f64(p)
         d32, d64 = o.degridder(p), o.degridder_f64(p)
+        cov = np.zeros(p.total_timesteps, bool)      # degridder: only rows some subgrid covers
+        for s in range(p.nr_subgrids):
+            _, _, _, t0, nt = ctx(p, s)
+            cov[t0:t0 + nt] = True
         for emu in (False, True):
             tag = "fp16 operands" if emu else "exact operands"
             report(f"{name} gridder {tag}", gridder_sep(p, emu), g32, g64)
-            # degridder: only rows some subgrid covers
-            got = degridder_sep(p, emu)
-            cov = np.zeros(p.total_timesteps, bool)
-            for s in range(p.nr_subgrids):
-                _, _, _, t0, nt = ctx(p, s)
-                cov[t0:t0 + nt] = True
-            report(f"{name} degridder {tag}", got[cov], d32[cov], d64[cov])
+        for emu, tag in ((False, "exact operands"), ("f16x1", "one fp16 product"), ("f16x3", "three fp16 products"),
+                         ("fp8", "fp16 + e4m3 cross products")):
+            report(f"{name} degridder {tag}", degridder_sep(p, emu)[cov], d32[cov], d64[cov])
 
 
 if __name__ == "__main__":
