@@ -714,7 +714,7 @@ def run_ours(args) -> None:
             "unit": "MVis/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": top["ms_per_step"], "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None,
-            "dtype": "f32 phasors and accumulation; fp16 (hi + lo where stated) tcgen05 operands" if g_variant >= 20 else "f32",
+            "dtype": "f32 phasors and accumulation; fp16 (+ fp16 / e4m3 error-compensation parts where stated) tcgen05 operands" if g_variant >= 20 else "f32",
             "data": "synthetic",
             "config": dict(workload_config(shape, world), sincos=args.sincos,
                            gridder_variant=g_variant, degridder_variant=d_variant,
@@ -726,8 +726,8 @@ def run_ours(args) -> None:
                            gridder_kernel="gridder_sep.cu: row-column form, one tcgen05 GEMM per subgrid with the visibilities as K "
                                           "(A = fp16(Y vis), B = fp16 hi + lo column phasors), per-subgrid separability check on the "
                                           "device, per-pixel kernel behind it" if g_variant == 30 else f"variant {g_variant}",
-                           degridder_kernel="degridder_sep.cu: row-column form, tcgen05 GEMM over the columns (fp16 hi + lo both "
-                                            "operands), the sum over the rows on the CUDA cores out of TMEM; persistent warp-specialised pipeline, one CTA "
+                           degridder_kernel="degridder_sep.cu: row-column form, tcgen05 GEMM over the columns (hi hi in fp16, the "
+                                            "two cross products as one e4m3 MMA), the sum over the rows on the CUDA cores out of TMEM; persistent warp-specialised pipeline, one CTA "
                                             "per SM (producers / issuer / consumers / next-subgrid setup)" if d_variant == 30
                                             else f"variant {d_variant}"),
             "tflops": top["tflops"], "step_ms": top["step_ms"], "timed_steps": top["timed_steps"], "rounds": top["rounds"],
