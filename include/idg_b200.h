@@ -187,11 +187,14 @@ int idgb200_subgrid_fft(int64_t nr_subgrids, int subgrid_size, int direction,
 
 /* The kernel variant params->variant == 0 resolves to for this shape and sincos
  * mode (gridder != 0: the gridder, else the degridder); a non-zero variant is
- * returned unchanged.  Gridder: 29 / 24 / 21 = tcgen05 kernel (FAST sincos, shapes that fill
- * its tiles; 29 = 24 with planar launches - every w = 0, checked on the device - gridded
- * per mirror-image pixel pair), 10 = FP32 kernel.  Degridder: 24 / 22 = tcgen05 kernel with
- * fp16 hi + lo phasors (FAST sincos; 24 sums planar subgrids over pixel pairs, 28 = 24
- * without that), 4 = FP32 kernel.  IDGB200_EINVAL on bad params. */
+ * returned unchanged.  FAST sincos: 30 = the row-column tcgen05 kernels (gridder:
+ * subgrid sizes that are a multiple of 4; degridder: up to 64 x 64 pixels), which
+ * leave subgrids whose phase does not separate - and, for the gridder, subgrids
+ * whose sums cancel below the fp16 operand's error model - to the per-pixel / FP32
+ * kernel launched behind them on the same stream; other FAST shapes: gridder
+ * 24 / 21, degridder 24 / 22 = the per-pixel tcgen05 kernels where the shape fills
+ * their tiles.  Other sincos modes and remaining shapes: gridder 10, degridder 4 =
+ * the FP32 kernels.  IDGB200_EINVAL on bad params. */
 int idgb200_resolve_variant(const idgb200_params *params, int gridder);
 
 /* ---- host-pointer API --------------------------------------------------------

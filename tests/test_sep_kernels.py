@@ -252,6 +252,39 @@ def test_degridder_sep_config1():
     assert e_gpu <= 2 * e_cpu + 2e-5
 
 
+@pytest.mark.parametrize("variant", [31, 32])
+def test_degridder_sep_operand_scaling(variant):
+    """The B operand (P') is scaled per subgrid by a power of two into the range of its fp16 and e4m3 parts
+    (degridder_sep.cu: DS_B_EXP), the A operand by 2^8.  The degridder is linear in a subgrid, so
+    (a) a power-of-two factor on a subgrid's pixels comes back as exactly that factor on its visibilities, whatever
+        the magnitude (2^-100 .. 2^100) and different for every subgrid of a launch,
+    (b) a subgrid of zeros gives zeros (no scale), next to scaled ones,
+    (c) one pixel 10^6 times larger than the rest (most pixels then sit in the subnormal steps of the 8-bit parts)
+        stays inside the tolerance, which is relative to the largest visibility."""
+    o = oracle()
+    p = with_linear_channels(random_problem(216, subgrid_size=32, nr_channels=16, max_timesteps=24, nr_subgrids=6))
+    base = run_degridder(p, FAST, variant)
+    exps = [0, -100, 100, 37, -61, None]             # None: the subgrid of zeros
+    q = with_linear_channels(random_problem(216, subgrid_size=32, nr_channels=16, max_timesteps=24, nr_subgrids=6))
+    for s, e in enumerate(exps):
+        q.subgrids[s] = 0 if e is None else p.subgrids[s] * np.float32(2.0) ** e
+    got = run_degridder(q, FAST, variant)
+    for s, e in enumerate(exps):
+        t0, nt = int(p.metadata[s]["time_offset"]), int(p.metadata[s]["nr_timesteps"])
+        rows = slice(t0, t0 + nt)      # random_problem: one baseline, time_offset counts from the start of uvw
+        if e is None:
+            assert not got[rows].any()
+        else:
+            want = (base[rows].astype(np.float64) * 2.0 ** e).astype(np.float32)
+            assert np.array_equal(got[rows].view(np.float32), want.view(np.float32)), (s, e)
+    # (c) dynamic range inside one subgrid
+    r = with_linear_channels(random_problem(217, subgrid_size=32, nr_channels=16, max_timesteps=24, nr_subgrids=3))
+    r.subgrids[1, :, 13, 21] *= 1e6
+    ref = o.degridder(r)
+    rows = covered_rows(r)
+    assert_close(run_degridder(r, FAST, variant)[rows], ref[rows], 2, FAST, "degridder sep, one pixel 1e6 x the rest")
+
+
 # ---------------------------------------------------------- degridder: the pipelined persistent kernel (variant 32)
 PIPE, CLASSIC = 32, 31
 
