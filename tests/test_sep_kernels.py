@@ -275,7 +275,7 @@ def test_degridder_sep_operand_scaling(variant):
         if e is None:
             assert not got[rows].any()
         else:
-            want = (base[rows].astype(np.float64) * 2.0 ** e).astype(np.float32)
+            want = (base[rows].astype(np.complex128) * 2.0 ** e).astype(np.complex64)
             assert np.array_equal(got[rows].view(np.float32), want.view(np.float32)), (s, e)
     # (c) dynamic range inside one subgrid
     r = with_linear_channels(random_problem(217, subgrid_size=32, nr_channels=16, max_timesteps=24, nr_subgrids=3))
