@@ -10,9 +10,10 @@
 //   Q[v][(y, p, re|im)] = A[v][(x, cos|sin)] * B[(x, cos|sin)][(y, p, re|im)]      M = 128, K = 2 N, N = 8 N
 //     A = X in fp16 hi + lo (32 phasors per visibility instead of 1024: three-term recurrence over equally
 //         spaced channels, else one sincos per channel),
-//     B = P' in fp16 hi + lo, built once per subgrid (power-of-two scaling into fp16 range),
-//     three products per K step (hi hi, lo hi, hi lo): the operands keep ~22 bits, which the reference's
-//     smooth degridder input needs (its visibilities are small sums of large terms: DESIGN.md 4.6),
+//     B = P' in fp16 hi + lo, built once per subgrid (power-of-two scaling into the range of the parts),
+//     an error-compensated product per K step: hi hi as an fp16 MMA, the two cross products lo hi + hi lo as ONE e4m3
+//     MMA (DS_FP8_LO below): the reference's smooth degridder input needs more than fp16's 11 bits on both
+//     operands (its visibilities are small sums of large terms: DESIGN.md 4.6),
 // and the outer sum runs on the CUDA cores straight out of TMEM: thread = visibility (TMEM lane = row), one
 // sincos per (visibility, row y), four complex multiply-adds, then one coalesced 32-byte store per visibility:
 // every visibility of the subgrid's time range is written exactly once.
@@ -487,11 +488,11 @@ degridder_sep_kernel(const KernelArgs a, const int tmem_cols, int *__restrict__ 
 
 // ---------------------------------------------------------------------------------------------------------------------
 // The same arithmetic as a warp-specialised, persistent pipeline: ONE CTA per SM that loops over subgrids, 20 warps.
-//   warps  0- 7  producers: the A rows (column phasors X, fp16 hi + lo) of tile i + 1 / i + 2 into one of two A buffers
+//   warps  0- 7  producers: the A rows (column phasors X, fp16 + e4m3 parts) of tile i + 1 / i + 2 into one of two A buffers
 //   warps  8-15  consumers: the sum over the rows y of tile i out of one of two accumulators (all 512 TMEM columns);
 //                two warps per TMEM lane quadrant, half of the rows each
-//   warp   16    issuer: the tile's 12 MMAs as soon as its A buffer is full and its accumulator has been drained
-//   warps 17-19  setup: the NEXT subgrid's separability check, B operand (P' in fp16 hi + lo, one of two B buffers),
+//   warp   16    issuer: the tile's 8 MMAs as soon as its A buffer is full and its accumulator has been drained
+//   warps 17-19  setup: the NEXT subgrid's separability check, B operand (P' in fp16 + e4m3 parts, one of two B buffers),
 //                staged uvw and row geometry, while the others are in the tile loop of the current subgrid
 // so that the tensor pipe, the producers' dependency chains and the consumers' TMEM reads overlap inside one CTA
 // instead of across two (the kernel above: a tile's phases one after the other, 2 CTAs per SM), and the per-subgrid
