@@ -298,7 +298,7 @@ gridder_sep_kernel(const KernelArgs a, const int ytiles, const int xtiles, const
       if (j >= 2) mbar_wait_u(empty_u + buf * 8, ((j >> 1) - 1) & 1);
 
       unsigned char *A = my_stage + buf * GS_A_BYTES, *B = my_stage + 2 * GS_A_BYTES;
-      {
+      if (!((IDGB200_ABLATE & 4) && !ablate_never())) {       // ablation builds (tools/power_probe.py): no A rows
         // ---- A rows (p, y): fp16 of scale * Y_c(y) * vis[c][p]
         const float4 *vs = reinterpret_cast<const float4 *>(my_vis + (j & (GS_VSLOTS - 1)) * 256);
 #pragma unroll
@@ -325,6 +325,7 @@ gridder_sep_kernel(const KernelArgs a, const int ytiles, const int xtiles, const
       if (j >= 1) mbar_wait_u(empty_u + (buf ^ 1) * 8, ((j - 1) >> 1) & 1);   // the previous stage's MMA has read B
 #pragma unroll
       for (int xi = 0; xi < XPL; xi++) {
+        if ((IDGB200_ABLATE & 8) && !ablate_never()) continue;     // ablation: no B rows
         // ---- B rows of column x: (hi|lo, re|im) x XT; re row = (cos, -sin), im row = (sin, cos) per visibility
         const int xx = lane + 32 * xi;
 #pragma unroll
@@ -397,8 +398,9 @@ gridder_sep_kernel(const KernelArgs a, const int ytiles, const int xtiles, const
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         if (elect_one()) {
           const unsigned w_addr = stage_u + pw * warp_bytes;
-          umma_f16(tmem_base, smem_desc(w_addr + buf * GS_A_BYTES, 128 * 16, 128), smem_desc(w_addr + 2 * GS_A_BYTES, 4 * XT * 16, 128), idesc,
-                   sidx > 0 ? 1u : 0u);
+          if (!((IDGB200_ABLATE & 1) && !ablate_never()))       // ablation: no MMAs
+            umma_f16(tmem_base, smem_desc(w_addr + buf * GS_A_BYTES, 128 * 16, 128), smem_desc(w_addr + 2 * GS_A_BYTES, 4 * XT * 16, 128), idesc,
+                     sidx > 0 ? 1u : 0u);
           umma_commit_u(empty_u + (pw * 2 + buf) * 8);
           if (sidx == nstages - 1) umma_commit_u(done_u);
         }

@@ -2,10 +2,10 @@
 # Ablation builds (tools/ablate.py times them; never shipped): libidgb200_ablateN.so = the library with
 # the kernels named in KERNELS (default: the pipelined row-column degridder's file) compiled with -DIDGB200_ABLATE=N,
 # every other object as the Makefile built it (untuned objects: N = 0 is the like-for-like baseline).
-#   bit 0 (1)  no MMAs                                   (gridder_tc.cu, degridder_tc8.cu, degridder_sep.cu pipeline)
+#   bit 0 (1)  no MMAs                                   (gridder_tc.cu, degridder_tc8.cu, gridder_sep.cu, degridder_sep.cu pipeline)
 #   bit 1 (2)  operand stores predicated off at run time (gridder_tc.cu, degridder_tc8.cu)
-#   bit 2 (4)  consumers skip the sum over the rows      (degridder_sep.cu pipeline)
-#   bit 3 (8)  producers skip the A rows                 (degridder_sep.cu pipeline)
+#   bit 2 (4)  consumers skip the sum over the rows      (degridder_sep.cu pipeline); producers skip the A rows (gridder_sep.cu)
+#   bit 3 (8)  producers skip the A rows                 (degridder_sep.cu pipeline); the B rows (gridder_sep.cu)
 #   bit 4 (16) setup warps skip the B operand            (degridder_sep.cu pipeline)
 set -e
 cd "$(dirname "$0")/.."

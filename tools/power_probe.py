@@ -1,5 +1,5 @@
 """Board power and SM clock of the row-column kernels under sustained load, per ablation build (tools/build_ablate.sh):
-NR_ITERATIONS launches (default 300, > 1 s) through each library's idgb200_p_run_*, nvidia-smi sampled every 100 ms
+NR_ITERATIONS launches (default 600, ~3 s) through each library's idgb200_p_run_*, nvidia-smi sampled every 100 ms
 meanwhile.  Energy per launch = median power x time per launch: both kernels sit at the 1 kW cap, so what a role costs in
 JOULES is what it costs in time.  Usage: python tools/power_probe.py [0,1,4,8] [gridder|degridder ...]"""
 import ctypes as C
@@ -29,7 +29,7 @@ class Sampler:
 
     def between(self, i0, i1):
         v = []
-        for ln in self.lines[i0 + 3:i1]:        # the first samples of a region see the ramp
+        for ln in self.lines[i0 + 2 * (i1 - i0) // 3:i1]:     # the last third of the region: nvidia-smi's power is a ~1 s average
             try:
                 c, p = (float(x) for x in ln.split(","))
                 v.append((c, p))
@@ -41,7 +41,7 @@ class Sampler:
 
 
 def main():
-    os.environ.setdefault("NR_ITERATIONS", "300")
+    os.environ.setdefault("NR_ITERATIONS", "600")
     os.environ["IDGB200_SINCOS"] = "0"
     os.environ["IDGB200_VARIANT"] = "0"
     os.environ.setdefault("IDGB200_ENERGY_SECONDS", "0")
