@@ -451,7 +451,8 @@ gridder_sep_kernel(const KernelArgs a, const int ytiles, const int xtiles, const
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (tid == 0 && nstages > 0 && s_red[40] + s_red[41] + s_red[42] + s_red[43] == 4.f &&
+  if (!IDGB200_ABLATE &&              // (an ablated kernel's sums are garbage: no redo behind it)
+      tid == 0 && nstages > 0 && s_red[40] + s_red[41] + s_red[42] + s_red[43] == 4.f &&
       s_red[16] + s_red[17] + s_red[18] + s_red[19] > 0.f &&
       atomicAdd(&cancel_tiles[s_local], 1) == tiles - 1)            // the last of the subgrid's tiles to say so
     cancel[1 + atomicAdd(&cancel[0], 1)] = s_local;                  // work list of the FP32 kernel
