@@ -742,6 +742,9 @@ def run_ours(args) -> None:
             "reference_gpu": ref_gpu,
             "cpu_baseline": cpu_baseline, "parity": parity, "e2e": e2e, "next_rows": next_rows, "adder_rs": adder_rs,
             "gpu_launches": int(round(t_g["launches_per_step"] * args.steps)),
+            # (kernels per `steps` steps: the row-column gridder + the two list-mode kernels behind it; the whole timed region,
+            # `rounds` x `steps` steps, launched gpu_launches_in_timed_region)
+            "gpu_launches_in_timed_region": int(round(t_g["launches_per_step"] * t_g["timed_steps"])),
             "clocks": clocks, "device": idg.device_name(),
         }
         emit(out)
