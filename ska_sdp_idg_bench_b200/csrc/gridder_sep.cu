@@ -83,32 +83,21 @@ __device__ __forceinline__ void mbar_wait_sleep(const unsigned bar, const unsign
 }
 
 // XPL: columns per lane (1: tiles of <= 32 columns, 2: of 33..64)
-// SHAPE: 0 = any shape; 2 / 8 = subgrids of 32 x 32 pixels (one full tile) with exactly 16 / 64 channels (2 / 8 whole channel
-// blocks): tile extents, operand row offsets and the stage cursor's steps are compile-time constants there (~50 instructions
-// of a stage's ~430), at 3 CTAs per SM so that the registers this takes are there
-#ifndef GS_SPEC
-#define GS_SPEC 1
-#endif
-#ifndef GS_SPEC_CTAS
-#define GS_SPEC_CTAS 3
-#endif
-template <int XPL, int SHAPE>
-__global__ void __launch_bounds__(GS_THREADS, SHAPE != 0 ? GS_SPEC_CTAS : XPL == 1 ? 4 : 2)
-gridder_sep_kernel(const KernelArgs a, const int ytiles_, const int xtiles_, const int tmem_cols, int *__restrict__ todo,
+template <int XPL>
+__global__ void __launch_bounds__(GS_THREADS, XPL == 1 ? 4 : 2)
+gridder_sep_kernel(const KernelArgs a, const int ytiles, const int xtiles, const int tmem_cols, int *__restrict__ todo,
                    int *__restrict__ cancel, int *__restrict__ cancel_tiles) {
   extern __shared__ __align__(1024) unsigned char smem[];
-  constexpr bool SP = SHAPE != 0;
-  const int N = SP ? 32 : a.subgrid_size, C = SP ? SHAPE * GS_CB : a.nr_channels;
-  const int ytiles = SP ? 1 : ytiles_, xtiles = SP ? 1 : xtiles_;
+  const int N = a.subgrid_size, C = a.nr_channels;
   const int tiles = ytiles * xtiles;
-  const int s_local = SP ? (int)blockIdx.x : (int)blockIdx.x / tiles, tile = SP ? 0 : (int)blockIdx.x - s_local * tiles;
-  const int ytile = SP ? 0 : tile / xtiles, xtile = SP ? 0 : tile - ytile * xtiles;
-  const int y0 = ytile * 32, ny = SP ? 32 : min(32, N - y0);
-  const int x0 = xtile * 64, XT = SP ? 32 : min(64, N - x0);       // XT % 4 == 0 (the launcher's condition)
+  const int s_local = blockIdx.x / tiles, tile = blockIdx.x - s_local * tiles;
+  const int ytile = tile / xtiles, xtile = tile - ytile * xtiles;
+  const int y0 = ytile * 32, ny = min(32, N - y0);
+  const int x0 = xtile * 64, XT = min(64, N - x0);       // XT % 4 == 0 (the launcher's condition)
   const int s = a.subgrid_offset + s_local;
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
-  const int ncb = SP ? SHAPE : (C + GS_CB - 1) / GS_CB;
+  const int ncb = (C + GS_CB - 1) / GS_CB;
   const int b_bytes = 4 * XT * 32;                        // B: 4 XT rows x 16 fp16
   // per producer warp: two A buffers and ONE B buffer (of the kernel's largest tile).  A stage's A rows are most of its
   // work, so by the time a warp turns to the B rows the MMA of its previous stage - the last reader of B - has long
@@ -515,8 +504,7 @@ cudaError_t launch_gridder_sep(const KernelArgs &a, int *d_todo, int *d_cancel, 
   const int ncb = (a.nr_channels + GS_CB - 1) / GS_CB;
   const size_t warp_bytes = 2 * GS_A_BYTES + (wide ? 4 * 64 * 32 : 4 * 32 * 32);
   const size_t smem = GS_W * warp_bytes + GS_W * GS_VSLOTS * 256 + (4 * GS_W + 1) * 8 + 8 + 192 + (size_t)ncb * (GS_CB + 2) * 4;
-  const int shape = !GS_SPEC || N != 32 ? 0 : a.nr_channels == 16 ? 2 : a.nr_channels == 64 ? 8 : 0;
-  auto k = wide ? gridder_sep_kernel<2, 0> : shape == 2 ? gridder_sep_kernel<1, 2> : shape == 8 ? gridder_sep_kernel<1, 8> : gridder_sep_kernel<1, 0>;
+  auto k = wide ? gridder_sep_kernel<2> : gridder_sep_kernel<1>;
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   k<<<dim3((unsigned)a.nr_subgrids * ytiles * xtiles), dim3(GS_THREADS), smem, stream>>>(a, ytiles, xtiles, tmem_cols, d_todo, d_cancel, d_cancel_tiles);
